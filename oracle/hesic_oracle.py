@@ -1,0 +1,418 @@
+"""CPU oracle for the HESIC / HESIC+ stereo forward path.  TEST INFRASTRUCTURE ONLY.
+
+A functional restatement, in plain torch-CPU fp32, of what the reference's
+``HSIC.forward`` computes, written against a ``state_dict`` with the
+reference's key names.  It is the checker for the CUDA path; nothing in the
+product (``hesic_b200/``) imports it.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl
+reference`` legs may use it.
+
+Pinning: ``tests/golden/make_golden.py`` imports the *reference itself* from
+/root/reference (in the build container) and stores its outputs; the CPU test
+suite checks every function here against those fixtures.  One input of the
+path is NOT pinned by the reference: ``kornia.warp_perspective`` is an
+un-vendored, un-pinned third-party dependency, so
+``warp_perspective`` below restates kornia's published algorithm
+(``align_corners=True`` convention) and the goldens were produced with that
+same restatement standing in for kornia: **warp parity is unpinned**.
+
+Every function cites the reference file:line it follows (paths relative to
+/root/reference).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+REPARAM_OFFSET = 2.0 ** -18
+
+
+# ----------------------------------------------------------------------------
+# compressai/ops/parametrizers.py:21-44, bound_ops.py:19-52
+def nonneg_reparam(p, minimum=0.0):
+    pedestal = REPARAM_OFFSET ** 2
+    bound = (minimum + pedestal) ** 0.5
+    out = torch.max(p, torch.tensor([bound], dtype=p.dtype))
+    return out ** 2 - torch.tensor([pedestal], dtype=p.dtype)
+
+
+# compressai/layers/gdn.py:55-70
+def gdn(x, beta_p, gamma_p, inverse=False, beta_min=1e-6):
+    C = x.shape[1]
+    beta = nonneg_reparam(beta_p, beta_min)
+    gamma = nonneg_reparam(gamma_p, 0.0).reshape(C, C, 1, 1)
+    norm = F.conv2d(x ** 2, gamma, beta)
+    norm = torch.sqrt(norm) if inverse else torch.rsqrt(norm)
+    return x * norm
+
+
+# compressai/models/utils.py:104-118
+def conv(x, w, b, stride=2, k=None):
+    k = w.shape[-1] if k is None else k
+    return F.conv2d(x, w, b, stride=stride, padding=k // 2)
+
+
+def deconv(x, w, b, stride=2):
+    k = w.shape[-1]
+    return F.conv_transpose2d(x, w, b, stride=stride, padding=k // 2, output_padding=stride - 1)
+
+
+# ----------------------------------------------------------------------------
+# kornia.warp_perspective (third-party, un-vendored; call sites newnet1.py:746,753,767)
+def _normal_transform_pixel(h, w):
+    return torch.tensor([[2.0 / (w - 1), 0.0, -1.0], [0.0, 2.0 / (h - 1), -1.0], [0.0, 0.0, 1.0]])
+
+
+def warp_perspective(src, M, dsize, align_corners=True):
+    B, _, H, W = src.shape
+    h_out, w_out = dsize
+    src_norm = _normal_transform_pixel(H, W)[None]
+    dst_norm = _normal_transform_pixel(h_out, w_out)[None]
+    dst_norm_trans_src_norm = dst_norm @ (M.float() @ torch.inverse(src_norm))
+    src_norm_trans_dst_norm = torch.inverse(dst_norm_trans_src_norm)
+    xs = torch.linspace(-1, 1, w_out)
+    ys = torch.linspace(-1, 1, h_out)
+    gx, gy = torch.meshgrid(xs, ys, indexing="xy")  # [h_out, w_out]
+    pts = torch.stack((gx, gy, torch.ones_like(gx)), dim=-1)  # [h,w,3]
+    p = pts[None] @ src_norm_trans_dst_norm[:, None].transpose(-1, -2)  # [B,h,w,3]
+    z = p[..., 2:3]
+    scale = torch.where(z.abs() > 1e-8, 1.0 / z, torch.ones_like(z))
+    grid = scale * p[..., :2]
+    return F.grid_sample(src, grid, mode="bilinear", padding_mode="zeros", align_corners=align_corners)
+
+
+# ----------------------------------------------------------------------------
+# compressai/entropy_models/entropy_models.py:98-125
+def quantize(x, mode, means=None):
+    if mode not in ("dequantize", "symbols"):
+        raise ValueError(f'Invalid quantization mode: "{mode}"')
+    out = x.clone()
+    if means is not None:
+        out = out - means
+    out = torch.round(out)
+    if mode == "dequantize":
+        if means is not None:
+            out = out + means
+        return out
+    return out.int()
+
+
+# entropy_models.py:350-369
+def eb_logits_cumulative(v, matrices, biases, factors):
+    logits = v
+    for i in range(len(matrices)):
+        logits = torch.matmul(F.softplus(matrices[i]), logits)
+        logits = logits + biases[i]
+        if i < len(factors):
+            logits = logits + torch.tanh(factors[i]) * torch.tanh(logits)
+    return logits
+
+
+def eb_params(sd, prefix):
+    mats = [sd[f"{prefix}._matrices.{i}"] for i in range(5)]
+    bias = [sd[f"{prefix}._biases.{i}"] for i in range(5)]
+    fac = [sd[f"{prefix}._factors.{i}"] for i in range(4)]
+    return mats, bias, fac, sd[f"{prefix}.quantiles"]
+
+
+# entropy_models.py:384-411 (eval mode), :371-382
+def entropy_bottleneck(x, mats, bias, fac, quantiles, likelihood_bound=1e-9):
+    xp = x.permute(1, 2, 3, 0).contiguous()
+    shape = xp.shape
+    values = xp.reshape(xp.size(0), 1, -1)
+    medians = quantiles[:, :, 1:2]
+    outputs = quantize(values, "dequantize", medians)
+    lower = eb_logits_cumulative(outputs - 0.5, mats, bias, fac)
+    upper = eb_logits_cumulative(outputs + 0.5, mats, bias, fac)
+    sign = -torch.sign(lower + upper)
+    lik = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+    if likelihood_bound > 0:
+        lik = torch.max(lik, torch.tensor([likelihood_bound]))
+    outputs = outputs.reshape(shape).permute(3, 0, 1, 2).contiguous()
+    lik = lik.reshape(shape).permute(3, 0, 1, 2).contiguous()
+    return outputs, lik
+
+
+# entropy_models.py:615-620
+def std_cumulative(x):
+    return 0.5 * torch.erfc(float(-(2 ** -0.5)) * x)
+
+
+# entropy_models.py:661-702 (GaussianMixtureConditional, eval; quantises with means=None :697)
+def gmm_conditional(y, scales, means, weights, K, scale_bound=0.11, likelihood_bound=1e-9):
+    y_hat = torch.round(y)
+    M = y.shape[1]
+    lik = None
+    for k in range(K):
+        sl = slice(M * k, M * (k + 1))
+        values = torch.abs(y_hat - means[:, sl])
+        s = torch.max(scales[:, sl], torch.tensor([scale_bound]))
+        upper = std_cumulative((0.5 - values) / s)
+        lower = std_cumulative((-0.5 - values) / s)
+        term = (upper - lower) * weights[:, sl]
+        lik = term if lik is None else lik + term
+    if likelihood_bound > 0:
+        lik = torch.max(lik, torch.tensor([likelihood_bound]))
+    return y_hat, lik
+
+
+# entropy_models.py:528-554 (GaussianConditional, eval)
+def gaussian_conditional(y, scales, means=None, scale_bound=0.11, likelihood_bound=1e-9):
+    y_hat = quantize(y, "dequantize", means)
+    values = y_hat - means if means is not None else y_hat
+    s = torch.max(scales, torch.tensor([scale_bound]))
+    values = torch.abs(values)
+    upper = std_cumulative((0.5 - values) / s)
+    lower = std_cumulative((-0.5 - values) / s)
+    lik = upper - lower
+    if likelihood_bound > 0:
+        lik = torch.max(lik, torch.tensor([likelihood_bound]))
+    return y_hat, lik
+
+
+# entropy_models.py:556-562 ; scale table compressai/models/priors.py get_scale_table
+def scale_table(mn=0.11, mx=256.0, levels=64):
+    return torch.exp(torch.linspace(math.log(mn), math.log(mx), levels))
+
+
+def build_indexes(scales, table, scale_bound=0.11):
+    s = torch.max(scales, torch.tensor([scale_bound]))
+    idx = torch.full(s.shape, len(table) - 1, dtype=torch.int32)
+    for t in table[:-1]:
+        idx -= (s <= t).int()
+    return idx
+
+
+# entropy_models.py:413-418
+def eb_build_indexes(size):
+    N, C, H, W = size
+    return torch.arange(C).view(1, -1, 1, 1).int().repeat(N, 1, H, W)
+
+
+# ywz/mywork/newnet1.py:441-453 (python double loop == global max per (b,c))
+def spatial_pool2d(X):
+    return X.amax(dim=(2, 3), keepdim=True).float()
+
+
+# ----------------------------------------------------------------------------
+# model pieces, keyed by reference state_dict names
+def _cw(sd, p):
+    return sd[p + ".weight"], sd[p + ".bias"]
+
+
+def _gdn(sd, p, x, inverse=False):
+    return gdn(x, sd[p + ".beta"], sd[p + ".gamma"], inverse)
+
+
+# newnet1.py:580-601
+def encoder1(sd, x, p="encoder1"):
+    x = _gdn(sd, p + ".g_a_gdn1", conv(x, *_cw(sd, p + ".g_a_conv1")))
+    x = _gdn(sd, p + ".g_a_gdn2", conv(x, *_cw(sd, p + ".g_a_conv2")))
+    x = _gdn(sd, p + ".g_a_gdn3", conv(x, *_cw(sd, p + ".g_a_conv3")))
+    return conv(x, *_cw(sd, p + ".g_a_conv4"))
+
+
+# newnet1.py:627-655
+def encoder2(sd, x1_warp, x2, p="encoder2"):
+    pre = conv(torch.cat((x1_warp, x2), dim=-3), *_cw(sd, p + ".pre_conv"), stride=1)
+    pre = _gdn(sd, p + ".pre_gdn", pre)
+    return encoder1(sd, pre, p)
+
+
+# newnet1.py:603-624
+def decoder1(sd, y_hat, p="decoder1"):
+    x = _gdn(sd, p + ".g_s_gdn1", deconv(y_hat, *_cw(sd, p + ".g_s_conv1")), True)
+    x = _gdn(sd, p + ".g_s_gdn2", deconv(x, *_cw(sd, p + ".g_s_conv2")), True)
+    x = _gdn(sd, p + ".g_s_gdn3", deconv(x, *_cw(sd, p + ".g_s_conv3")), True)
+    return deconv(x, *_cw(sd, p + ".g_s_conv4"))
+
+
+# newnet1.py:657-692
+def decoder2(sd, y_hat, x1_hat_warp, p="decoder2"):
+    c4 = decoder1(sd, y_hat, p)
+    a1 = _gdn(sd, p + ".after_gdn", c4, True)
+    return deconv(torch.cat((a1, x1_hat_warp), dim=-3), *_cw(sd, p + ".after_conv"), stride=1)
+
+
+# newnet1.py:420-437
+def encode_hyper(sd, y, p):
+    q = p + ".encode_hyper"
+    x = F.relu(conv(torch.abs(y), *_cw(sd, q + ".0"), stride=1))
+    x = F.relu(conv(x, *_cw(sd, q + ".2")))
+    return conv(x, *_cw(sd, q + ".4"))
+
+
+def _mix_softmax(t, K, M):
+    t = torch.reshape(t, (-1, K, M, 1, 1))
+    t = F.softmax(t, dim=-4)
+    return torch.reshape(t, (-1, M * K, 1, 1))
+
+
+# newnet1.py:456-514
+def gmm_hyper_y1(sd, z, p, K, M):
+    s = F.relu(deconv(z, *_cw(sd, p + ".gmm_sigma.0")))
+    s = F.relu(deconv(s, *_cw(sd, p + ".gmm_sigma.2")))
+    s = F.relu(conv(s, *_cw(sd, p + ".gmm_sigma.4"), stride=1))
+    m = F.leaky_relu(deconv(z, *_cw(sd, p + ".gmm_means.0")))
+    m = F.leaky_relu(deconv(m, *_cw(sd, p + ".gmm_means.2")))
+    m = conv(m, *_cw(sd, p + ".gmm_means.4"), stride=1)
+    w = F.leaky_relu(deconv(z, *_cw(sd, p + ".gmm_weights.0")))
+    w = deconv(w, *_cw(sd, p + ".gmm_weights.2"))
+    w = F.leaky_relu(spatial_pool2d(w))
+    w = conv(w, *_cw(sd, p + ".gmm_weights.5"), stride=1)
+    return s, m, _mix_softmax(w, K, M)
+
+
+# newnet1.py:517-577 (UpsamplingBilinear2d == align_corners=True)
+def gmm_hyper_y2(sd, z2, y1, p, K, M):
+    up = F.interpolate(z2, scale_factor=4, mode="bilinear", align_corners=True)
+    c = torch.cat((up, y1), dim=-3)
+    s = F.relu(conv(c, *_cw(sd, p + ".gmm_sigma.0"), stride=1))
+    s = F.relu(conv(s, *_cw(sd, p + ".gmm_sigma.2"), stride=1))
+    s = F.relu(conv(s, *_cw(sd, p + ".gmm_sigma.4"), stride=1))
+    m = F.leaky_relu(conv(c, *_cw(sd, p + ".gmm_means.0"), stride=1))
+    m = F.leaky_relu(conv(m, *_cw(sd, p + ".gmm_means.2"), stride=1))
+    m = conv(m, *_cw(sd, p + ".gmm_means.4"), stride=1)
+    w = F.leaky_relu(conv(c, *_cw(sd, p + ".gmm_weights.0"), stride=1))
+    w = conv(w, *_cw(sd, p + ".gmm_weights.2"), stride=1)
+    w = F.leaky_relu(spatial_pool2d(w))
+    w = conv(w, *_cw(sd, p + ".gmm_weights.5"), stride=1)
+    return s, m, _mix_softmax(w, K, M)
+
+
+def hsic_forward(sd, x1, x2, h, K=5, twice_left=True, align_corners=True, taps=None):
+    """newnet1.HSIC.forward (newnet1.py:724-783); ``twice_left=False`` gives the
+    .trash/newnet9.py:620-661 variant that test3real.py imports.  ``taps`` (a dict)
+    collects intermediate tensors for per-op parity tests."""
+    T = taps if taps is not None else {}
+    M = sd["encoder1.g_a_conv4.weight"].shape[0]
+    size = (x1.shape[-2], x1.shape[-1])
+    y1 = encoder1(sd, x1)
+    z1 = encode_hyper(sd, y1, "_h_a1")
+    z1_hat, z1_lik = entropy_bottleneck(z1, *eb_params(sd, "entropy_bottleneck1"))
+    s1, m1, w1 = gmm_hyper_y1(sd, z1_hat, "_h_s1", K, M)
+    y1_hat, y1_lik = gmm_conditional(y1, s1, m1, w1, K)
+    x1_hat = decoder1(sd, y1_hat)
+    x1_warp = warp_perspective(x1, h, size, align_corners)
+    y2 = encoder2(sd, x1_warp, x2)
+    x1_hat_warp = warp_perspective(x1_hat, h, size, align_corners)
+    if twice_left:
+        y1_cond = torch.round(encoder1(sd, x1_hat_warp))
+    else:
+        y1_cond = y1_hat
+    z2 = encode_hyper(sd, y2, "_h_a2")
+    z2_hat, z2_lik = entropy_bottleneck(z2, *eb_params(sd, "entropy_bottleneck2"))
+    s2, m2, w2 = gmm_hyper_y2(sd, z2_hat, y1_cond, "_h_s2", K, M)
+    y2_hat, y2_lik = gmm_conditional(y2, s2, m2, w2, K)
+    x2_hat = decoder2(sd, y2_hat, x1_hat_warp)
+    T.update(y1=y1, z1=z1, z1_hat=z1_hat, sigma1=s1, means1=m1, weights1=w1, x1_warp=x1_warp, y2=y2,
+             x1_hat_warp=x1_hat_warp, y1_cond=y1_cond, z2=z2, z2_hat=z2_hat, sigma2=s2, means2=m2, weights2=w2)
+    return {"x1_hat": x1_hat, "x2_hat": x2_hat, "y1_hat": y1_hat, "y2_hat": y2_hat,
+            "likelihoods": {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}}
+
+
+def _seq(sd, p, x, spec):
+    """spec: list of ('conv'|'deconv', idx, stride) / 'lrelu' entries, nn.Sequential style."""
+    for item in spec:
+        if item == "lrelu":
+            x = F.leaky_relu(x)
+        else:
+            kind, idx, stride = item
+            w, b = _cw(sd, f"{p}.{idx}")
+            x = conv(x, w, b, stride=stride) if kind == "conv" else deconv(x, w, b, stride=stride)
+    return x
+
+
+_HA = [("conv", 0, 1), "lrelu", ("conv", 2, 2), "lrelu", ("conv", 4, 2)]
+_HS = [("deconv", 0, 2), "lrelu", ("deconv", 2, 2), "lrelu", ("conv", 4, 1)]
+_EP = [("conv", 0, 1), "lrelu", ("conv", 2, 1), "lrelu", ("conv", 4, 1)]
+
+
+def masked_conv(sd, p, x):
+    # compressai/layers/layers.py:21-45 (weight *= mask, then conv, padding 2)
+    w = sd[p + ".weight"] * sd[p + ".mask"]
+    return F.conv2d(x, w, sd[p + ".bias"], stride=1, padding=w.shape[-1] // 2)
+
+
+def hsic_joint_forward(sd, x1, x2, h, align_corners=True, taps=None):
+    """newnet1_joint.HSIC.forward (newnet1_joint.py:675-753), eval mode."""
+    T = taps if taps is not None else {}
+    size = (x1.shape[-2], x1.shape[-1])
+    y1 = encoder1(sd, x1)
+    z1 = _seq(sd, "h_a1", y1, _HA)
+    z1_hat, z1_lik = entropy_bottleneck(z1, *eb_params(sd, "entropy_bottleneck1"))
+    params1 = _seq(sd, "h_s1", z1_hat, _HS)
+    y1_hat = torch.round(y1)
+    ctx1 = masked_conv(sd, "context_prediction1", y1_hat)
+    gp1 = _seq(sd, "entropy_parameters1", torch.cat((params1, ctx1), dim=1), _EP)
+    sc1, mu1 = gp1.chunk(2, 1)
+    _, y1_lik = gaussian_conditional(y1, sc1, mu1)
+    x1_hat = decoder1(sd, y1_hat)
+    x1_warp = warp_perspective(x1, h, size, align_corners)
+    y2 = encoder2(sd, x1_warp, x2)
+    z2 = _seq(sd, "h_a2", y2, _HA)
+    z2_hat, z2_lik = entropy_bottleneck(z2, *eb_params(sd, "entropy_bottleneck2"))
+    x1_hat_warp = warp_perspective(x1_hat, h, size, align_corners)
+    y1_cond = torch.round(encoder1(sd, x1_hat_warp))
+    params2 = _seq(sd, "h_s2", z2_hat, _HS)
+    y2_hat = torch.round(y2)
+    ctx2 = masked_conv(sd, "context_prediction2", y2_hat)
+    gp2 = _seq(sd, "entropy_parameters2", torch.cat((params2, ctx2, y1_cond), dim=1), _EP)
+    sc2, mu2 = gp2.chunk(2, 1)
+    _, y2_lik = gaussian_conditional(y2, sc2, mu2)
+    x2_hat = decoder2(sd, y2_hat, x1_hat_warp)
+    T.update(y1=y1, z1=z1, z1_hat=z1_hat, scales1=sc1, means1=mu1, y2=y2, z2=z2, z2_hat=z2_hat,
+             scales2=sc2, means2=mu2, x1_warp=x1_warp, x1_hat_warp=x1_hat_warp, y1_cond=y1_cond)
+    return {"x1_hat": x1_hat, "x2_hat": x2_hat, "y1_hat": y1_hat, "y2_hat": y2_hat,
+            "likelihoods": {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}}
+
+
+# ----------------------------------------------------------------------------
+# Independent_EN (newnet1.py:272-311, 1278-1300; layers.py:125-147) -- SURVEY 8f rank 1
+def _resblock(sd, p, x):
+    out = F.leaky_relu(F.conv2d(x, *_cw(sd, p + ".conv1"), padding=1))
+    out = F.leaky_relu(F.conv2d(out, *_cw(sd, p + ".conv2"), padding=1))
+    return out + x
+
+
+def _enh_block(sd, p, x):
+    out = _resblock(sd, p + ".RB1", x)
+    out = _resblock(sd, p + ".RB2", out)
+    out = _resblock(sd, p + ".RB3", out)
+    return out + x
+
+
+def enhancement(sd, p, x, other_warp):
+    out = F.conv2d(torch.cat((x, other_warp), dim=-3), *_cw(sd, p + ".conv1"), padding=1)
+    for eb in ("EB1", "EB2", "EB3"):
+        out = _enh_block(sd, f"{p}.{eb}", out)
+    out = F.conv2d(out, *_cw(sd, p + ".conv2"), padding=1)
+    return out + x
+
+
+def independent_en_forward(sd, x1_hat, x2_hat, h, align_corners=True):
+    size = (x1_hat.shape[-2], x1_hat.shape[-1])
+    x1_hat_warp = warp_perspective(x1_hat, h, size, align_corners)
+    x2_hat_warp = warp_perspective(x2_hat, torch.inverse(h), size, align_corners)
+    return {"x1_hat": enhancement(sd, "EH1", x1_hat, x2_hat_warp),
+            "x2_hat": enhancement(sd, "EH2", x2_hat, x1_hat_warp)}
+
+
+# ----------------------------------------------------------------------------
+# EntropyBottleneck.update() tables (entropy_models.py:302-343) -- float part; the
+# pmf -> integer CDF step is oracle/coder_oracle.c (ops.cpp:24-81)
+def eb_update_pmf(mats, bias, fac, quantiles):
+    medians = quantiles[:, 0, 1]
+    minima = torch.clamp(torch.ceil(medians - quantiles[:, 0, 0]).int(), min=0)
+    maxima = torch.clamp(torch.ceil(quantiles[:, 0, 2] - medians).int(), min=0)
+    offset = -minima
+    pmf_start = medians - minima
+    pmf_length = maxima + minima + 1
+    max_length = int(pmf_length.max())
+    samples = torch.arange(max_length)[None, :] + pmf_start[:, None, None]
+    lower = eb_logits_cumulative(samples - 0.5, mats, bias, fac)
+    upper = eb_logits_cumulative(samples + 0.5, mats, bias, fac)
+    sign = -torch.sign(lower + upper)
+    pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
+    tail = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+    return pmf, tail, pmf_length, offset
