@@ -1,0 +1,147 @@
+"""ctypes binding of include/hesic_b200.h (the C-ABI drop-in boundary).
+
+PyTorch is used here only as the owner of device memory and streams: every
+call passes raw device pointers, sizes and the current CUDA stream handle.
+There is no fallback: if libhesic_b200.so is missing or cannot be loaded the
+import fails loudly, and device entry points raise when handed CPU tensors.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libhesic_b200.so")
+
+FMT_NCHW, FMT_NHWC, FMT_SPLIT = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
+OP_COPY, OP_ABS, OP_ROUND = 0, 1, 2
+EB_PARAMS = 60
+
+
+class HesicError(RuntimeError):
+    pass
+
+
+class CTensor(ctypes.Structure):
+    _fields_ = [("p0", c_void_p), ("p1", c_void_p), ("fmt", c_int32), ("B", c_int32), ("C", c_int32),
+                ("H", c_int32), ("W", c_int32), ("Cs", c_int32)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"hesic_b200: {LIB_PATH} not found. Build it with `python -m hesic_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+_TP = POINTER(CTensor)
+_FP = POINTER(c_float)
+_sig = {
+    "hesic_abi_version": ([], c_int),
+    "hesic_last_error": ([], c_char_p),
+    "hesic_device_check": ([c_char_p, c_int], c_int),
+    "hesic_launch_count": ([c_int], c_int64),
+    "hesic_conv_create": ([c_int] * 8, c_void_p),
+    "hesic_conv_destroy": ([c_void_p], None),
+    "hesic_conv_load": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "hesic_conv_set_gdn": ([c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p], c_int),
+    "hesic_conv_forward": ([c_void_p, _TP, _TP, c_int, c_int, c_void_p], c_int),
+    "hesic_gdn": ([_TP, _TP, c_void_p, c_void_p, c_int, c_float, c_void_p], c_int),
+    "hesic_warp_perspective": ([_TP, c_void_p, _TP, c_int, c_void_p], c_int),
+    "hesic_eb_pack": ([POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_int, c_void_p, c_void_p], c_int),
+    "hesic_entropy_bottleneck": ([_TP, c_void_p, c_float, _TP, _TP, c_void_p, c_void_p], c_int),
+    "hesic_gaussian_conditional": ([_TP, _TP, _TP, c_void_p, c_int, c_int, c_float, c_float, _TP, _TP, c_void_p, c_void_p], c_int),
+    "hesic_spatial_max": ([_TP, c_void_p, c_void_p], c_int),
+    "hesic_mixture_weights": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
+    "hesic_upsample_bilinear": ([_TP, _TP, c_int, c_void_p], c_int),
+    "hesic_convert": ([_TP, _TP, c_int, c_void_p], c_int),
+    "hesic_prepare_symbols": ([_TP, c_void_p, _TP, c_void_p, c_void_p], c_int),
+    "hesic_build_indexes_channel": ([c_int, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
+    "hesic_build_indexes_scale": ([_TP, c_void_p, c_int, c_float, c_void_p, c_void_p], c_int),
+    "hesic_sum_squared_error": ([_TP, _TP, c_void_p, c_void_p], c_int),
+    "hesic_pmf_to_quantized_cdf": ([_FP, c_int, c_int, POINTER(c_uint32)], c_int),
+    "hesic_rans_encoder_create": ([], c_void_p),
+    "hesic_rans_encoder_destroy": ([c_void_p], None),
+    "hesic_rans_encoder_push": ([c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
+    "hesic_rans_encoder_flush": ([c_void_p, c_void_p, c_int64], c_int64),
+    "hesic_rans_decoder_create": ([], c_void_p),
+    "hesic_rans_decoder_destroy": ([c_void_p], None),
+    "hesic_rans_decoder_set_stream": ([c_void_p, c_void_p, c_int64], c_int),
+    "hesic_rans_decoder_decode": ([c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int),
+}
+EXPORTS = tuple(_sig)
+for _name, (_args, _res) in _sig.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = _res
+
+if lib.hesic_abi_version() != 1:
+    raise ImportError("hesic_b200: ABI version mismatch between _capi.py and libhesic_b200.so")
+
+
+def last_error():
+    return (lib.hesic_last_error() or b"").decode()
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -3:
+        raise NotImplementedError(msg)
+    raise HesicError(msg)
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hesic_b200: CUDA tensors required -- this path has no CPU fallback "
+                               "(the CPU implementation is the reference itself)")
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def nchw(t, C=None, c0=0):
+    """Descriptor for a contiguous NCHW fp32 torch tensor (optionally a channel slice [c0, c0+C))."""
+    assert t.dtype == torch.float32 and t.is_contiguous(), "expected contiguous fp32"
+    B, Cs, H, W = t.shape
+    C = Cs - c0 if C is None else C
+    return CTensor(t.data_ptr() + 4 * c0 * H * W, None, FMT_NCHW, B, C, H, W, Cs)
+
+
+def nhwc(t, C=None, c0=0):
+    """Descriptor for a contiguous [B,H,W,C] fp32 torch tensor (NHWC storage)."""
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    B, H, W, Cs = t.shape
+    C = Cs - c0 if C is None else C
+    return CTensor(t.data_ptr() + 4 * c0, None, FMT_NHWC, B, C, H, W, Cs)
+
+
+def split(t, C=None, c0=0):
+    """Descriptor for a [2,B,H,W,C] bf16 torch tensor holding the (hi, lo) planes."""
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[0] == 2
+    _, B, H, W, Cs = t.shape
+    C = Cs - c0 if C is None else C
+    plane = B * H * W * Cs * 2
+    return CTensor(t.data_ptr() + 2 * c0, t.data_ptr() + plane + 2 * c0, FMT_SPLIT, B, C, H, W, Cs)
+
+
+def null():
+    return CTensor(None, None, 0, 0, 0, 0, 0, 0)
+
+
+def ref(ct):
+    return ctypes.byref(ct)

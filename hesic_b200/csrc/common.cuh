@@ -1,0 +1,134 @@
+// Shared device/host helpers for the hesic_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/hesic_b200.h"
+
+namespace hesic {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int cuda_fail(cudaError_t e, const char *what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return HESIC_E_CUDA;
+}
+
+#define HESIC_CUDA(expr)                                   \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return hesic::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define HESIC_REQUIRE(cond, ...)   \
+  do {                             \
+    if (!(cond)) {                 \
+      hesic::set_error(__VA_ARGS__); \
+      return HESIC_E_INVALID;      \
+    }                              \
+  } while (0)
+
+// call after every kernel launch
+inline int launched(const char *name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, name);
+  return HESIC_OK;
+}
+#define HESIC_LAUNCHED(name)           \
+  do {                                 \
+    int _r = hesic::launched(name);    \
+    if (_r != HESIC_OK) return _r;     \
+  } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---------------------------------------------------------------------------------------------
+// Device view of a hesic_tensor
+struct TView {
+  const void *p0;
+  const void *p1;
+  int fmt, B, C, H, W, Cs;
+};
+
+inline TView view(const hesic_tensor *t) {
+  TView v;
+  v.p0 = t->p0; v.p1 = t->p1; v.fmt = t->fmt; v.B = t->B; v.C = t->C; v.H = t->H; v.W = t->W;
+  v.Cs = t->Cs > 0 ? t->Cs : t->C;
+  return v;
+}
+
+inline bool same_shape(const hesic_tensor *a, const hesic_tensor *b) {
+  return a->B == b->B && a->C == b->C && a->H == b->H && a->W == b->W;
+}
+
+inline int check_tensor(const hesic_tensor *t, const char *name, bool allow_null_data = false) {
+  HESIC_REQUIRE(t != nullptr, "%s: null tensor descriptor", name);
+  HESIC_REQUIRE(t->fmt >= 0 && t->fmt <= 2, "%s: bad format %d", name, t->fmt);
+  HESIC_REQUIRE(t->B >= 0 && t->C >= 0 && t->H >= 0 && t->W >= 0, "%s: negative size", name);
+  HESIC_REQUIRE(t->Cs == 0 || t->Cs >= t->C, "%s: Cs < C", name);
+  if (!allow_null_data && (int64_t)t->B * t->C * t->H * t->W > 0) {
+    HESIC_REQUIRE(t->p0 != nullptr, "%s: null data pointer", name);
+    if (t->fmt == HESIC_FMT_NHWC_SPLIT) HESIC_REQUIRE(t->p1 != nullptr, "%s: null lo plane", name);
+  }
+  return HESIC_OK;
+}
+
+__device__ __forceinline__ size_t toff(const TView &t, int b, int c, int y, int x) {
+  if (t.fmt == HESIC_FMT_NCHW_F32) return (((size_t)b * t.Cs + c) * t.H + y) * t.W + x;
+  return (((size_t)b * t.H + y) * t.W + x) * t.Cs + c;
+}
+
+__device__ __forceinline__ float tload(const TView &t, int b, int c, int y, int x) {
+  size_t o = toff(t, b, c, y, x);
+  if (t.fmt == HESIC_FMT_NHWC_SPLIT) {
+    return __bfloat162float(((const __nv_bfloat16 *)t.p0)[o]) + __bfloat162float(((const __nv_bfloat16 *)t.p1)[o]);
+  }
+  return ((const float *)t.p0)[o];
+}
+
+// value = hi + lo with hi = rn_bf16(v), lo = rn_bf16(v - hi): |v - hi - lo| <= 2^-18 |v|
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ void tstore(const TView &t, int b, int c, int y, int x, float v) {
+  size_t o = toff(t, b, c, y, x);
+  if (t.fmt == HESIC_FMT_NHWC_SPLIT) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    ((__nv_bfloat16 *)t.p0)[o] = hi;
+    ((__nv_bfloat16 *)t.p1)[o] = lo;
+  } else {
+    ((float *)t.p0)[o] = v;
+  }
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == HESIC_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == HESIC_ACT_LEAKY_RELU) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
+// NonNegativeParametrizer.forward (compressai/ops/parametrizers.py:41-44)
+__device__ __forceinline__ float nonneg_reparam(float p, float minimum) {
+  const float pedestal = 1.4551915228366852e-11f;  // (2^-18)^2
+  float bound = sqrtf(minimum + pedestal);
+  float o = fmaxf(p, bound);
+  return o * o - pedestal;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace hesic

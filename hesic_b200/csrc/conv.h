@@ -1,0 +1,29 @@
+// Convolution plan shared by the SIMT and tcgen05 paths.
+#pragma once
+#include "common.cuh"
+
+struct hesic_conv {
+  int Cin = 0, Cout = 0, kh = 0, kw = 0, stride = 1, pad = 0, transposed = 0, out_pad = 0;
+  // SIMT operand: fp32 [kh*kw*Cin][Cout] (tap-major rows, Cout contiguous)
+  float *w_simt = nullptr;
+  float *bias = nullptr;   // [Cout] (zeros when the layer has no bias)
+  // tcgen05 operands: bf16 hi / lo planes [kh*kw][CoutPad][Cin] (K-major per tap)
+  __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
+  int CoutPad = 0;
+  bool loaded = false;
+  // fused GDN
+  bool has_gdn = false;
+  int gdn_inverse = 0;
+  float *gdn_beta = nullptr;    // reparametrised beta [Cout]
+  float *gdn_w_simt = nullptr;  // fp32 [Cout(j)][Cout(i)] = gamma[i][j]
+  __nv_bfloat16 *gdn_g_hi = nullptr, *gdn_g_lo = nullptr;  // bf16 planes [Cout(i)][Cout(j)] (K-major)
+};
+
+namespace hesic {
+int conv_out_size(const hesic_conv *c, int in, int k);
+int conv_forward_simt(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s);
+int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s);
+bool conv_tc_supported(const hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y);
+int gdn_simt(const hesic_tensor *x, const hesic_tensor *y, const float *beta_rp, const float *w_simt, int inverse,
+             cudaStream_t s);
+}  // namespace hesic

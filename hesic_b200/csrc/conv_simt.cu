@@ -1,0 +1,359 @@
+// Generic fp32 implicit-GEMM convolution on CUDA cores (sm_100a).
+//
+// Role in the design: (1) the layers whose GEMM shape cannot feed a tensor-core tile -- the
+// full-resolution edge layers with Cin or Cout in {3, 6} (newnet1.py:583,612,629,670) and the
+// 3-channel GDNs -- and (2) the correctness anchor the tcgen05 path (conv_tc.cu) is validated
+// against on the device.  One kernel covers nn.Conv2d (any stride) and nn.ConvTranspose2d in gather
+// form, with bias + activation (+ GDN as a 1x1 contraction over x^2) fused.
+#include "conv.h"
+
+namespace hesic {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+struct ConvArgs {
+  TView x, y;
+  const float *w;     // [K][Cout]
+  const float *bias;  // [Cout]
+  int Cin, Cout, kh, kw, stride, pad, transposed;
+  int Hout, Wout, K, M;
+  int act;
+  int gdn;  // 0 conv, 1 GDN, 2 inverse GDN (A = x^2, epilogue x * (r)sqrt)
+};
+
+template <bool NHWC_IN>
+__global__ void __launch_bounds__(NT) conv_simt_kernel(const ConvArgs a) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  // A-load mapping: NHWC -> consecutive threads walk k (channels); NCHW -> walk pixels.
+  int am[4], ak[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int e = tid + i * NT;
+    if (NHWC_IN) { ak[i] = e % BK; am[i] = e / BK; }
+    else         { am[i] = e % BM; ak[i] = e / BM; }
+  }
+  int ab[4], aoy[4], aox[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + am[i];
+    if (m < a.M) {
+      ab[i] = m / (a.Hout * a.Wout);
+      int r = m - ab[i] * a.Hout * a.Wout;
+      aoy[i] = r / a.Wout;
+      aox[i] = r - aoy[i] * a.Wout;
+    } else {
+      ab[i] = -1; aoy[i] = 0; aox[i] = 0;
+    }
+  }
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < a.K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = 0.f;
+      int kg = k0 + ak[i];
+      if (kg < a.K && ab[i] >= 0) {
+        int tap = kg / a.Cin, ci = kg - tap * a.Cin;
+        int ky = tap / a.kw, kx = tap - ky * a.kw;
+        int iy, ix;
+        bool ok = true;
+        if (!a.transposed) {
+          iy = aoy[i] * a.stride + ky - a.pad;
+          ix = aox[i] * a.stride + kx - a.pad;
+        } else {
+          int ty_ = aoy[i] + a.pad - ky, tx_ = aox[i] + a.pad - kx;
+          ok = ty_ >= 0 && tx_ >= 0 && (ty_ % a.stride) == 0 && (tx_ % a.stride) == 0;
+          iy = ty_ / a.stride;
+          ix = tx_ / a.stride;
+        }
+        if (ok && iy >= 0 && iy < a.x.H && ix >= 0 && ix < a.x.W) {
+          v = tload(a.x, ab[i], ci, iy, ix);
+          if (a.gdn) v = v * v;
+        }
+      }
+      As[ak[i]][am[i]] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * NT;
+      int n = e % BN, k = e / BN;
+      int kg = k0 + k;
+      Bs[k][n] = (kg < a.K && n0 + n < a.Cout) ? a.w[(size_t)kg * a.Cout + n0 + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+    int b = m / (a.Hout * a.Wout);
+    int r = m - b * a.Hout * a.Wout;
+    int oy = r / a.Wout, ox = r - oy * a.Wout;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= a.Cout) continue;
+      float v = acc[i][j] + a.bias[n];
+      if (a.gdn) {
+        float xin = tload(a.x, b, n, oy, ox);
+        v = xin * (a.gdn == 2 ? sqrtf(v) : rsqrtf(v));
+      }
+      v = apply_act(v, a.act);
+      tstore(a.y, b, n, oy, ox, v);
+    }
+  }
+}
+
+int conv_out_size(const hesic_conv *c, int in, int k) {
+  if (!c->transposed) return (in + 2 * c->pad - k) / c->stride + 1;
+  return (in - 1) * c->stride - 2 * c->pad + k + c->out_pad;
+}
+
+static int launch_simt(const ConvArgs &a, cudaStream_t s) {
+  if (a.M == 0 || a.Cout == 0) return HESIC_OK;
+  dim3 grid((a.M + BM - 1) / BM, (a.Cout + BN - 1) / BN);
+  if (a.x.fmt == HESIC_FMT_NCHW_F32) conv_simt_kernel<false><<<grid, NT, 0, s>>>(a);
+  else conv_simt_kernel<true><<<grid, NT, 0, s>>>(a);
+  HESIC_LAUNCHED("conv_simt_kernel");
+  return HESIC_OK;
+}
+
+int conv_forward_simt(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s) {
+  ConvArgs a;
+  a.x = view(x); a.y = view(y);
+  a.w = c->w_simt; a.bias = c->bias;
+  a.Cin = c->Cin; a.Cout = c->Cout; a.kh = c->kh; a.kw = c->kw; a.stride = c->stride; a.pad = c->pad;
+  a.transposed = c->transposed;
+  a.Hout = y->H; a.Wout = y->W; a.K = c->kh * c->kw * c->Cin; a.M = y->B * y->H * y->W;
+  a.act = c->has_gdn ? HESIC_ACT_NONE : act; a.gdn = 0;
+  if (!c->has_gdn) return launch_simt(a, s);
+  // unfused: conv -> scratch in y's own storage is not possible (GDN mixes channels), so run the conv
+  // into a temporary fp32 NHWC buffer and the GDN contraction from there.
+  float *tmp = nullptr;
+  size_t n = (size_t)y->B * y->H * y->W * c->Cout;
+  HESIC_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), s));
+  hesic_tensor t = *y;
+  t.p0 = tmp; t.p1 = nullptr; t.fmt = HESIC_FMT_NHWC_F32; t.Cs = c->Cout;
+  a.y = view(&t);
+  int r = launch_simt(a, s);
+  if (r == HESIC_OK) {
+    r = gdn_simt(&t, y, c->gdn_beta, c->gdn_w_simt, c->gdn_inverse, s);
+    if (r == HESIC_OK && act != HESIC_ACT_NONE) { set_error("activation after fused GDN is not supported"); r = HESIC_E_UNSUPPORTED; }
+  }
+  cudaFreeAsync(tmp, s);
+  return r;
+}
+
+int gdn_simt(const hesic_tensor *x, const hesic_tensor *y, const float *beta_rp, const float *w_simt, int inverse,
+             cudaStream_t s) {
+  ConvArgs a;
+  a.x = view(x); a.y = view(y);
+  a.w = w_simt; a.bias = beta_rp;
+  a.Cin = x->C; a.Cout = x->C; a.kh = 1; a.kw = 1; a.stride = 1; a.pad = 0; a.transposed = 0;
+  a.Hout = x->H; a.Wout = x->W; a.K = x->C; a.M = x->B * x->H * x->W;
+  a.act = HESIC_ACT_NONE; a.gdn = inverse ? 2 : 1;
+  return launch_simt(a, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand packing
+__global__ void pack_conv_kernel(const float *__restrict__ w, const float *__restrict__ mask, int Cin, int Cout,
+                                 int kh, int kw, int transposed, int CoutPad, float *__restrict__ w_simt,
+                                 __nv_bfloat16 *__restrict__ w_hi, __nv_bfloat16 *__restrict__ w_lo) {
+  size_t total = (size_t)kh * kw * Cin * CoutPad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int ci = i % Cin;
+    size_t r = i / Cin;
+    int co = r % CoutPad;
+    int tap = r / CoutPad;
+    int ky = tap / kw, kx = tap % kw;
+    float v = 0.f;
+    if (co < Cout) {
+      size_t src = transposed ? ((((size_t)ci * Cout + co) * kh + ky) * kw + kx)
+                              : ((((size_t)co * Cin + ci) * kh + ky) * kw + kx);
+      v = w[src];
+      if (mask) v *= mask[src];
+      w_simt[((size_t)tap * Cin + ci) * Cout + co] = v;
+    }
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    w_hi[i] = hi;  // [tap][CoutPad][Cin]
+    w_lo[i] = lo;
+  }
+}
+
+__global__ void pack_gdn_kernel(const float *__restrict__ beta, const float *__restrict__ gamma, int C, float beta_bound,
+                                float gamma_bound, float pedestal, float *__restrict__ beta_rp,
+                                float *__restrict__ w_simt, __nv_bfloat16 *__restrict__ g_hi,
+                                __nv_bfloat16 *__restrict__ g_lo) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < C) {
+    float o = fmaxf(beta[idx], beta_bound);
+    beta_rp[idx] = o * o - pedestal;
+  }
+  if (idx < C * C) {
+    int i = idx / C, j = idx % C;  // gamma[i][j]: output channel i, input channel j
+    float o = fmaxf(gamma[idx], gamma_bound);
+    float g = o * o - pedestal;
+    w_simt[(size_t)j * C + i] = g;
+    if (g_hi) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(g, hi, lo);
+      g_hi[idx] = hi;
+      g_lo[idx] = lo;
+    }
+  }
+}
+
+__global__ void fill_zero_kernel(float *p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+static void reparam_bounds(float minimum, float *bound, float *pedestal) {
+  // compressai/ops/parametrizers.py:27-36 -- computed in Python doubles, stored as fp32 buffers
+  double off = ldexp(1.0, -18);
+  *pedestal = (float)(off * off);
+  *bound = (float)sqrt((double)minimum + off * off);
+}
+
+int pack_gdn(const float *beta, const float *gamma, int C, float beta_min, float *beta_rp, float *w_simt,
+             __nv_bfloat16 *g_hi, __nv_bfloat16 *g_lo, cudaStream_t s) {
+  float bb, gb, ped;
+  reparam_bounds(beta_min, &bb, &ped);
+  reparam_bounds(0.f, &gb, &ped);
+  int n = C * C;
+  pack_gdn_kernel<<<(n + 255) / 256, 256, 0, s>>>(beta, gamma, C, bb, gb, ped, beta_rp, w_simt, g_hi, g_lo);
+  HESIC_LAUNCHED("pack_gdn_kernel");
+  return HESIC_OK;
+}
+
+}  // namespace hesic
+
+using namespace hesic;
+
+extern "C" hesic_conv *hesic_conv_create(int Cin, int Cout, int kh, int kw, int stride, int pad, int transposed,
+                                         int output_padding) {
+  if (Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0 || output_padding < 0) {
+    set_error("hesic_conv_create: invalid geometry");
+    return nullptr;
+  }
+  hesic_conv *c = new hesic_conv();
+  c->Cin = Cin; c->Cout = Cout; c->kh = kh; c->kw = kw; c->stride = stride; c->pad = pad;
+  c->transposed = transposed ? 1 : 0; c->out_pad = output_padding;
+  c->CoutPad = (Cout + 15) / 16 * 16;
+  return c;
+}
+
+extern "C" void hesic_conv_destroy(hesic_conv *c) {
+  if (!c) return;
+  cudaFree(c->w_simt); cudaFree(c->bias); cudaFree(c->w_hi); cudaFree(c->w_lo);
+  cudaFree(c->gdn_beta); cudaFree(c->gdn_w_simt); cudaFree(c->gdn_g_hi); cudaFree(c->gdn_g_lo);
+  delete c;
+}
+
+extern "C" int hesic_conv_load(hesic_conv *c, const float *weight, const float *bias, const float *mask, void *stream) {
+  HESIC_REQUIRE(c && weight, "hesic_conv_load: null argument");
+  cudaStream_t s = as_stream(stream);
+  size_t taps = (size_t)c->kh * c->kw;
+  if (!c->w_simt) {
+    HESIC_CUDA(cudaMalloc(&c->w_simt, taps * c->Cin * c->Cout * sizeof(float)));
+    HESIC_CUDA(cudaMalloc(&c->bias, c->Cout * sizeof(float)));
+    HESIC_CUDA(cudaMalloc(&c->w_hi, taps * c->Cin * c->CoutPad * sizeof(__nv_bfloat16)));
+    HESIC_CUDA(cudaMalloc(&c->w_lo, taps * c->Cin * c->CoutPad * sizeof(__nv_bfloat16)));
+  }
+  size_t total = taps * c->Cin * c->CoutPad;
+  int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_conv_kernel<<<blocks, 256, 0, s>>>(weight, mask, c->Cin, c->Cout, c->kh, c->kw, c->transposed, c->CoutPad,
+                                          c->w_simt, c->w_hi, c->w_lo);
+  HESIC_LAUNCHED("pack_conv_kernel");
+  if (bias) {
+    HESIC_CUDA(cudaMemcpyAsync(c->bias, bias, c->Cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    fill_zero_kernel<<<(c->Cout + 255) / 256, 256, 0, s>>>(c->bias, c->Cout);
+    HESIC_LAUNCHED("fill_zero_kernel");
+  }
+  c->loaded = true;
+  return HESIC_OK;
+}
+
+extern "C" int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float *gamma, int inverse, float beta_min,
+                                  void *stream) {
+  HESIC_REQUIRE(c, "hesic_conv_set_gdn: null conv");
+  if (!beta || !gamma) { c->has_gdn = false; return HESIC_OK; }
+  int C = c->Cout;
+  if (!c->gdn_beta) {
+    HESIC_CUDA(cudaMalloc(&c->gdn_beta, C * sizeof(float)));
+    HESIC_CUDA(cudaMalloc(&c->gdn_w_simt, (size_t)C * C * sizeof(float)));
+    HESIC_CUDA(cudaMalloc(&c->gdn_g_hi, (size_t)C * C * sizeof(__nv_bfloat16)));
+    HESIC_CUDA(cudaMalloc(&c->gdn_g_lo, (size_t)C * C * sizeof(__nv_bfloat16)));
+  }
+  int r = pack_gdn(beta, gamma, C, beta_min, c->gdn_beta, c->gdn_w_simt, c->gdn_g_hi, c->gdn_g_lo, as_stream(stream));
+  if (r != HESIC_OK) return r;
+  c->has_gdn = true;
+  c->gdn_inverse = inverse ? 1 : 0;
+  return HESIC_OK;
+}
+
+extern "C" int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, int path,
+                                  void *stream) {
+  HESIC_REQUIRE(c && c->loaded, "hesic_conv_forward: weights not loaded");
+  int r;
+  if ((r = check_tensor(x, "conv input")) != HESIC_OK) return r;
+  if ((r = check_tensor(y, "conv output")) != HESIC_OK) return r;
+  HESIC_REQUIRE(x->C == c->Cin, "conv: input has %d channels, layer expects %d", x->C, c->Cin);
+  HESIC_REQUIRE(y->C == c->Cout, "conv: output has %d channels, layer produces %d", y->C, c->Cout);
+  HESIC_REQUIRE(y->B == x->B, "conv: batch mismatch");
+  int Ho = conv_out_size(c, x->H, c->kh), Wo = conv_out_size(c, x->W, c->kw);
+  HESIC_REQUIRE(y->H == Ho && y->W == Wo, "conv: output is %dx%d, expected %dx%d", y->H, y->W, Ho, Wo);
+  HESIC_REQUIRE(act >= 0 && act <= 2, "conv: bad activation %d", act);
+  cudaStream_t s = as_stream(stream);
+  bool tc_ok = conv_tc_supported(c, x, y);
+  if (path == HESIC_PATH_TCGEN05 && !tc_ok) {
+    set_error("conv: shape/format not supported by the tcgen05 path");
+    return HESIC_E_UNSUPPORTED;
+  }
+  if (path == HESIC_PATH_TCGEN05 || (path == HESIC_PATH_AUTO && tc_ok)) return conv_forward_tc(c, x, y, act, s);
+  return conv_forward_simt(c, x, y, act, s);
+}
+
+extern "C" int hesic_gdn(const hesic_tensor *x, const hesic_tensor *y, const float *beta, const float *gamma,
+                         int inverse, float beta_min, void *stream) {
+  int r;
+  if ((r = check_tensor(x, "gdn input")) != HESIC_OK) return r;
+  if ((r = check_tensor(y, "gdn output")) != HESIC_OK) return r;
+  HESIC_REQUIRE(same_shape(x, y), "gdn: shape mismatch");
+  HESIC_REQUIRE(beta && gamma, "gdn: null parameters");
+  cudaStream_t s = as_stream(stream);
+  int C = x->C;
+  float *buf = nullptr;
+  HESIC_CUDA(cudaMallocAsync(&buf, ((size_t)C * C + C) * sizeof(float), s));
+  r = pack_gdn(beta, gamma, C, beta_min, buf + (size_t)C * C, buf, nullptr, nullptr, s);
+  if (r == HESIC_OK) r = gdn_simt(x, y, buf + (size_t)C * C, buf, inverse, s);
+  cudaFreeAsync(buf, s);
+  return r;
+}

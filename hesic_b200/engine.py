@@ -1,0 +1,278 @@
+"""Whole-forward orchestration of HSIC (HESIC), its no-twiceLeft variant and HESIC+.
+
+Host glue only: it walks the module tree of a ``newnet1`` / ``newnet9`` /
+``newnet1_joint`` ``HSIC`` instance, keeps one packed ``ConvPlan`` per layer
+(re-packed when a parameter changes) and enqueues the sm_100a kernels of
+libhesic_b200.so on the current stream in the order of newnet1.py:724-783 /
+newnet1_joint.py:675-753.  Data layout between layers is the library's native
+one -- channels-last bf16 (hi, lo) split planes for everything a tensor-core
+conv consumes, channels-last fp32 for the entropy-model inputs -- and only the
+tensors the reference returns are materialised as NCHW fp32.  Differences from
+the reference's op sequence, none of which change results:
+
+* GDN / IGDN is attached to the preceding convolution's plan (fused epilogue);
+* the two identical warps of ``x1_hat`` (newnet1.py:753 and :767) run once;
+* ``torch.cat`` never materialises: producers write channel slices of the
+  concatenation buffer;
+* ``spatial_pool2d``'s B*960 Python iterations are one reduction kernel, and
+  the LeakyReLU -> conv1x1 -> softmax tail is one kernel;
+* sum(log2 likelihood) partials for bpp are accumulated by the likelihood
+  kernels into ``engine.log2_sums`` (device doubles: y1, y2, z1, z2).
+"""
+import torch
+
+from . import _capi as C
+from . import functional as F
+
+_lib = C.lib
+
+
+def _split(B, H, W, Cn, dev):
+    return torch.empty((2, B, H, W, Cn), device=dev, dtype=torch.bfloat16)
+
+
+def _nhwc(B, H, W, Cn, dev):
+    return torch.empty((B, H, W, Cn), device=dev, dtype=torch.float32)
+
+
+def _nchw(B, Cn, H, W, dev):
+    return torch.empty((B, Cn, H, W), device=dev, dtype=torch.float32)
+
+
+class HesicEngine:
+    def __init__(self, model, variant, align_corners=True, path=C.PATH_AUTO):
+        assert variant in ("newnet1", "newnet9", "joint")
+        self.m = model
+        self.variant = variant
+        self.align_corners = align_corners
+        self.path = path
+        self.log2_sums = None
+
+    # ---- helpers -------------------------------------------------------------------------
+    def _plan(self, conv_mod, gdn_mod=None):
+        plan = conv_mod.hesic_plan()
+        if gdn_mod is not None:
+            plan.set_gdn(gdn_mod.beta, gdn_mod.gamma, gdn_mod.inverse, gdn_mod.beta_min)
+        else:
+            plan.set_gdn(None, None, False)
+        return plan
+
+    def _conv(self, conv_mod, x_desc, out, out_desc_fn, act=C.ACT_NONE, gdn=None):
+        """Run conv_mod on descriptor x_desc; ``out`` is (kind, channels[, existing tensor, c0])."""
+        plan = self._plan(conv_mod, gdn)
+        plan.run(x_desc, out_desc_fn, act, self.path)
+
+    def _run(self, conv_mod, x_desc, B, H, W, kind, act=C.ACT_NONE, gdn=None, dst=None):
+        """Convolve and return (tensor, descriptor).  kind: 'split' | 'nhwc' | 'nchw'.
+        dst=(tensor, c0) writes a channel slice of an existing concat buffer of that kind."""
+        plan = self._plan(conv_mod, gdn)
+        Ho, Wo = plan.out_hw(H, W)
+        Cout = plan.geom[1]
+        dev = self.dev
+        if dst is not None:
+            t, c0 = dst
+        else:
+            c0 = 0
+            t = {"split": _split, "nhwc": _nhwc}[kind](B, Ho, Wo, Cout, dev) if kind != "nchw" else _nchw(B, Cout, Ho, Wo, dev)
+        d = {"split": C.split, "nhwc": C.nhwc, "nchw": C.nchw}[kind](t, Cout, c0)
+        plan.run(x_desc, d, act, self.path)
+        return t, d, Ho, Wo
+
+    def _convert(self, src_desc, dst_desc, op=C.OP_COPY):
+        C.check(_lib.hesic_convert(C.ref(src_desc), C.ref(dst_desc), op, C.stream()))
+
+    def _warp(self, src_desc, h, dst_desc):
+        C.check(_lib.hesic_warp_perspective(C.ref(src_desc), C.ptr(h), C.ref(dst_desc), int(self.align_corners), C.stream()))
+
+    # ---- sub-networks ---------------------------------------------------------------------
+    def _analysis(self, enc, x_desc, B, H, W):
+        """Encoder1 / the g_a part of Encoder2 (newnet1.py:580-601): returns y as NHWC fp32."""
+        _, d, H, W = self._run(enc.g_a_conv1, x_desc, B, H, W, "split", gdn=enc.g_a_gdn1)
+        _, d, H, W = self._run(enc.g_a_conv2, d, B, H, W, "split", gdn=enc.g_a_gdn2)
+        _, d, H, W = self._run(enc.g_a_conv3, d, B, H, W, "split", gdn=enc.g_a_gdn3)
+        y, d, H, W = self._run(enc.g_a_conv4, d, B, H, W, "nhwc")
+        return y, d, H, W
+
+    def _synthesis(self, dec, y_desc, B, H, W, last_kind="nchw", last_gdn=None, last_dst=None):
+        """Decoder1 / the g_s part of Decoder2 (newnet1.py:603-624)."""
+        _, d, H, W = self._run(dec.g_s_conv1, y_desc, B, H, W, "split", gdn=dec.g_s_gdn1)
+        _, d, H, W = self._run(dec.g_s_conv2, d, B, H, W, "split", gdn=dec.g_s_gdn2)
+        _, d, H, W = self._run(dec.g_s_conv3, d, B, H, W, "split", gdn=dec.g_s_gdn3)
+        return self._run(dec.g_s_conv4, d, B, H, W, last_kind, gdn=last_gdn, dst=last_dst)
+
+    def _seq3(self, seq, idx, acts, x_desc, B, H, W, last_kind, last_dst=None):
+        """Three-layer nn.Sequential (conv/deconv at ``idx``) with activations ``acts``."""
+        _, d, H, W = self._run(seq[idx[0]], x_desc, B, H, W, "split", act=acts[0])
+        _, d, H, W = self._run(seq[idx[1]], d, B, H, W, "split", act=acts[1])
+        return self._run(seq[idx[2]], d, B, H, W, last_kind, act=acts[2], dst=last_dst)
+
+    def _bottleneck(self, eb, z, zd, B, H, W, acc):
+        """EntropyBottleneck.forward: z (NHWC fp32) -> z_hat (split NHWC), likelihood (NCHW fp32)."""
+        Cn = z.shape[-1]
+        z_hat = _split(B, H, W, Cn, self.dev)
+        lik = _nchw(B, Cn, H, W, self.dev)
+        zh_d = C.split(z_hat)
+        C.check(_lib.hesic_entropy_bottleneck(C.ref(zd), C.ptr(eb.hesic_params()), eb._lik_bound(), C.ref(zh_d),
+                                              C.ref(C.nchw(lik)), C.ptr(acc), C.stream()))
+        return z_hat, zh_d, lik
+
+    def _mixture_head(self, seq, x_desc, B, H, W, K, M):
+        """gmm_weights branch (newnet1.py:484-512 / 546-574): -> softmaxed weights [B, K*M]."""
+        _, d, H1, W1 = self._run(seq[0], x_desc, B, H, W, "split", act=C.ACT_LEAKY)
+        t, d, H2, W2 = self._run(seq[2], d, B, H1, W1, "nhwc")
+        pooled = torch.empty((B, K * M), device=self.dev, dtype=torch.float32)
+        C.check(_lib.hesic_spatial_max(C.ref(d), C.ptr(pooled), C.stream()))
+        conv1x1 = seq[5]
+        out = torch.empty((B, K * M), device=self.dev, dtype=torch.float32)
+        w = conv1x1.weight.detach()
+        C.check(_lib.hesic_mixture_weights(C.ptr(pooled), C.ptr(w), C.ptr(conv1x1.bias.detach()), B, K, M, C.ptr(out), C.stream()))
+        return out
+
+    def _gmm(self, gm, y_d, s_d, m_d, w, B, H, W, M, K, acc):
+        y_hat = _nchw(B, M, H, W, self.dev)
+        lik = _nchw(B, M, H, W, self.dev)
+        C.check(_lib.hesic_gaussian_conditional(C.ref(y_d), C.ref(s_d), C.ref(m_d), C.ptr(w), K, 1, gm._scale_bound_value(),
+                                                gm._lik_bound(), C.ref(C.nchw(y_hat)), C.ref(C.nchw(lik)), C.ptr(acc),
+                                                C.stream()))
+        return y_hat, lik
+
+    # ---- forward --------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x1, x2, h):
+        m = self.m
+        C.require_cuda(x1, x2, h)
+        if x1.shape != x2.shape or x1.dim() != 4 or x1.shape[1] != 3:
+            raise ValueError(f"expected two [B,3,H,W] images, got {tuple(x1.shape)} and {tuple(x2.shape)}")
+        B, _, H, W = x1.shape
+        if H % 64 or W % 64:
+            raise ValueError("HSIC.forward needs H and W divisible by 64 (four stride-2 stages + two in the hyper path)")
+        if tuple(h.shape) != (B, 3, 3):
+            raise ValueError(f"h_matrix must be [B,3,3], got {tuple(h.shape)}")
+        x1 = x1.float().contiguous()
+        x2 = x2.float().contiguous()
+        h = h.float().contiguous()
+        self.dev = dev = x1.device
+        M, K = m.M, m.K
+        acc = torch.zeros(4, device=dev, dtype=torch.float64)  # sum log2 p: y1, y2, z1, z2
+        self.log2_sums = acc
+        a = lambda i: acc[i:i + 1]
+        joint = self.variant == "joint"
+
+        # ---- view 1 --------------------------------------------------------------------
+        y1, y1_d, Hy, Wy = self._analysis(m.encoder1, C.nchw(x1), B, H, W)
+        if joint:
+            y1_hat, y1_lik, y1h_split_d = self._joint_entropy(1, y1, y1_d, None, B, Hy, Wy, a(2), a(0))
+        else:
+            y1_abs = _split(B, Hy, Wy, M, dev)
+            self._convert(y1_d, C.split(y1_abs), C.OP_ABS)
+            z1, z1_d, Hz, Wz = self._seq3(m._h_a1.encode_hyper, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_NONE),
+                                          C.split(y1_abs), B, Hy, Wy, "nhwc")
+            z1_hat, z1h_d, z1_lik = self._bottleneck(m.entropy_bottleneck1, z1, z1_d, B, Hz, Wz, a(2))
+            hs = m._h_s1
+            _, s_d, _, _ = self._seq3(hs.gmm_sigma, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_RELU), z1h_d, B, Hz, Wz, "nhwc")
+            _, m_d, _, _ = self._seq3(hs.gmm_means, (0, 2, 4), (C.ACT_LEAKY, C.ACT_LEAKY, C.ACT_NONE), z1h_d, B, Hz, Wz, "nhwc")
+            w1 = self._mixture_head(hs.gmm_weights, z1h_d, B, Hz, Wz, K, M)
+            y1_hat, y1_lik = self._gmm(m.gaussian1, y1_d, s_d, m_d, w1, B, Hy, Wy, M, K, a(0))
+            y1h_split = _split(B, Hy, Wy, M, dev)
+            y1h_split_d = C.split(y1h_split)
+            self._convert(C.nchw(y1_hat), y1h_split_d)
+        x1_hat, _, _, _ = self._synthesis(m.decoder1, y1h_split_d, B, Hy, Wy)
+
+        # ---- view 2 analysis -------------------------------------------------------------
+        cat_in = _nchw(B, 6, H, W, dev)    # cat(x1_warp, x2)            newnet1.py:643
+        cat_out = _nchw(B, 6, H, W, dev)   # cat(after_gdn(..), x1_hat_warp)  newnet1.py:686
+        self._warp(C.nchw(x1), h, C.nchw(cat_in, 3, 0))
+        self._convert(C.nchw(x2), C.nchw(cat_in, 3, 3))
+        enc2 = m.encoder2
+        pre, pre_d, _, _ = self._run(enc2.pre_conv, C.nchw(cat_in), B, H, W, "nchw", gdn=enc2.pre_gdn)
+        y2, y2_d, _, _ = self._analysis(enc2, pre_d, B, H, W)
+        x1hw_d = C.nchw(cat_out, 3, 3)
+        self._warp(C.nchw(x1_hat), h, x1hw_d)          # newnet1.py:753 and :767 (identical) run once
+
+        # ---- conditioning on the left view ----------------------------------------------
+        if joint:
+            cond_buf = _split(B, Hy, Wy, 5 * M, dev)   # cat(params2, ctx2, y1_hat_warpf2)  newnet1_joint.py:722
+            cond_c0 = 4 * M
+        else:
+            N = m.N
+            cond_buf = _split(B, Hy, Wy, N + M, dev)   # cat(up(z2_hat), y1)                newnet1.py:565
+            cond_c0 = N
+        cond_slice = C.split(cond_buf, M, cond_c0)
+        if self.variant == "newnet9":
+            self._convert(y1h_split_d, cond_slice)
+        else:
+            yw, yw_d, _, _ = self._analysis(m.encoder1, x1hw_d, B, H, W)   # "twiceLeft" re-encode
+            self._convert(yw_d, cond_slice, C.OP_ROUND)
+
+        # ---- view 2 entropy model ---------------------------------------------------------
+        if joint:
+            y2_hat, y2_lik, y2h_split_d = self._joint_entropy(2, y2, y2_d, cond_buf, B, Hy, Wy, a(3), a(1))
+        else:
+            y2_abs = _split(B, Hy, Wy, M, dev)
+            self._convert(y2_d, C.split(y2_abs), C.OP_ABS)
+            z2, z2_d, Hz, Wz = self._seq3(m._h_a2.encode_hyper, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_NONE),
+                                          C.split(y2_abs), B, Hy, Wy, "nhwc")
+            z2_hat, z2h_d, z2_lik = self._bottleneck(m.entropy_bottleneck2, z2, z2_d, B, Hz, Wz, a(3))
+            C.check(_lib.hesic_upsample_bilinear(C.ref(z2h_d), C.ref(C.split(cond_buf, m.N, 0)), 4, C.stream()))
+            hs = m._h_s2
+            cd = C.split(cond_buf)
+            r3, r2 = C.ACT_RELU, C.ACT_LEAKY
+            _, s_d, _, _ = self._seq3(hs.gmm_sigma, (0, 2, 4), (r3, r3, r3), cd, B, Hy, Wy, "nhwc")
+            _, m_d, _, _ = self._seq3(hs.gmm_means, (0, 2, 4), (r2, r2, C.ACT_NONE), cd, B, Hy, Wy, "nhwc")
+            w2 = self._mixture_head(hs.gmm_weights, cd, B, Hy, Wy, K, M)
+            y2_hat, y2_lik = self._gmm(m.gaussian2, y2_d, s_d, m_d, w2, B, Hy, Wy, M, K, a(1))
+            y2h_split = _split(B, Hy, Wy, M, dev)
+            y2h_split_d = C.split(y2h_split)
+            self._convert(C.nchw(y2_hat), y2h_split_d)
+
+        # ---- view 2 synthesis ---------------------------------------------------------------
+        dec2 = m.decoder2
+        self._synthesis(dec2, y2h_split_d, B, Hy, Wy, last_kind="nchw", last_gdn=dec2.after_gdn, last_dst=(cat_out, 0))
+        x2_hat, _, _, _ = self._run(dec2.after_conv, C.nchw(cat_out), B, H, W, "nchw")
+
+        out = {"x1_hat": x1_hat, "x2_hat": x2_hat}
+        if self.variant != "newnet9":
+            out["y1_hat"] = y1_hat
+            out["y2_hat"] = y2_hat
+        if joint:
+            z1_lik, z2_lik = self._z_liks
+        out["likelihoods"] = {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}
+        return out
+
+    # ---- HESIC+ entropy model of one view (newnet1_joint.py:676-692 / 706-727) ---------------
+    def _joint_entropy(self, view, y, y_d, cond_buf, B, Hy, Wy, acc_z, acc_y):
+        m = self.m
+        M = m.M
+        dev = self.dev
+        h_a = getattr(m, f"h_a{view}")
+        h_s = getattr(m, f"h_s{view}")
+        ep = getattr(m, f"entropy_parameters{view}")
+        ctxp = getattr(m, f"context_prediction{view}")
+        eb = getattr(m, f"entropy_bottleneck{view}")
+        L = C.ACT_LEAKY
+        y_split = _split(B, Hy, Wy, M, dev)
+        self._convert(y_d, C.split(y_split))
+        z, z_d, Hz, Wz = self._seq3(h_a, (0, 2, 4), (L, L, C.ACT_NONE), C.split(y_split), B, Hy, Wy, "nhwc")
+        z_hat, zh_d, z_lik = self._bottleneck(eb, z, z_d, B, Hz, Wz, acc_z)
+        if view == 1:
+            self._z_liks = [z_lik, None]
+            buf = _split(B, Hy, Wy, 4 * M, dev)      # cat(params1, ctx_params1)  newnet1_joint.py:687-688
+        else:
+            self._z_liks[1] = z_lik
+            buf = cond_buf
+        self._seq3(h_s, (0, 2, 4), (L, L, C.ACT_NONE), zh_d, B, Hz, Wz, "split", last_dst=(buf, 0))
+        yh_split = _split(B, Hy, Wy, M, dev)
+        yh_d = C.split(yh_split)
+        self._convert(y_d, yh_d, C.OP_ROUND)         # y_hat = round(y)  (:684-685)
+        y_hat = _nchw(B, M, Hy, Wy, dev)
+        self._convert(yh_d, C.nchw(y_hat))
+        self._run(ctxp, yh_d, B, Hy, Wy, "split", dst=(buf, 2 * M))
+        gp, gp_d, _, _ = self._seq3(ep, (0, 2, 4), (L, L, C.ACT_NONE), C.split(buf), B, Hy, Wy, "nhwc")
+        scales_d = C.nhwc(gp, M, 0)
+        means_d = C.nhwc(gp, M, M)
+        lik = _nchw(B, M, Hy, Wy, dev)
+        gc = m.gaussian_conditional1                  # the reference uses conditional1 for both views (:725)
+        C.check(_lib.hesic_gaussian_conditional(C.ref(y_d), C.ref(scales_d), C.ref(means_d), None, 1, 0,
+                                                gc._scale_bound_value(), gc._lik_bound(), None, C.ref(C.nchw(lik)),
+                                                C.ptr(acc_y), C.stream()))
+        return y_hat, lik, yh_d

@@ -1,0 +1,315 @@
+"""Operator-level host API over the C-ABI: the same operations the reference's
+``compressai.layers`` / ``compressai.entropy_models`` / ``kornia`` calls perform,
+taking and returning NCHW fp32 CUDA tensors.  Plumbing only -- every function
+allocates its outputs with torch and launches hand-written sm_100a kernels
+through ``_capi``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi as C
+
+_lib = C.lib
+
+
+def _f32(t):
+    C.require_cuda(t)
+    if t.dtype != torch.float32:
+        raise TypeError(f"hesic_b200: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+class ConvPlan:
+    """Owns a ``hesic_conv`` handle: packed weights (+ optional fused GDN) of one
+    nn.Conv2d / nn.ConvTranspose2d as built by compressai/models/utils.py:104-118."""
+
+    def __init__(self, Cin, Cout, k, stride, pad, transposed=False, output_padding=0):
+        kh, kw = (k, k) if isinstance(k, int) else k
+        self.geom = (Cin, Cout, kh, kw, stride, pad, int(transposed), output_padding)
+        self.h = _lib.hesic_conv_create(*self.geom)
+        if not self.h:
+            raise ValueError(C.last_error())
+        self._key = None
+        self._gdn_key = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.hesic_conv_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ver(*ts):
+        return tuple((t.data_ptr(), t._version, t.device.index) if t is not None else None for t in ts)
+
+    def load(self, weight, bias=None, mask=None):
+        key = self._ver(weight, bias, mask)
+        if key == self._key:
+            return self
+        w = _f32(weight.detach())
+        b = _f32(bias.detach()) if bias is not None else None
+        m = _f32(mask.detach()) if mask is not None else None
+        C.check(_lib.hesic_conv_load(self.h, C.ptr(w), C.ptr(b), C.ptr(m), C.stream()))
+        self._key = key
+        return self
+
+    def set_gdn(self, beta, gamma, inverse, beta_min=1e-6):
+        if beta is None:
+            C.check(_lib.hesic_conv_set_gdn(self.h, None, None, 0, 0.0, C.stream()))
+            self._gdn_key = None
+            return self
+        key = self._ver(beta, gamma) + (inverse,)
+        if key == self._gdn_key:
+            return self
+        C.check(_lib.hesic_conv_set_gdn(self.h, C.ptr(_f32(beta.detach())), C.ptr(_f32(gamma.detach())), int(inverse),
+                                        float(beta_min), C.stream()))
+        self._gdn_key = key
+        return self
+
+    def out_hw(self, H, W):
+        Cin, Cout, kh, kw, s, p, tr, op = self.geom
+        if not tr:
+            return (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
+        return (H - 1) * s - 2 * p + kh + op, (W - 1) * s - 2 * p + kw + op
+
+    def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO):
+        C.check(_lib.hesic_conv_forward(self.h, C.ref(x_desc), C.ref(y_desc), act, path, C.stream()))
+
+
+def conv2d(x, plan, act=C.ACT_NONE, path=C.PATH_AUTO):
+    """NCHW fp32 in -> NCHW fp32 out through a loaded ConvPlan."""
+    x = _f32(x)
+    B, _, H, W = x.shape
+    Ho, Wo = plan.out_hw(H, W)
+    y = torch.empty((B, plan.geom[1], Ho, Wo), device=x.device, dtype=torch.float32)
+    if path == C.PATH_SIMT:
+        plan.run(C.nchw(x), C.nchw(y), act, path)
+        return y
+    # tensor-core path consumes / produces the split NHWC planes
+    xs = torch.empty((2, B, H, W, x.shape[1]), device=x.device, dtype=torch.bfloat16)
+    C.check(_lib.hesic_convert(C.ref(C.nchw(x)), C.ref(C.split(xs)), C.OP_COPY, C.stream()))
+    yn = torch.empty((B, Ho, Wo, plan.geom[1]), device=x.device, dtype=torch.float32)
+    try:
+        plan.run(C.split(xs), C.nhwc(yn), act, path)
+    except NotImplementedError:
+        if path == C.PATH_TC:
+            raise
+        plan.run(C.nchw(x), C.nchw(y), act, C.PATH_SIMT)
+        return y
+    C.check(_lib.hesic_convert(C.ref(C.nhwc(yn)), C.ref(C.nchw(y)), C.OP_COPY, C.stream()))
+    return y
+
+
+def gdn(x, beta, gamma, inverse=False, beta_min=1e-6):
+    """compressai/layers/gdn.py:55-70 with the raw (un-reparametrised) parameters."""
+    x = _f32(x)
+    C.require_cuda(beta, gamma)
+    y = torch.empty_like(x)
+    C.check(_lib.hesic_gdn(C.ref(C.nchw(x)), C.ref(C.nchw(y)), C.ptr(_f32(beta.detach())), C.ptr(_f32(gamma.detach())),
+                           int(inverse), float(beta_min), C.stream()))
+    return y
+
+
+def warp_perspective(src, M, dsize, align_corners=True, out=None):
+    """kornia.warp_perspective(src, M, dsize) -- bilinear, zero padding."""
+    src = _f32(src)
+    M = _f32(M)
+    if M.shape != (src.shape[0], 3, 3):
+        raise ValueError(f"warp_perspective: M must be [B,3,3], got {tuple(M.shape)}")
+    if out is None:
+        out = torch.empty((src.shape[0], src.shape[1], int(dsize[0]), int(dsize[1])), device=src.device, dtype=torch.float32)
+    C.check(_lib.hesic_warp_perspective(C.ref(C.nchw(src)), C.ptr(M), C.ref(C.nchw(out)), int(bool(align_corners)), C.stream()))
+    return out
+
+
+def eb_pack(matrices, biases, factors, quantiles):
+    """Pre-activate the EntropyBottleneck parameters into the 60-float-per-channel device table."""
+    Cn = quantiles.shape[0]
+    ts = [_f32(t.detach()) for t in list(matrices) + list(biases) + list(factors)]
+    q = _f32(quantiles.detach())
+    out = torch.empty((Cn, C.EB_PARAMS), device=q.device, dtype=torch.float32)
+    arr = lambda xs: (ctypes.c_void_p * len(xs))(*[t.data_ptr() for t in xs])
+    C.check(_lib.hesic_eb_pack(arr(ts[0:5]), arr(ts[5:10]), arr(ts[10:14]), C.ptr(q), Cn, C.ptr(out), C.stream()))
+    return out
+
+
+def entropy_bottleneck(z, params, likelihood_bound=1e-9, log2_acc=None):
+    """EntropyBottleneck.forward (eval): returns (z_hat, likelihood), NCHW fp32."""
+    z = _f32(z)
+    z_hat = torch.empty_like(z)
+    lik = torch.empty_like(z)
+    C.check(_lib.hesic_entropy_bottleneck(C.ref(C.nchw(z)), C.ptr(params), float(likelihood_bound), C.ref(C.nchw(z_hat)),
+                                          C.ref(C.nchw(lik)), C.ptr(log2_acc), C.stream()))
+    return z_hat, lik
+
+
+def gaussian_mixture_conditional(y, scales, means, weights, K, scale_bound=0.11, likelihood_bound=1e-9, log2_acc=None):
+    """GaussianMixtureConditional.forward (eval).  weights: [B, K*M, 1, 1]."""
+    y, scales, means = _f32(y), _f32(scales), _f32(means)
+    w = _f32(weights).reshape(y.shape[0], -1)
+    if w.shape[1] != K * y.shape[1]:
+        raise ValueError("weights must have K*M channels")
+    y_hat = torch.empty_like(y)
+    lik = torch.empty_like(y)
+    C.check(_lib.hesic_gaussian_conditional(C.ref(C.nchw(y)), C.ref(C.nchw(scales)), C.ref(C.nchw(means)), C.ptr(w), K, 1,
+                                            float(scale_bound), float(likelihood_bound), C.ref(C.nchw(y_hat)),
+                                            C.ref(C.nchw(lik)), C.ptr(log2_acc), C.stream()))
+    return y_hat, lik
+
+
+def gaussian_conditional(y, scales, means=None, scale_bound=0.11, likelihood_bound=1e-9, log2_acc=None):
+    """GaussianConditional.forward (eval)."""
+    y, scales = _f32(y), _f32(scales)
+    mu = C.nchw(_f32(means)) if means is not None else C.null()
+    y_hat = torch.empty_like(y)
+    lik = torch.empty_like(y)
+    C.check(_lib.hesic_gaussian_conditional(C.ref(C.nchw(y)), C.ref(C.nchw(scales)), C.ref(mu), None, 1, 0,
+                                            float(scale_bound), float(likelihood_bound), C.ref(C.nchw(y_hat)),
+                                            C.ref(C.nchw(lik)), C.ptr(log2_acc), C.stream()))
+    return y_hat, lik
+
+
+def spatial_max(x):
+    """spatial_pool2d (newnet1.py:441-453): [B,C,H,W] -> [B,C,1,1] fp32."""
+    x = _f32(x)
+    out = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=torch.float32)
+    C.check(_lib.hesic_spatial_max(C.ref(C.nchw(x)), C.ptr(out), C.stream()))
+    return out.reshape(x.shape[0], x.shape[1], 1, 1)
+
+
+def mixture_weights(pooled, w1x1, bias, K, M):
+    """LeakyReLU -> conv1x1 -> softmax over the K components: [B,K*M(,1,1)] -> [B,K*M,1,1]."""
+    B = pooled.shape[0]
+    p = _f32(pooled).reshape(B, K * M)
+    out = torch.empty((B, K * M), device=p.device, dtype=torch.float32)
+    C.check(_lib.hesic_mixture_weights(C.ptr(p), C.ptr(_f32(w1x1.detach()).reshape(K * M, K * M)),
+                                       C.ptr(_f32(bias.detach()) if bias is not None else None), B, K, M, C.ptr(out), C.stream()))
+    return out.reshape(B, K * M, 1, 1)
+
+
+def upsample_bilinear(x, scale):
+    x = _f32(x)
+    y = torch.empty((x.shape[0], x.shape[1], x.shape[2] * scale, x.shape[3] * scale), device=x.device, dtype=torch.float32)
+    C.check(_lib.hesic_upsample_bilinear(C.ref(C.nchw(x)), C.ref(C.nchw(y)), int(scale), C.stream()))
+    return y
+
+
+def round_half_even(x):
+    x = _f32(x)
+    y = torch.empty_like(x)
+    C.check(_lib.hesic_convert(C.ref(C.nchw(x)), C.ref(C.nchw(y)), C.OP_ROUND, C.stream()))
+    return y
+
+
+def prepare_symbols(x, means=None):
+    """int32 symbols = round_half_even(x - means), [B, C*H*W] (EntropyModel.compress prep).
+    ``means``: None, a [1,C,1,1] / [C] per-channel tensor, or a full tensor like x."""
+    x = _f32(x)
+    B = x.shape[0]
+    out = torch.empty((B, x[0].numel()), device=x.device, dtype=torch.int32)
+    cm, full = None, None
+    if means is not None:
+        if means.numel() == x.shape[1]:
+            cm = _f32(means.detach()).reshape(-1)
+        elif means.shape == x.shape:
+            full = C.nchw(_f32(means))
+        else:
+            raise ValueError("Invalid means parameters")
+    C.check(_lib.hesic_prepare_symbols(C.ref(C.nchw(x)), C.ptr(cm), C.ref(full) if full is not None else None, C.ptr(out),
+                                       C.stream()))
+    return out
+
+
+def build_indexes_channel(size, device):
+    B, Cn, H, W = size
+    out = torch.empty((B, Cn, H, W), device=device, dtype=torch.int32)
+    C.check(_lib.hesic_build_indexes_channel(B, Cn, H, W, C.ptr(out), C.stream()))
+    return out
+
+
+def build_indexes_scale(scales, table, scale_bound=0.11):
+    scales = _f32(scales)
+    table = _f32(table)
+    out = torch.empty(scales.shape, device=scales.device, dtype=torch.int32)
+    C.check(_lib.hesic_build_indexes_scale(C.ref(C.nchw(scales)), C.ptr(table), table.numel(), float(scale_bound),
+                                           C.ptr(out), C.stream()))
+    return out
+
+
+def sum_squared_error(a, b, acc):
+    a, b = _f32(a), _f32(b)
+    C.check(_lib.hesic_sum_squared_error(C.ref(C.nchw(a)), C.ref(C.nchw(b)), C.ptr(acc), C.stream()))
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side coder (numpy arrays; no device involved)
+def pmf_to_quantized_cdf(pmf, precision=16):
+    pmf = np.ascontiguousarray(pmf, dtype=np.float32)
+    cdf = np.zeros(pmf.size + 1, dtype=np.uint32)
+    C.check(_lib.hesic_pmf_to_quantized_cdf(pmf.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), pmf.size, int(precision),
+                                            cdf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))))
+    return cdf
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class RansEncoderHandle:
+    def __init__(self):
+        self.h = _lib.hesic_rans_encoder_create()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.hesic_rans_encoder_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def push(self, symbols, indexes, cdfs, cdf_sizes, offsets):
+        s, i, c, z, o = _i32(symbols).reshape(-1), _i32(indexes).reshape(-1), _i32(cdfs), _i32(cdf_sizes), _i32(offsets)
+        if s.size != i.size:
+            raise ValueError("symbols and indexes must have the same length")
+        if c.ndim != 2 or z.size != c.shape[0] or o.size != c.shape[0]:
+            raise ValueError("cdfs must be [n_cdfs, pitch] with matching sizes/offsets")
+        C.check(_lib.hesic_rans_encoder_push(self.h, s.ctypes.data, i.ctypes.data, s.size, c.ctypes.data, c.shape[0],
+                                             c.shape[1], z.ctypes.data, o.ctypes.data))
+
+    def flush(self):
+        n = _lib.hesic_rans_encoder_flush(self.h, None, 0)
+        if n < 0:
+            C.check(int(n))
+        buf = np.empty(n, dtype=np.uint8)
+        n2 = _lib.hesic_rans_encoder_flush(self.h, buf.ctypes.data, n)
+        assert n2 == n
+        return buf.tobytes()
+
+
+class RansDecoderHandle:
+    def __init__(self):
+        self.h = _lib.hesic_rans_decoder_create()
+        self._buf = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.hesic_rans_decoder_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_stream(self, data):
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        C.check(_lib.hesic_rans_decoder_set_stream(self.h, buf.ctypes.data, buf.size))
+
+    def decode(self, indexes, cdfs, cdf_sizes, offsets):
+        i, c, z, o = _i32(indexes).reshape(-1), _i32(cdfs), _i32(cdf_sizes), _i32(offsets)
+        out = np.empty(i.size, dtype=np.int32)
+        C.check(_lib.hesic_rans_decoder_decode(self.h, i.ctypes.data, i.size, c.ctypes.data, c.shape[0], c.shape[1],
+                                               z.ctypes.data, o.ctypes.data, out.ctypes.data))
+        return out

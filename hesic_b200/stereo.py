@@ -1,0 +1,403 @@
+"""Stereo codec modules with the reference's interface (ywz/mywork/newnet1.py,
+newnet1_joint.py, .trash/newnet9.py): same class names, constructor arguments,
+attribute / ``state_dict`` names and ``forward`` return values, so the authors'
+checkpoints load strictly and the drivers run unchanged.  ``HSIC.forward`` hands
+the whole pass to ``HesicEngine``; the sub-modules' own ``forward`` methods work
+stand-alone on NCHW fp32 CUDA tensors through the operator-level kernels.
+
+``compressai`` here is the stand-in under ``hesic_b200/compat/site``
+(``hesic_b200.compat.install()`` must have run, which the ``newnet*`` modules
+in that directory guarantee by construction).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from compressai.entropy_models import EntropyBottleneck, GaussianConditional, GaussianMixtureConditional
+from compressai.layers import GDN, MaskedConv2d, ResidualBlock, conv3x3
+from compressai.models.utils import conv, deconv
+
+from . import _capi as C
+from . import functional as F
+from .engine import HesicEngine
+
+
+class CompressionModel(nn.Module):
+    """Two-bottleneck base class of the stereo models (newnet1.py:36-106)."""
+
+    def __init__(self, entropy_bottleneck_channels, init_weights=True):
+        super().__init__()
+        self.entropy_bottleneck1 = EntropyBottleneck(entropy_bottleneck_channels)
+        self.entropy_bottleneck2 = EntropyBottleneck(entropy_bottleneck_channels)
+        if init_weights:
+            self._initialize_weights()
+
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def _initialize_weights(self):
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    def forward(self, *args):
+        raise NotImplementedError()
+
+    def parameters(self):
+        for m in self.children():
+            if isinstance(m, EntropyBottleneck):
+                continue
+            for p in m.parameters():
+                yield p
+
+    def aux_parameters(self):
+        for m in self.children():
+            if isinstance(m, EntropyBottleneck):
+                for p in m.parameters():
+                    yield p
+
+    def update(self, force=False):
+        for m in self.children():
+            if isinstance(m, EntropyBottleneck):
+                m.update(force=force)
+
+
+class RateDistortionLoss(nn.Module):
+    """newnet1.py:110-129 (single-image form kept for name compatibility)."""
+
+    def __init__(self, lmbda=1e-2):
+        super().__init__()
+        self.mse = nn.MSELoss()
+        self.lmbda = lmbda
+
+    def forward(self, output, target):
+        N, _, H, W = target.size()
+        num_pixels = N * H * W
+        out = {}
+        out["bpp_loss"] = sum((torch.log(lk).sum() / (-math.log(2) * num_pixels)) for lk in output["likelihoods"].values())
+        out["mse_loss"] = self.mse(output["x_hat"], target)
+        out["loss"] = self.lmbda * 255 ** 2 * out["mse_loss"] + out["bpp_loss"]
+        return out
+
+
+class AverageMeter:
+    """Running average (newnet1.py:132-144)."""
+
+    def __init__(self):
+        self.val = 0
+        self.avg = 0
+        self.sum = 0
+        self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+class encode_hyper(nn.Module):
+    """|y| -> conv s1, ReLU, conv s2, ReLU, conv s2 (newnet1.py:420-437)."""
+
+    def __init__(self, N, M):
+        super().__init__()
+        self.encode_hyper = nn.Sequential(conv(M, N, kernel_size=5, stride=1), nn.ReLU(), conv(N, N, kernel_size=5),
+                                          nn.ReLU(), conv(N, N, kernel_size=5))
+
+    def forward(self, y):
+        return self.encode_hyper(torch.abs(y))
+
+
+class spatial_pool2d(nn.Module):
+    """Global spatial maximum per (b, c) (newnet1.py:441-453), one reduction kernel."""
+
+    def forward(self, X):
+        C.require_cuda(X)
+        return F.spatial_max(X)
+
+
+def _mix_softmax_head(seq, x, K, M):
+    """deconv/conv, LeakyReLU, conv, global max, LeakyReLU, conv1x1, softmax over K."""
+    t = seq[2](nn.functional.leaky_relu(seq[0](x)))
+    pooled = F.spatial_max(t)
+    return F.mixture_weights(pooled, seq[5].weight, seq[5].bias, K, M)
+
+
+class gmm_hyper_y1(nn.Module):
+    """z1_hat -> (sigma, means, weights) of the K-component mixture (newnet1.py:456-514)."""
+
+    def __init__(self, N, M, K):
+        super().__init__()
+        self.N, self.M, self.K = N, M, K
+        self.gmm_sigma = nn.Sequential(deconv(N, N, kernel_size=5), nn.ReLU(), deconv(N, N, kernel_size=5), nn.ReLU(),
+                                       conv(N, M * K, kernel_size=5, stride=1), nn.ReLU())
+        self.gmm_means = nn.Sequential(deconv(N, N, kernel_size=5), nn.LeakyReLU(), deconv(N, N, kernel_size=5),
+                                       nn.LeakyReLU(), conv(N, M * K, kernel_size=5, stride=1))
+        self.gmm_weights = nn.Sequential(deconv(N, N, kernel_size=5), nn.LeakyReLU(), deconv(N, M * K, kernel_size=5),
+                                         spatial_pool2d(), nn.LeakyReLU(), conv(M * K, M * K, kernel_size=1, stride=1))
+
+    def forward(self, z1):
+        return self.gmm_sigma(z1), self.gmm_means(z1), _mix_softmax_head(self.gmm_weights, z1, self.K, self.M)
+
+
+class gmm_hyper_y2(nn.Module):
+    """(z2_hat upsampled x4, y1) -> (sigma, means, weights) (newnet1.py:517-577)."""
+
+    def __init__(self, N, M, K):
+        super().__init__()
+        self.N, self.M, self.K = N, M, K
+        self.upsample_layer = nn.UpsamplingBilinear2d(scale_factor=4)
+        self.gmm_sigma = nn.Sequential(conv(N + M, N, kernel_size=5, stride=1), nn.ReLU(),
+                                       conv(N, N, kernel_size=5, stride=1), nn.ReLU(),
+                                       conv(N, M * K, kernel_size=5, stride=1), nn.ReLU())
+        self.gmm_means = nn.Sequential(conv(N + M, N, kernel_size=5, stride=1), nn.LeakyReLU(),
+                                       conv(N, N, kernel_size=5, stride=1), nn.LeakyReLU(),
+                                       conv(N, M * K, kernel_size=5, stride=1))
+        self.gmm_weights = nn.Sequential(conv(N + M, N, kernel_size=5, stride=1), nn.LeakyReLU(),
+                                         conv(N, M * K, kernel_size=5, stride=1), spatial_pool2d(), nn.LeakyReLU(),
+                                         conv(M * K, M * K, kernel_size=1, stride=1))
+
+    def forward(self, z2, y1):
+        C.require_cuda(z2, y1)
+        cat_in = torch.cat((F.upsample_bilinear(z2, 4), y1), dim=-3)
+        return (self.gmm_sigma(cat_in), self.gmm_means(cat_in),
+                _mix_softmax_head(self.gmm_weights, cat_in, self.K, self.M))
+
+
+class Encoder1(nn.Module):
+    """Left-view analysis transform (newnet1.py:580-601)."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__()
+        self.g_a_conv1 = conv(3, N)
+        self.g_a_gdn1 = GDN(N)
+        self.g_a_conv2 = conv(N, N)
+        self.g_a_gdn2 = GDN(N)
+        self.g_a_conv3 = conv(N, N)
+        self.g_a_gdn3 = GDN(N)
+        self.g_a_conv4 = conv(N, M)
+
+    def forward(self, x):
+        g1 = self.g_a_gdn1(self.g_a_conv1(x))
+        g2 = self.g_a_gdn2(self.g_a_conv2(g1))
+        g3 = self.g_a_gdn3(self.g_a_conv3(g2))
+        return self.g_a_conv4(g3), g1, g2, g3
+
+
+class Decoder1(nn.Module):
+    """Left-view synthesis transform (newnet1.py:603-624)."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__()
+        self.g_s_conv1 = deconv(M, N)
+        self.g_s_gdn1 = GDN(N, inverse=True)
+        self.g_s_conv2 = deconv(N, N)
+        self.g_s_gdn2 = GDN(N, inverse=True)
+        self.g_s_conv3 = deconv(N, N)
+        self.g_s_gdn3 = GDN(N, inverse=True)
+        self.g_s_conv4 = deconv(N, 3)
+
+    def forward(self, y_hat):
+        g1 = self.g_s_gdn1(self.g_s_conv1(y_hat))
+        g2 = self.g_s_gdn2(self.g_s_conv2(g1))
+        g3 = self.g_s_gdn3(self.g_s_conv3(g2))
+        return self.g_s_conv4(g3), g1, g2, g3
+
+
+class Encoder2(nn.Module):
+    """Right-view analysis: cat(x1_warp, x2) -> conv(6->3) -> GDN(3) -> g_a stack (newnet1.py:627-655)."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__()
+        self.pre_conv = conv(6, 3, stride=1)
+        self.pre_gdn = GDN(3)
+        self.g_a_conv1 = conv(3, N)
+        self.g_a_gdn1 = GDN(N)
+        self.g_a_conv2 = conv(N, N)
+        self.g_a_gdn2 = GDN(N)
+        self.g_a_conv3 = conv(N, N)
+        self.g_a_gdn3 = GDN(N)
+        self.g_a_conv4 = conv(N, M)
+
+    def forward(self, x1_warp, x2):
+        x = self.pre_gdn(self.pre_conv(torch.cat((x1_warp, x2), dim=-3)))
+        x = self.g_a_gdn1(self.g_a_conv1(x))
+        x = self.g_a_gdn2(self.g_a_conv2(x))
+        x = self.g_a_gdn3(self.g_a_conv3(x))
+        return self.g_a_conv4(x)
+
+
+class Decoder2(nn.Module):
+    """Right-view synthesis: g_s stack -> IGDN(3) -> cat(., x1_hat_warp) -> deconv(6->3, s1)
+    (newnet1.py:657-692)."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__()
+        self.g_s_conv1 = deconv(M, N)
+        self.g_s_gdn1 = GDN(N, inverse=True)
+        self.g_s_conv2 = deconv(N, N)
+        self.g_s_gdn2 = GDN(N, inverse=True)
+        self.g_s_conv3 = deconv(N, N)
+        self.g_s_gdn3 = GDN(N, inverse=True)
+        self.g_s_conv4 = deconv(N, 3)
+        self.after_gdn = GDN(3, inverse=True)
+        self.after_conv = deconv(6, 3, stride=1)
+
+    def forward(self, y_hat, x1_hat_warp):
+        x = self.g_s_gdn1(self.g_s_conv1(y_hat))
+        x = self.g_s_gdn2(self.g_s_conv2(x))
+        x = self.g_s_gdn3(self.g_s_conv3(x))
+        x = self.after_gdn(self.g_s_conv4(x))
+        return self.after_conv(torch.cat((x, x1_hat_warp), dim=-3))
+
+
+class _HSICBase(CompressionModel):
+    _variant = "newnet1"
+
+    def __init__(self, N=128, M=192, K=5, **kwargs):
+        super().__init__(entropy_bottleneck_channels=N, **kwargs)
+        self.gaussian1 = GaussianMixtureConditional(K=K)
+        self.gaussian2 = GaussianMixtureConditional(K=K)
+        self.N, self.M, self.K = int(N), int(M), int(K)
+        self.encoder1 = Encoder1(N, M)
+        self.encoder2 = Encoder2(N, M)
+        self.decoder1 = Decoder1(N, M)
+        self.decoder2 = Decoder2(N, M)
+        self._build_hyper(N, M, K)
+        object.__setattr__(self, "_engine", None)
+
+    def _build_hyper(self, N, M, K):
+        self._h_a1 = encode_hyper(N=N, M=M)
+        self._h_a2 = encode_hyper(N=N, M=M)
+        self._h_s1 = gmm_hyper_y1(N=N, M=M, K=K)
+        self._h_s2 = gmm_hyper_y2(N=N, M=M, K=K)
+
+    @property
+    def hesic_engine(self):
+        if self._engine is None:
+            object.__setattr__(self, "_engine", HesicEngine(self, self._variant))
+        return self._engine
+
+    def forward(self, x1, x2, h_matrix):
+        """The stereo forward pass (newnet1.py:724-783), eval mode, on the B200 kernels."""
+        if self.training:
+            raise NotImplementedError("hesic_b200: HSIC.forward is the inference path; call .eval() first")
+        return self.hesic_engine.forward(x1, x2, h_matrix)
+
+    # EntropyModel helpers the reference also hangs on the model (newnet1.py:786-821)
+    def _quantize(self, inputs, mode, means=None):
+        return self.gaussian1._quantize(inputs, mode, means)
+
+    def _standardized_cumulative(self, inputs):
+        return 0.5 * torch.erfc(float(-(2 ** -0.5)) * inputs)
+
+    def compress(self, *args, **kwargs):
+        raise NotImplementedError("hesic_b200: the range-coder file codec (newnet1.py:823-1273) is the 'next' row of "
+                                  "SURVEY.md section 8f; EntropyBottleneck.compress/decompress are available")
+
+    decompress = compress
+
+
+class HSIC(_HSICBase):
+    """HESIC (ywz/mywork/newnet1.py:698-783), with the "twiceLeft" re-encode of the warped x1_hat."""
+    _variant = "newnet1"
+
+
+class HSIC_NoTwiceLeft(_HSICBase):
+    """ywz/mywork/.trash/newnet9.py:620-661 -- what test3real.py imports: view-2 mixture conditioned on
+    y1_hat directly, and no y*_hat in the returned dict."""
+    _variant = "newnet9"
+
+
+class HSIC_Joint(_HSICBase):
+    """HESIC+ (ywz/mywork/newnet1_joint.py:586-753): mean-scale hyperprior + masked-conv context model,
+    with the warped left latent concatenated into the right view's entropy parameters."""
+    _variant = "joint"
+
+    def _build_hyper(self, N, M, K):
+        def h_a():
+            return nn.Sequential(conv(M, N, stride=1, kernel_size=3), nn.LeakyReLU(inplace=True),
+                                 conv(N, N, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                 conv(N, N, stride=2, kernel_size=5))
+
+        def h_s():
+            return nn.Sequential(deconv(N, M, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                 deconv(M, M * 3 // 2, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                 conv(M * 3 // 2, M * 2, stride=1, kernel_size=3))
+
+        def ep(cin):
+            from hesic_b200.modules import Conv2d
+            return nn.Sequential(Conv2d(cin, M * 10 // 3, 1), nn.LeakyReLU(inplace=True),
+                                 Conv2d(M * 10 // 3, M * 8 // 3, 1), nn.LeakyReLU(inplace=True),
+                                 Conv2d(M * 8 // 3, M * 6 // 3, 1))
+
+        self.h_a1 = h_a()
+        self.h_s1 = h_s()
+        self.entropy_parameters1 = ep(M * 12 // 3)
+        self.context_prediction1 = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
+        self.gaussian_conditional1 = GaussianConditional(None)
+        self.h_a2 = h_a()
+        self.h_s2 = h_s()
+        self.entropy_parameters2 = ep(5 * M)
+        self.context_prediction2 = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
+        self.gaussian_conditional2 = GaussianConditional(None)
+
+
+# ---------------------------------------------------------------------------------------------
+# Independent_EN: cross-quality enhancement that follows HSIC in test3real.py:186
+# (newnet1.py:272-311, 1278-1300) -- SURVEY.md 8f rank 1.
+class Enhancement_Block(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.RB1 = ResidualBlock(32, 32)
+        self.RB2 = ResidualBlock(32, 32)
+        self.RB3 = ResidualBlock(32, 32)
+
+    def forward(self, x):
+        return self.RB3(self.RB2(self.RB1(x))) + x
+
+
+class Enhancement(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = conv3x3(6, 32)
+        self.EB1 = Enhancement_Block()
+        self.EB2 = Enhancement_Block()
+        self.EB3 = Enhancement_Block()
+        self.conv2 = conv3x3(32, 3)
+
+    def forward(self, x, x_another_warp):
+        out = self.conv1(torch.cat((x, x_another_warp), dim=-3))
+        out = self.EB3(self.EB2(self.EB1(out)))
+        return self.conv2(out) + x
+
+
+class Independent_EN(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.EH1 = Enhancement()
+        self.EH2 = Enhancement()
+
+    def forward(self, x1_hat, x2_hat, h_matrix):
+        C.require_cuda(x1_hat, x2_hat, h_matrix)
+        size = (x1_hat.size(-2), x1_hat.size(-1))
+        x1_hat_warp = F.warp_perspective(x1_hat, h_matrix, size)
+        x2_hat_warp = F.warp_perspective(x2_hat, torch.inverse(h_matrix), size)
+        return {"x1_hat": self.EH1(x1_hat, x2_hat_warp), "x2_hat": self.EH2(x2_hat, x1_hat_warp)}
+
+
+class GMM_together(nn.Module):
+    """HSIC followed by Independent_EN (newnet1.py:1304-1321)."""
+
+    def __init__(self, N=128, M=192, K=5, **kwargs):
+        super().__init__()
+        self.m1 = HSIC(N, M, K)
+        self.m2 = Independent_EN()
+
+    def forward(self, x1, x2, h):
+        out1 = self.m1(x1, x2, h)
+        out2 = self.m2(out1["x1_hat"], out1["x2_hat"], h)
+        return {"x1_hat": out2["x1_hat"], "x2_hat": out2["x2_hat"], "likelihoods": out1["likelihoods"]}

@@ -1,0 +1,186 @@
+/* hesic_b200 -- C ABI of the B200-native HESIC stereo-compression forward path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The
+ * Python host side (hesic_b200/compat: `compressai.*`, `newnet1`, `newnet1_joint`,
+ * `newnet9`, `kornia` stand-in) binds it with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - every pointer marked "dev" is a CUDA device pointer on the current device;
+ *    "host" pointers are ordinary host memory;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    all device entry points are asynchronous on that stream;
+ *  - return value 0 = success, <0 = error (HESIC_E_*); hesic_last_error() gives the
+ *    message for the calling thread.  There is NO CPU fallback: calling a device entry
+ *    point without a usable sm_100 device returns HESIC_E_CUDA.
+ */
+#ifndef HESIC_B200_H_
+#define HESIC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HESIC_ABI_VERSION 1
+
+enum {
+  HESIC_OK = 0,
+  HESIC_E_INVALID = -1,   /* bad argument (maps to ValueError on the Python side) */
+  HESIC_E_CUDA = -2,      /* CUDA runtime / driver error, or no sm_100 device      */
+  HESIC_E_UNSUPPORTED = -3,
+  HESIC_E_OVERFLOW = -4   /* output buffer too small                               */
+};
+
+/* Activation layouts in HBM.  SPLIT is the native inter-layer format of the conv stack:
+ * two bf16 planes (hi, lo) with value = float(hi) + float(lo), i.e. a 16-bit-mantissa
+ * decomposition of the fp32 value that feeds the bf16x3 tcgen05 path without conversion. */
+enum { HESIC_FMT_NCHW_F32 = 0, HESIC_FMT_NHWC_F32 = 1, HESIC_FMT_NHWC_SPLIT = 2 };
+
+typedef struct {
+  void *p0;        /* dev: float data, or bf16 'hi' plane, already offset to channel 0 of the view */
+  void *p1;        /* dev: bf16 'lo' plane (SPLIT), else NULL                                        */
+  int32_t fmt;     /* HESIC_FMT_*                                                                    */
+  int32_t B, C, H, W;
+  int32_t Cs;      /* channels of the underlying buffer (>= C): lets a producer write a channel
+                      slice of a concatenation buffer (torch.cat on the reference side)            */
+} hesic_tensor;
+
+enum { HESIC_ACT_NONE = 0, HESIC_ACT_RELU = 1, HESIC_ACT_LEAKY_RELU = 2 /* slope 0.01 */ };
+enum { HESIC_PATH_AUTO = 0, HESIC_PATH_SIMT = 1, HESIC_PATH_TCGEN05 = 2 };
+
+int hesic_abi_version(void);
+const char *hesic_last_error(void);
+/* 0 when a sm_100 device is current and the kernels can launch; fills name (may be NULL). */
+int hesic_device_check(char *name, int name_len);
+/* number of kernels this library launched since the last reset (bench.py "gpu_launches") */
+int64_t hesic_launch_count(int reset);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution / transposed convolution (+ bias, activation, optional fused GDN).
+ * Replaces nn.Conv2d / nn.ConvTranspose2d as built by compressai/models/utils.py:104-118
+ * (`conv`, `deconv`), MaskedConv2d (compressai/layers/layers.py:21-45) and the GDN that follows
+ * them in newnet1.py:580-692 (compressai/layers/gdn.py:55-70).
+ */
+typedef struct hesic_conv hesic_conv;
+
+hesic_conv *hesic_conv_create(int Cin, int Cout, int kh, int kw, int stride, int pad, int transposed,
+                              int output_padding);
+void hesic_conv_destroy(hesic_conv *c);
+/* weight: dev fp32 in the reference layout (conv [Cout,Cin,kh,kw]; transposed [Cin,Cout,kh,kw]);
+ * bias: dev fp32 [Cout] or NULL; mask: dev fp32 like weight or NULL (MaskedConv2d). Packs the
+ * operand planes the kernels read (fp32 tap-major for the SIMT path, bf16 hi/lo K-major per tap for
+ * tcgen05). */
+int hesic_conv_load(hesic_conv *c, const float *weight, const float *bias, const float *mask, void *stream);
+/* Attach a GDN/IGDN to the conv epilogue. beta [Cout], gamma [Cout,Cout] are the RAW parameters of
+ * compressai.layers.GDN; the non-negative reparametrisation (ops/parametrizers.py:41-44) is applied
+ * on the device.  Pass NULLs to detach. */
+int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float *gamma, int inverse, float beta_min,
+                       void *stream);
+int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, int path,
+                       void *stream);
+
+/* Stand-alone GDN (compressai/layers/gdn.py:55-70) with raw parameters, any C. */
+int hesic_gdn(const hesic_tensor *x, const hesic_tensor *y, const float *beta, const float *gamma, int inverse,
+              float beta_min, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * kornia.warp_perspective(src, M, dsize) as called at newnet1.py:746,753,767,1287,1291:
+ * dst(x,y) = bilinear(src, M^-1 (x,y,1)), zero padding, kornia's normalise/invert/denormalise
+ * arithmetic, align_corners selectable (1 = the convention used throughout this repository).
+ * M: dev fp32 [B,3,3].  src/dst: NCHW fp32 (dst may be a channel slice). */
+int hesic_warp_perspective(const hesic_tensor *src, const float *M, const hesic_tensor *dst, int align_corners,
+                           void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * EntropyBottleneck.forward, eval mode (compressai/entropy_models/entropy_models.py:384-411,
+ * 350-382): z_hat = round(z - median) + median; likelihood = |sigmoid(s*u) - sigmoid(s*l)| clamped.
+ * params: dev fp32, per channel 58 floats packed as
+ *   [softplus(M0) 3 | b0 3 | tanh(f0) 3 | softplus(M1) 9 | b1 3 | tanh(f1) 3 | M2 9 | b2 3 | f2 3 |
+ *    M3 9 | b3 3 | f3 3 | softplus(M4) 3 | b4 1 | median 1 | pad 1]  (hesic_eb_pack builds it from the
+ * raw _matrices/_biases/_factors/quantiles tensors).
+ * z_hat / lik may be NULL-p0 tensors to skip an output.  log2_sum: dev double[1] accumulator for
+ * sum(log2 lik) (the bpp partial of ywz/mywork/test3real.py:115-122) or NULL. */
+#define HESIC_EB_PARAMS_PER_CHANNEL 60
+int hesic_eb_pack(const float *const *matrices /*5*/, const float *const *biases /*5*/,
+                  const float *const *factors /*4*/, const float *quantiles, int C, float *params_out,
+                  void *stream);
+int hesic_entropy_bottleneck(const hesic_tensor *z, const float *params, float likelihood_bound,
+                             const hesic_tensor *z_hat, const hesic_tensor *lik, double *log2_sum, void *stream);
+
+/* GaussianMixtureConditional.forward, eval mode (entropy_models.py:661-702): y_hat = round(y);
+ * lik = sum_k w[k*M+m] * (Phi((.5-|y_hat-mu|)/s) - Phi((-.5-|y_hat-mu|)/s)), s = max(sigma, bound).
+ * scales/means: [B, K*M, H, W]; weights: dev fp32 [B, K*M].  K = 1 with weights == NULL is
+ * GaussianConditional.forward (entropy_models.py:528-554): y_hat = round(y - mu) + mu (mu may be
+ * absent: means->p0 == NULL). */
+int hesic_gaussian_conditional(const hesic_tensor *y, const hesic_tensor *scales, const hesic_tensor *means,
+                               const float *weights, int K, int mixture, float scale_bound,
+                               float likelihood_bound, const hesic_tensor *y_hat, const hesic_tensor *lik,
+                               double *log2_sum, void *stream);
+
+/* spatial_pool2d (newnet1.py:441-453) + LeakyReLU + conv1x1(K*M -> K*M) + softmax over the K
+ * components (newnet1.py:498-512,572-574).  x: [B, K*M, H, W]; w1x1: dev fp32 [K*M, K*M] (the
+ * reference's [Cout,Cin,1,1]); out: dev fp32 [B, K*M].  pooled (dev [B,K*M], may be NULL) receives
+ * the raw spatial maximum. */
+int hesic_spatial_max(const hesic_tensor *x, float *out_max, void *stream);
+int hesic_mixture_weights(const float *pooled, const float *w1x1, const float *bias, int B, int K, int M,
+                          float *out, void *stream);
+
+/* nn.UpsamplingBilinear2d(scale_factor=s) (align_corners=True; newnet1.py:524,564). */
+int hesic_upsample_bilinear(const hesic_tensor *x, const hesic_tensor *y, int scale, void *stream);
+
+/* Layout / format conversion with an optional pointwise op: 0 copy, 1 abs (newnet1.py:435),
+ * 2 round-half-even (EntropyModel._quantize 'dequantize', entropy_models.py:98-125). */
+enum { HESIC_OP_COPY = 0, HESIC_OP_ABS = 1, HESIC_OP_ROUND = 2 };
+int hesic_convert(const hesic_tensor *x, const hesic_tensor *y, int op, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Symbol / CDF-index preparation for the host rANS coder -- integer outputs, bit-exact with
+ * EntropyModel.compress (entropy_models.py:165-196): symbols = int32(round_half_even(x - mean)),
+ * flattened per image in C,H,W order.  means: NULL, per-channel (dev fp32 [C]) or a full tensor.
+ * indexes: EntropyBottleneck._build_indexes (entropy_models.py:413-418): channel id; or
+ * GaussianConditional.build_indexes (entropy_models.py:556-562):
+ *   (n_table-1) - #{ s in table[:-1] : max(scale, bound) <= s }.
+ * out_*: dev int32 [B, C*H*W]. */
+int hesic_prepare_symbols(const hesic_tensor *x, const float *channel_means, const hesic_tensor *means,
+                          int32_t *out_symbols, void *stream);
+int hesic_build_indexes_channel(int B, int C, int H, int W, int32_t *out_indexes, void *stream);
+int hesic_build_indexes_scale(const hesic_tensor *scales, const float *table, int n_table, float scale_bound,
+                              int32_t *out_indexes, void *stream);
+
+/* Rate-distortion partial sums (RateDistortionLoss, ywz/mywork/test3real.py:90-124):
+ * acc[0] += sum((a-b)^2) over all elements (double).  The likelihood kernels above accumulate
+ * sum(log2 p) themselves. */
+int hesic_sum_squared_error(const hesic_tensor *a, const hesic_tensor *b, double *acc, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side entropy coder (stays on the host, as in the reference).
+ * compressai._CXX.pmf_to_quantized_cdf (compressai/cpp_exts/ops/ops.cpp:24-81); cdf_out holds n+1. */
+int hesic_pmf_to_quantized_cdf(const float *pmf, int n, int precision, uint32_t *cdf_out);
+/* compressai.ans.RansEncoder.encode_with_indexes / BufferedRansEncoder (rans_interface.cpp:99-204).
+ * cdfs: host int32 [n_cdfs, cdf_pitch] dense table.  An encoder object buffers symbols across
+ * encode calls until flush (BufferedRansEncoder semantics). */
+typedef struct hesic_rans_encoder hesic_rans_encoder;
+hesic_rans_encoder *hesic_rans_encoder_create(void);
+void hesic_rans_encoder_destroy(hesic_rans_encoder *e);
+int hesic_rans_encoder_push(hesic_rans_encoder *e, const int32_t *symbols, const int32_t *indexes, int64_t n,
+                            const int32_t *cdfs, int n_cdfs, int cdf_pitch, const int32_t *cdf_sizes,
+                            const int32_t *offsets);
+/* returns the number of bytes the stream needs; writes it if out_cap is large enough, else
+ * HESIC_E_OVERFLOW is NOT raised and nothing is consumed: call again with a larger buffer. */
+int64_t hesic_rans_encoder_flush(hesic_rans_encoder *e, uint8_t *out, int64_t out_cap);
+/* compressai.ans.RansDecoder (rans_interface.cpp:206-350): set_stream + decode_stream. */
+typedef struct hesic_rans_decoder hesic_rans_decoder;
+hesic_rans_decoder *hesic_rans_decoder_create(void);
+void hesic_rans_decoder_destroy(hesic_rans_decoder *d);
+int hesic_rans_decoder_set_stream(hesic_rans_decoder *d, const uint8_t *stream, int64_t nbytes);
+int hesic_rans_decoder_decode(hesic_rans_decoder *d, const int32_t *indexes, int64_t n, const int32_t *cdfs,
+                              int n_cdfs, int cdf_pitch, const int32_t *cdf_sizes, const int32_t *offsets,
+                              int32_t *out_symbols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HESIC_B200_H_ */
