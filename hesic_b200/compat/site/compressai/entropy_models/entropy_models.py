@@ -305,7 +305,11 @@ class _GaussianBase(EntropyModel):
         return scipy.stats.norm.ppf(quantile)
 
     def _scale_bound_value(self):
-        return float(self.lower_bound_scale.bound.item())
+        # cached on the host: reading the buffer every forward would be a device->host sync
+        key = (self.lower_bound_scale.bound.data_ptr(), self.lower_bound_scale.bound._version)
+        if getattr(self, "_bound_cache", (None, None))[0] != key:
+            self._bound_cache = (key, float(self.lower_bound_scale.bound.item()))
+        return self._bound_cache[1]
 
     def update_scale_table(self, scale_table, force=False):
         if self._offset.numel() > 0 and not force:

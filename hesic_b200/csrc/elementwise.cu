@@ -30,11 +30,12 @@ __device__ __forceinline__ void block_add_double(double v, double *acc) {
 
 // ---------------------------------------------------------------------------------------------
 // kornia.warp_perspective.  Thread = one destination pixel, all channels.  The 3x3 chain
-// N_dst * M * N_src^-1 and its inverse are evaluated once per block in fp64; per-pixel arithmetic is
-// fp32 in kornia's order (normalised grid -> S*g -> divide -> grid_sample unnormalise -> bilinear).
+// N_dst * M * N_src^-1 and its inverse are evaluated once per block, and the per-pixel sampling
+// coordinate (normalised grid -> S*g -> divide -> grid_sample unnormalise) per thread, both in fp64;
+// the bilinear blend itself is fp32 like grid_sample's.
 __global__ void __launch_bounds__(256) warp_kernel(const TView src, const float *__restrict__ Mx, const TView dst,
                                                   int align_corners) {
-  __shared__ float S[9];
+  __shared__ double S[9];
   const int b = blockIdx.z;
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const float *m = Mx + b * 9;
@@ -58,39 +59,39 @@ __global__ void __launch_bounds__(256) warp_kernel(const TView src, const float 
     double c00 = T[4] * T[8] - T[5] * T[7], c01 = T[5] * T[6] - T[3] * T[8], c02 = T[3] * T[7] - T[4] * T[6];
     double det = T[0] * c00 + T[1] * c01 + T[2] * c02;
     double id = 1.0 / det;
-    S[0] = (float)(c00 * id); S[1] = (float)((T[2] * T[7] - T[1] * T[8]) * id); S[2] = (float)((T[1] * T[5] - T[2] * T[4]) * id);
-    S[3] = (float)(c01 * id); S[4] = (float)((T[0] * T[8] - T[2] * T[6]) * id); S[5] = (float)((T[2] * T[3] - T[0] * T[5]) * id);
-    S[6] = (float)(c02 * id); S[7] = (float)((T[1] * T[6] - T[0] * T[7]) * id); S[8] = (float)((T[0] * T[4] - T[1] * T[3]) * id);
+    S[0] = (c00 * id); S[1] = ((T[2] * T[7] - T[1] * T[8]) * id); S[2] = ((T[1] * T[5] - T[2] * T[4]) * id);
+    S[3] = (c01 * id); S[4] = ((T[0] * T[8] - T[2] * T[6]) * id); S[5] = ((T[2] * T[3] - T[0] * T[5]) * id);
+    S[6] = (c02 * id); S[7] = ((T[1] * T[6] - T[0] * T[7]) * id); S[8] = ((T[0] * T[4] - T[1] * T[3]) * id);
   }
   __syncthreads();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= dst.W || y >= dst.H) return;
-  // torch.linspace(-1, 1, n): symmetric evaluation around the midpoint
-  float stepx = dst.W > 1 ? 2.f / (float)(dst.W - 1) : 0.f;
-  float stepy = dst.H > 1 ? 2.f / (float)(dst.H - 1) : 0.f;
-  float gx = x < dst.W / 2 ? -1.f + stepx * x : 1.f - stepx * (dst.W - 1 - x);
-  float gy = y < dst.H / 2 ? -1.f + stepy * y : 1.f - stepy * (dst.H - 1 - y);
-  float u = gx * S[0] + gy * S[1] + S[2];
-  float v = gx * S[3] + gy * S[4] + S[5];
-  float z = gx * S[6] + gy * S[7] + S[8];
-  float sc = fabsf(z) > 1e-8f ? 1.f / z : 1.f;
+  // Sampling coordinates in fp64: at 512x512 the fp32 chain ((u+1)/2)*(W-1) alone loses ~2e-4 px,
+  // which is visible at the 1e-4 level on textured images; the fp64 evaluation is exact to ~1e-12 px.
+  double gx = dst.W > 1 ? -1.0 + 2.0 * x / (double)(dst.W - 1) : -1.0;
+  double gy = dst.H > 1 ? -1.0 + 2.0 * y / (double)(dst.H - 1) : -1.0;
+  double u = gx * S[0] + gy * S[1] + S[2];
+  double v = gx * S[3] + gy * S[4] + S[5];
+  double z = gx * S[6] + gy * S[7] + S[8];
+  double sc = fabs(z) > 1e-8 ? 1.0 / z : 1.0;
   u *= sc; v *= sc;
-  float ix, iy;
+  double ix, iy;
   if (align_corners) {
-    ix = ((u + 1.f) / 2.f) * (float)(src.W - 1);
-    iy = ((v + 1.f) / 2.f) * (float)(src.H - 1);
+    ix = ((u + 1.0) / 2.0) * (double)(src.W - 1);
+    iy = ((v + 1.0) / 2.0) * (double)(src.H - 1);
   } else {
-    ix = ((u + 1.f) * (float)src.W - 1.f) / 2.f;
-    iy = ((v + 1.f) * (float)src.H - 1.f) / 2.f;
+    ix = ((u + 1.0) * (double)src.W - 1.0) / 2.0;
+    iy = ((v + 1.0) * (double)src.H - 1.0) / 2.0;
   }
-  float fx = floorf(ix), fy = floorf(iy);
+  bool finite = isfinite(ix) && isfinite(iy) && fabs(ix) < 1e9 && fabs(iy) < 1e9;
+  double fx = finite ? floor(ix) : 0.0, fy = finite ? floor(iy) : 0.0;
   int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
-  float wnw = ((float)x1 - ix) * ((float)y1 - iy), wne = (ix - (float)x0) * ((float)y1 - iy);
-  float wsw = ((float)x1 - ix) * (iy - (float)y0), wse = (ix - (float)x0) * (iy - (float)y0);
+  float ax = (float)(ix - fx), ay = (float)(iy - fy);
+  float wnw = (1.f - ax) * (1.f - ay), wne = ax * (1.f - ay);
+  float wsw = (1.f - ax) * ay, wse = ax * ay;
   bool vx0 = x0 >= 0 && x0 < src.W, vx1 = x1 >= 0 && x1 < src.W;
   bool vy0 = y0 >= 0 && y0 < src.H, vy1 = y1 >= 0 && y1 < src.H;
-  bool finite = isfinite(ix) && isfinite(iy);
   for (int c = 0; c < src.C; ++c) {
     float o = 0.f;
     if (finite) {

@@ -27,16 +27,27 @@ from . import functional as F
 _lib = C.lib
 
 
+# Every intermediate is referenced by raw pointer from kernels queued on the stream, so the torch
+# tensors that own the memory are kept alive until the next forward() (``_LIVE``); otherwise the
+# caching allocator could hand a dropped buffer to a later layer while an earlier kernel still reads it.
+_LIVE = []
+
+
+def _keep(t):
+    _LIVE.append(t)
+    return t
+
+
 def _split(B, H, W, Cn, dev):
-    return torch.empty((2, B, H, W, Cn), device=dev, dtype=torch.bfloat16)
+    return _keep(torch.empty((2, B, H, W, Cn), device=dev, dtype=torch.bfloat16))
 
 
 def _nhwc(B, H, W, Cn, dev):
-    return torch.empty((B, H, W, Cn), device=dev, dtype=torch.float32)
+    return _keep(torch.empty((B, H, W, Cn), device=dev, dtype=torch.float32))
 
 
 def _nchw(B, Cn, H, W, dev):
-    return torch.empty((B, Cn, H, W), device=dev, dtype=torch.float32)
+    return _keep(torch.empty((B, Cn, H, W), device=dev, dtype=torch.float32))
 
 
 class HesicEngine:
@@ -56,11 +67,6 @@ class HesicEngine:
         else:
             plan.set_gdn(None, None, False)
         return plan
-
-    def _conv(self, conv_mod, x_desc, out, out_desc_fn, act=C.ACT_NONE, gdn=None):
-        """Run conv_mod on descriptor x_desc; ``out`` is (kind, channels[, existing tensor, c0])."""
-        plan = self._plan(conv_mod, gdn)
-        plan.run(x_desc, out_desc_fn, act, self.path)
 
     def _run(self, conv_mod, x_desc, B, H, W, kind, act=C.ACT_NONE, gdn=None, dst=None):
         """Convolve and return (tensor, descriptor).  kind: 'split' | 'nhwc' | 'nchw'.
@@ -120,10 +126,10 @@ class HesicEngine:
         """gmm_weights branch (newnet1.py:484-512 / 546-574): -> softmaxed weights [B, K*M]."""
         _, d, H1, W1 = self._run(seq[0], x_desc, B, H, W, "split", act=C.ACT_LEAKY)
         t, d, H2, W2 = self._run(seq[2], d, B, H1, W1, "nhwc")
-        pooled = torch.empty((B, K * M), device=self.dev, dtype=torch.float32)
+        pooled = _keep(torch.empty((B, K * M), device=self.dev, dtype=torch.float32))
         C.check(_lib.hesic_spatial_max(C.ref(d), C.ptr(pooled), C.stream()))
         conv1x1 = seq[5]
-        out = torch.empty((B, K * M), device=self.dev, dtype=torch.float32)
+        out = _keep(torch.empty((B, K * M), device=self.dev, dtype=torch.float32))
         w = conv1x1.weight.detach()
         C.check(_lib.hesic_mixture_weights(C.ptr(pooled), C.ptr(w), C.ptr(conv1x1.bias.detach()), B, K, M, C.ptr(out), C.stream()))
         return out
@@ -148,9 +154,10 @@ class HesicEngine:
             raise ValueError("HSIC.forward needs H and W divisible by 64 (four stride-2 stages + two in the hyper path)")
         if tuple(h.shape) != (B, 3, 3):
             raise ValueError(f"h_matrix must be [B,3,3], got {tuple(h.shape)}")
-        x1 = x1.float().contiguous()
-        x2 = x2.float().contiguous()
-        h = h.float().contiguous()
+        del _LIVE[:]
+        x1 = _keep(x1.float().contiguous())
+        x2 = _keep(x2.float().contiguous())
+        h = _keep(h.float().contiguous())
         self.dev = dev = x1.device
         M, K = m.M, m.K
         acc = torch.zeros(4, device=dev, dtype=torch.float64)  # sum log2 p: y1, y2, z1, z2

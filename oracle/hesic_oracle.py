@@ -59,19 +59,23 @@ def deconv(x, w, b, stride=2):
 
 # ----------------------------------------------------------------------------
 # kornia.warp_perspective (third-party, un-vendored; call sites newnet1.py:746,753,767)
-def _normal_transform_pixel(h, w):
-    return torch.tensor([[2.0 / (w - 1), 0.0, -1.0], [0.0, 2.0 / (h - 1), -1.0], [0.0, 0.0, 1.0]])
+def _normal_transform_pixel(h, w, dtype=torch.float32):
+    return torch.tensor([[2.0 / (w - 1), 0.0, -1.0], [0.0, 2.0 / (h - 1), -1.0], [0.0, 0.0, 1.0]], dtype=dtype)
 
 
-def warp_perspective(src, M, dsize, align_corners=True):
+def warp_perspective(src, M, dsize, align_corners=True, dtype=torch.float32):
+    """``dtype=torch.float64`` evaluates the same algorithm in double: kornia's fp32
+    normalise -> invert -> denormalise chain carries ~1e-3 px of rounding noise at 512x512
+    (SURVEY.md section 7 "Warp numerics"), which the double evaluation removes."""
     B, _, H, W = src.shape
     h_out, w_out = dsize
-    src_norm = _normal_transform_pixel(H, W)[None]
-    dst_norm = _normal_transform_pixel(h_out, w_out)[None]
-    dst_norm_trans_src_norm = dst_norm @ (M.float() @ torch.inverse(src_norm))
+    src = src.to(dtype)
+    src_norm = _normal_transform_pixel(H, W, dtype)[None]
+    dst_norm = _normal_transform_pixel(h_out, w_out, dtype)[None]
+    dst_norm_trans_src_norm = dst_norm @ (M.to(dtype) @ torch.inverse(src_norm))
     src_norm_trans_dst_norm = torch.inverse(dst_norm_trans_src_norm)
-    xs = torch.linspace(-1, 1, w_out)
-    ys = torch.linspace(-1, 1, h_out)
+    xs = torch.linspace(-1, 1, w_out, dtype=dtype)
+    ys = torch.linspace(-1, 1, h_out, dtype=dtype)
     gx, gy = torch.meshgrid(xs, ys, indexing="xy")  # [h_out, w_out]
     pts = torch.stack((gx, gy, torch.ones_like(gx)), dim=-1)  # [h,w,3]
     p = pts[None] @ src_norm_trans_dst_norm[:, None].transpose(-1, -2)  # [B,h,w,3]
