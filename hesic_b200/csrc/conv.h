@@ -17,6 +17,9 @@ struct hesic_conv {
   float *gdn_beta = nullptr;    // reparametrised beta [Cout]
   float *gdn_w_simt = nullptr;  // fp32 [Cout(j)][Cout(i)] = gamma[i][j]
   __nv_bfloat16 *gdn_g_hi = nullptr, *gdn_g_lo = nullptr;  // bf16 planes [Cout(i)][Cout(j)] (K-major)
+  // tcgen05 path: cached TMA tensor maps of the static operands (w_hi, w_lo, gamma_hi, gamma_lo)
+  unsigned char *tc_maps = nullptr;
+  int tc_maps_bn = 0, tc_maps_gdn = -1;
 };
 
 namespace hesic {

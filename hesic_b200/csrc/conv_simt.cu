@@ -273,6 +273,7 @@ extern "C" void hesic_conv_destroy(hesic_conv *c) {
   if (!c) return;
   cudaFree(c->w_simt); cudaFree(c->bias); cudaFree(c->w_hi); cudaFree(c->w_lo);
   cudaFree(c->gdn_beta); cudaFree(c->gdn_w_simt); cudaFree(c->gdn_g_hi); cudaFree(c->gdn_g_lo);
+  free(c->tc_maps);
   delete c;
 }
 

@@ -1,10 +1,725 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the kernel lands in this file).
+// tcgen05 implicit-GEMM convolution / transposed convolution with fused bias, activation and GDN.
+//
+// GEMM view (one "task" = one 128-pixel x BN-channel output tile of one sub-pixel phase):
+//     D[pixel, co] = sum_{tap} sum_{ci} A_tap[pixel, ci] * W_tap[co, ci]
+// * A is never materialised (no im2col buffer).  Activations live in HBM as channels-last bf16
+//   (hi, lo) planes; for every (tap, 64-channel chunk) one TMA box of bw x bh x bb pixels x 64
+//   channels lands in shared memory already in the 128B-swizzled K-major layout tcgen05.mma reads.
+//   TMA's out-of-bounds zero fill IS the convolution's zero padding.
+//     - stride-1 conv:       tensor map (C, W, 1, H, B), box origin shifted by the tap offset
+//     - stride-2 conv:       space-to-depth VIEW of the same memory, (2C, W/2, 2, H/2, B): tap
+//                            ky-p = 2*dy+py selects the parity plane py and a stride-1 shift dy
+//     - transposed conv s2:  four sub-pixel phases; phase (ry,rx) is a stride-1 conv over the input
+//                            with the taps ky = ry+p (mod 2) (9/6/6/4 taps for k5), written to the
+//                            interleaved output positions -- no zero-insertion work
+// * fp32 parity on bf16 tensor cores: value = hi + lo (16 mantissa bits), and every k-step issues
+//   Ah*Wh + Ah*Wl + Al*Wh into one fp32 TMEM accumulator ("bf16x3").
+// * GDN / IGDN is a second contraction over the squared conv output: the epilogue warps square the
+//   accumulator tile, write it back to TMEM as a bf16 (hi, lo) A operand, and the MMA warp runs
+//   x^2 * gamma^T (A from TMEM, gamma from SMEM) into a norm accumulator; a second epilogue pass
+//   forms x * rsqrt(beta + norm) (or * sqrt for IGDN).  The GDN MMAs of tile t are issued in the
+//   middle of tile t+1's main loop so the tensor pipe never waits for an epilogue.
+// * persistent, warp-specialised CTA (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer and
+//   TMEM owner, warps 2-5 = epilogue.  TMEM: 2 x 128(256) accumulator columns + 128 operand + 128
+//   norm columns.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "conv.h"
 
 namespace hesic {
-bool conv_tc_supported(const hesic_conv *, const hesic_tensor *, const hesic_tensor *) { return false; }
-int conv_forward_tc(hesic_conv *, const hesic_tensor *, const hesic_tensor *, int, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return HESIC_E_UNSUPPORTED;
+namespace tc {
+
+constexpr int BM = 128;                 // pixels per tile (UMMA M)
+constexpr int BK = 64;                  // channels per k-step: 128 B of bf16 = one SW128 row
+constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_TAPS = 32;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_X2HI = 256, COL_X2LO = 320, COL_NORM = 384;
+constexpr int GDN_AT = 6;               // k-step of tile t+1 before which GDN(t) is issued
+constexpr int SMEM_LIMIT = 232448;      // 227 KB
+constexpr int BAR_BYTES = 256;
+
+struct Tap {
+  int8_t dy, dx, py, px;
+  int16_t w;
+  int16_t pad_;
+};
+
+struct Params {
+  int tiles_x, tiles_y, tiles_b;
+  int lbw, lbh;            // log2 of the box width / height (bw*bh*bb == 128)
+  int bw, bh, bb;
+  int n_tiles, BN;
+  int n_phases, os;        // transposed conv: os = stride, phases = os*os; conv: 1, 1
+  int tap_begin[5];
+  Tap taps[MAX_TAPS];
+  int kchunks;
+  int in_Cs;
+  int Cout;
+  int out_fmt, out_Cs;
+  void *y0, *y1;
+  int Hout, Wout, B;
+  const float *bias;
+  int act;
+  int gdn;                 // 0 none, 1 GDN, 2 inverse GDN
+  const float *beta;
+  int stages;
+  uint32_t stage_bytes, b_bytes;
+  int n_tasks;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol error can never hang the GPU.  The first wait that exceeds the time limit
+// records who/what/where in g_tc_dbg and raises g_tc_abort; every other wait then falls through at its
+// next checkpoint, the kernel drains (with garbage results) and the host reports HESIC_E_CUDA from
+// hesic_tc_status().
+__device__ unsigned int g_tc_abort = 0;
+__device__ unsigned int g_tc_dbg[8];
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 1023u) == 1023u) {
+      if (*(volatile unsigned int *)&g_tc_abort) return;
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 1000000000ull) {
+        if (atomicCAS(&g_tc_abort, 0u, 1u) == 0u) {
+          g_tc_dbg[0] = tag; g_tc_dbg[1] = blockIdx.x; g_tc_dbg[2] = threadIdx.x; g_tc_dbg[3] = parity;
+          g_tc_dbg[4] = it;
+        }
+        return;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap *map, uint32_t dst, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint32_t dst, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint32_t dst, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both K-major
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, A and B K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t instr_desc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
+  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  __nv_bfloat162 h;
+  h.x = ah; h.y = bh;
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  lo = pack_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
+}
+
+struct TaskCoord {
+  int mt, ph, nt;
+};
+__device__ __forceinline__ TaskCoord decode_task(const Params &p, int task) {
+  TaskCoord t;
+  t.nt = task % p.n_tiles;
+  int r = task / p.n_tiles;
+  t.ph = r % p.n_phases;
+  t.mt = r / p.n_phases;
+  return t;
+}
+
+// Same step sequence for the producer and the MMA warp.
+template <typename ConvStep, typename GdnStep>
+__device__ __forceinline__ void walk_schedule(const Params &p, ConvStep &&conv_step, GdnStep &&gdn_step) {
+  int lt = 0;
+  for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x, ++lt) {
+    TaskCoord tk = decode_task(p, task);
+    const int t0 = p.tap_begin[tk.ph], t1 = p.tap_begin[tk.ph + 1];
+    const int ksteps = (t1 - t0) * p.kchunks;
+    const int g = (p.gdn && lt > 0) ? min(GDN_AT, ksteps - 1) : -1;
+    int ks = 0;
+    for (int t = t0; t < t1; ++t) {
+      for (int kc = 0; kc < p.kchunks; ++kc, ++ks) {
+        if (ks == g) {
+          gdn_step(lt - 1, 0);
+          gdn_step(lt - 1, 1);
+        }
+        conv_step(lt, tk, t, kc, ks == 0, ks == ksteps - 1);
+      }
+    }
+  }
+  if (p.gdn && lt > 0) {
+    gdn_step(lt - 1, 0);
+    gdn_step(lt - 1, 1);
+  }
+}
+
+__device__ __forceinline__ void store_chunk(const Params &p, const float (&v)[32], size_t pix, int n_base) {
+  if (p.out_fmt == HESIC_FMT_NHWC_SPLIT) {
+    __nv_bfloat16 *h = (__nv_bfloat16 *)p.y0 + pix * p.out_Cs + n_base;
+    __nv_bfloat16 *l = (__nv_bfloat16 *)p.y1 + pix * p.out_Cs + n_base;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (n_base + g * 8 < p.Cout) {
+        uint4 hv, lv;
+        split_pair(v[g * 8 + 0], v[g * 8 + 1], hv.x, lv.x);
+        split_pair(v[g * 8 + 2], v[g * 8 + 3], hv.y, lv.y);
+        split_pair(v[g * 8 + 4], v[g * 8 + 5], hv.z, lv.z);
+        split_pair(v[g * 8 + 6], v[g * 8 + 7], hv.w, lv.w);
+        *reinterpret_cast<uint4 *>(h + g * 8) = hv;
+        *reinterpret_cast<uint4 *>(l + g * 8) = lv;
+      }
+    }
+  } else {
+    float *o = (float *)p.y0 + pix * p.out_Cs + n_base;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (n_base + g * 4 < p.Cout)
+        *reinterpret_cast<float4 *>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+               const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * p.stage_bytes;
+  // barrier map (8 B each)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto acc_full = [&](int b) { return bar_base + 128u + 8u * b; };
+  auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };
+  const uint32_t x2_full = bar_base + 160u, norm_full = bar_base + 168u, norm_empty = bar_base + 176u;
+  const uint32_t tmem_slot = bar_base + 192u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&map_a_hi); prefetch_map(&map_a_lo); prefetch_map(&map_w_hi); prefetch_map(&map_w_lo);
+    if (p.gdn) { prefetch_map(&map_g_hi); prefetch_map(&map_g_lo); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
+    mbar_init(x2_full, 128); mbar_init(norm_full, 1); mbar_init(norm_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  const uint32_t acc_stride = p.gdn ? 128u : 256u;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1u; } };
+      const int txy = p.tiles_x * p.tiles_y;
+      walk_schedule(
+          p,
+          [&](int, const TaskCoord &tk, int t, int kc, bool, bool) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+            const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+            const uint32_t fb = full_bar(stage);
+            mbar_expect_tx(fb, 2u * A_TILE_BYTES + 2u * p.b_bytes);
+            const int tb = tk.mt / txy, rr = tk.mt - tb * txy;
+            const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+            const Tap tap = p.taps[t];
+            const int c = kc * BK + tap.px * p.in_Cs;
+            const int x = tx * p.bw + tap.dx, y = ty * p.bh + tap.dy, b = tb * p.bb;
+            tma_load_5d(&map_a_hi, sa, fb, c, x, tap.py, y, b);
+            tma_load_5d(&map_a_lo, sa + A_TILE_BYTES, fb, c, x, tap.py, y, b);
+            tma_load_3d(&map_w_hi, sa + 2 * A_TILE_BYTES, fb, kc * BK, tk.nt * p.BN, tap.w);
+            tma_load_3d(&map_w_lo, sa + 2 * A_TILE_BYTES + p.b_bytes, fb, kc * BK, tk.nt * p.BN, tap.w);
+            advance();
+          },
+          [&](int, int c) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, 9);
+            const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+            const uint32_t fb = full_bar(stage);
+            mbar_expect_tx(fb, 2u * 128u * 128u);
+            tma_load_2d(&map_g_hi, sa + 2 * A_TILE_BYTES, fb, c * BK, 0);
+            tma_load_2d(&map_g_lo, sa + 2 * A_TILE_BYTES + p.b_bytes, fb, c * BK, 0);
+            advance();
+          });
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1u; } };
+      const uint32_t idesc = instr_desc(p.BN), idesc_g = instr_desc(128);
+      walk_schedule(
+          p,
+          [&](int lt, const TaskCoord &, int, int, bool first, bool last) {
+            const int buf = lt & 1;
+            if (first) {
+              mbar_wait(acc_empty(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u, 2);
+              tc_fence_after();
+            }
+            mbar_wait(full_bar(stage), phase, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+            const uint64_t a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_TILE_BYTES);
+            const uint64_t b_hi = smem_desc(sa + 2 * A_TILE_BYTES), b_lo = smem_desc(sa + 2 * A_TILE_BYTES + p.b_bytes);
+            const uint32_t d = tmem_base + (uint32_t)buf * acc_stride;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);   // 32 B per K=16 step, encoded >> 4
+              mma_ss(d, a_hi + o, b_hi + o, idesc, (first && k == 0) ? 0u : 1u);
+              mma_ss(d, a_hi + o, b_lo + o, idesc, 1u);
+              mma_ss(d, a_lo + o, b_hi + o, idesc, 1u);
+            }
+            tc_commit(empty_bar(stage));
+            if (last) tc_commit(acc_full(buf));
+            advance();
+          },
+          [&](int lt, int c) {
+            if (c == 0) {
+              mbar_wait(x2_full, (uint32_t)lt & 1u, 4);
+              mbar_wait(norm_empty, ((uint32_t)lt & 1u) ^ 1u, 5);
+              tc_fence_after();
+            }
+            mbar_wait(full_bar(stage), phase, 6);
+            tc_fence_after();
+            const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+            const uint64_t b_hi = smem_desc(sa + 2 * A_TILE_BYTES), b_lo = smem_desc(sa + 2 * A_TILE_BYTES + p.b_bytes);
+            const uint32_t d = tmem_base + COL_NORM;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);
+              const uint32_t ah = tmem_base + COL_X2HI + (uint32_t)(c * 32 + k * 8);
+              const uint32_t al = tmem_base + COL_X2LO + (uint32_t)(c * 32 + k * 8);
+              mma_ts(d, ah, b_hi + o, idesc_g, (c == 0 && k == 0) ? 0u : 1u);
+              mma_ts(d, ah, b_lo + o, idesc_g, 1u);
+              mma_ts(d, al, b_hi + o, idesc_g, 1u);
+            }
+            tc_commit(empty_bar(stage));
+            if (c == 1) tc_commit(norm_full);
+            advance();
+          });
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int xi = row & (p.bw - 1), yi = (row >> p.lbw) & (p.bh - 1), bi = row >> (p.lbw + p.lbh);
+    const int txy = p.tiles_x * p.tiles_y;
+    int lt = 0;
+    for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x, ++lt) {
+      const TaskCoord tk = decode_task(p, task);
+      const int buf = lt & 1;
+      const int tb = tk.mt / txy, rr = tk.mt - tb * txy;
+      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      const int ry = tk.ph / p.os, rx = tk.ph - ry * p.os;
+      const int ox = (tx * p.bw + xi) * p.os + rx, oy = (ty * p.bh + yi) * p.os + ry, b = tb * p.bb + bi;
+      const bool valid = ox < p.Wout && oy < p.Hout && b < p.B;
+      const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
+      const int n0 = tk.nt * p.BN;
+      const uint32_t acc = tmem_base + lane_addr + (uint32_t)buf * acc_stride;
+
+      mbar_wait(acc_full(buf), ((uint32_t)lt >> 1) & 1u, 7);
+      tc_fence_after();
+      if (!p.gdn) {
+        for (int ch = 0; ch < p.BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(acc + ch * 32, r);
+          tmem_ld_wait();
+          float v[32];
+          const int nb = n0 + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float bj = (nb + j < p.Cout) ? __ldg(p.bias + nb + j) : 0.f;
+            v[j] = apply_act(__uint_as_float(r[j]) + bj, p.act);
+          }
+          if (valid) store_chunk(p, v, pix, nb);
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty(buf));
+      } else {
+        // pass 1: x = conv + bias; x^2 -> bf16 (hi, lo) A operand in TMEM
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(acc + ch * 32, r);
+          tmem_ld_wait();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(r[2 * j]) + __ldg(p.bias + ch * 32 + 2 * j);
+            float c = __uint_as_float(r[2 * j + 1]) + __ldg(p.bias + ch * 32 + 2 * j + 1);
+            split_pair(a * a, c * c, hi[j], lo[j]);
+          }
+          tmem_st16(tmem_base + lane_addr + COL_X2HI + ch * 16, hi);
+          tmem_st16(tmem_base + lane_addr + COL_X2LO + ch * 16, lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(x2_full);
+        // pass 2: y = x * rsqrt(beta + norm)   (IGDN: * sqrt)
+        mbar_wait(norm_full, (uint32_t)lt & 1u, 8);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32], q[32];
+          tmem_ld32(acc + ch * 32, r);
+          tmem_ld32(tmem_base + lane_addr + COL_NORM + ch * 32, q);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]) + __ldg(p.bias + ch * 32 + j);
+            float nrm = __uint_as_float(q[j]) + __ldg(p.beta + ch * 32 + j);
+            v[j] = x * (p.gdn == 2 ? sqrtf(nrm) : rsqrtf(nrm));
+          }
+          if (valid) store_chunk(p, v, pix, ch * 32);
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty(buf));
+        mbar_arrive(norm_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+// rank-n bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..n-1.
+static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
+                    const uint32_t *box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return HESIC_E_CUDA; }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,..] box=[%u,%u,%u,..]", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              box[0], box[1], rank > 2 ? box[2] : 0);
+    return HESIC_E_CUDA;
+  }
+  return HESIC_OK;
+}
+
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+static int posmod(int a, int m) { return ((a % m) + m) % m; }
+
+// N tile: multiple of 32, <= cap, exact divisor of round_up(Cout, 32) when possible (fewest tiles first)
+static int choose_bn(int Cout, bool gdn) {
+  if (gdn) return 128;
+  int c32 = (Cout + 31) / 32 * 32;
+  if (c32 <= 192) return c32;
+  for (int nt = 2; nt <= 16; ++nt) {
+    if (c32 % nt == 0 && (c32 / nt) % 32 == 0 && c32 / nt <= 192) return c32 / nt;
+  }
+  return 128;
+}
+
+struct Plan {
+  Params p;
+  int smem_bytes;
+};
+
+static int build_taps(const hesic_conv *c, Params &p) {
+  int n = 0;
+  if (!c->transposed) {
+    p.n_phases = 1; p.os = 1;
+    p.tap_begin[0] = 0;
+    for (int ky = 0; ky < c->kh; ++ky)
+      for (int kx = 0; kx < c->kw; ++kx) {
+        int oy = ky - c->pad, ox = kx - c->pad;
+        Tap t;
+        if (c->stride == 1) { t.dy = oy; t.py = 0; t.dx = ox; t.px = 0; }
+        else { t.py = posmod(oy, 2); t.dy = (oy - t.py) / 2; t.px = posmod(ox, 2); t.dx = (ox - t.px) / 2; }
+        t.w = (int16_t)(ky * c->kw + kx); t.pad_ = 0;
+        p.taps[n++] = t;
+      }
+    p.tap_begin[1] = n;
+  } else {
+    const int s = c->stride;
+    p.n_phases = s * s; p.os = s;
+    for (int ph = 0; ph < s * s; ++ph) {
+      const int ry = ph / s, rx = ph % s;
+      p.tap_begin[ph] = n;
+      for (int ky = 0; ky < c->kh; ++ky) {
+        if (posmod(ry + c->pad - ky, s) != 0) continue;
+        for (int kx = 0; kx < c->kw; ++kx) {
+          if (posmod(rx + c->pad - kx, s) != 0) continue;
+          Tap t;
+          t.dy = (ry + c->pad - ky) / s; t.dx = (rx + c->pad - kx) / s; t.py = 0; t.px = 0;
+          t.w = (int16_t)(ky * c->kw + kx); t.pad_ = 0;
+          p.taps[n++] = t;
+        }
+      }
+      if (n == p.tap_begin[ph]) return -1;   // a phase without taps
+    }
+    p.tap_begin[s * s] = n;
+  }
+  return n;
+}
+
+static bool aligned16(const void *q) { return ((uintptr_t)q & 15u) == 0; }
+
+}  // namespace tc
+
+bool conv_tc_supported(const hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y) {
+  using namespace tc;
+  if (x->fmt != HESIC_FMT_NHWC_SPLIT) return false;
+  if (y->fmt != HESIC_FMT_NHWC_SPLIT && y->fmt != HESIC_FMT_NHWC_F32) return false;
+  const int xCs = x->Cs > 0 ? x->Cs : x->C, yCs = y->Cs > 0 ? y->Cs : y->C;
+  if (c->Cin % 8 || c->Cin < 16 || xCs % 8 || !aligned16(x->p0) || !aligned16(x->p1)) return false;
+  if (c->Cout % 8 || c->Cout < 16 || yCs % 8 || !aligned16(y->p0)) return false;
+  if (y->fmt == HESIC_FMT_NHWC_SPLIT && !aligned16(y->p1)) return false;
+  if (c->kh * c->kw > MAX_TAPS || c->kh != c->kw) return false;
+  if (c->stride != 1 && c->stride != 2) return false;
+  if (!c->transposed && c->stride == 2 && ((x->H | x->W) & 1)) return false;
+  if (c->transposed && (c->kh < c->stride)) return false;
+  if (c->has_gdn && c->Cout != 128) return false;
+  if ((int64_t)x->B * x->H * x->W == 0 || (int64_t)y->B * y->H * y->W == 0) return false;
+  return encode_fn() != nullptr;
+}
+
+int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s) {
+  using namespace tc;
+  if (c->has_gdn && act != HESIC_ACT_NONE) {
+    set_error("activation after fused GDN is not supported");
+    return HESIC_E_UNSUPPORTED;
+  }
+  static int num_sms = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int dev = 0;
+    HESIC_CUDA(cudaGetDevice(&dev));
+    HESIC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    HESIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int xCs = x->Cs > 0 ? x->Cs : x->C, yCs = y->Cs > 0 ? y->Cs : y->C;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  const int ntaps = build_taps(c, p);
+  if (ntaps <= 0) { set_error("conv tcgen05: unsupported tap structure"); return HESIC_E_UNSUPPORTED; }
+  const int Hq = (y->H + p.os - 1) / p.os, Wq = (y->W + p.os - 1) / p.os;
+  p.bw = Wq >= 16 ? 16 : pow2ceil(Wq);
+  p.bh = std::min(BM / p.bw, pow2ceil(Hq));
+  p.bb = BM / (p.bw * p.bh);
+  p.lbw = ilog2(p.bw); p.lbh = ilog2(p.bh);
+  p.tiles_x = (Wq + p.bw - 1) / p.bw; p.tiles_y = (Hq + p.bh - 1) / p.bh; p.tiles_b = (y->B + p.bb - 1) / p.bb;
+  p.BN = choose_bn(c->Cout, c->has_gdn);
+  p.n_tiles = (c->Cout + p.BN - 1) / p.BN;
+  p.kchunks = (c->Cin + BK - 1) / BK;
+  p.in_Cs = xCs;
+  p.Cout = c->Cout;
+  p.out_fmt = y->fmt; p.out_Cs = yCs; p.y0 = y->p0; p.y1 = y->p1;
+  p.Hout = y->H; p.Wout = y->W; p.B = y->B;
+  p.bias = c->bias; p.act = act;
+  p.gdn = c->has_gdn ? (c->gdn_inverse ? 2 : 1) : 0;
+  p.beta = c->gdn_beta;
+  p.b_bytes = (uint32_t)p.BN * 128u;
+  p.stage_bytes = 2u * A_TILE_BYTES + 2u * p.b_bytes;
+  p.stages = std::min(8, (SMEM_LIMIT - 1024 - BAR_BYTES) / (int)p.stage_bytes);
+  if (p.stages < 2) { set_error("conv tcgen05: tile does not fit shared memory"); return HESIC_E_UNSUPPORTED; }
+  p.n_tasks = p.tiles_x * p.tiles_y * p.tiles_b * p.n_phases * p.n_tiles;
+  const int smem_bytes = p.stages * (int)p.stage_bytes + 1024 + BAR_BYTES;
+
+  // activation maps (depend on the input pointer -> encoded per call, host-only work)
+  CUtensorMap ma_hi, ma_lo;
+  {
+    uint64_t dims[5], strides[4];
+    uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bw, 1u, (uint32_t)p.bh, (uint32_t)p.bb};
+    const uint64_t e = 2;
+    if (!c->transposed && c->stride == 2) {
+      dims[0] = (uint64_t)xCs + x->C; dims[1] = x->W / 2; dims[2] = 2; dims[3] = x->H / 2; dims[4] = x->B;
+      strides[0] = 2ull * xCs * e; strides[1] = (uint64_t)x->W * xCs * e; strides[2] = 2ull * x->W * xCs * e;
+      strides[3] = (uint64_t)x->H * x->W * xCs * e;
+    } else {
+      dims[0] = x->C; dims[1] = x->W; dims[2] = 1; dims[3] = x->H; dims[4] = x->B;
+      strides[0] = (uint64_t)xCs * e; strides[1] = (uint64_t)x->W * xCs * e; strides[2] = (uint64_t)x->W * xCs * e;
+      strides[3] = (uint64_t)x->H * x->W * xCs * e;
+    }
+    int r = make_map(&ma_hi, x->p0, 5, dims, strides, box);
+    if (r == HESIC_OK) r = make_map(&ma_lo, x->p1, 5, dims, strides, box);
+    if (r != HESIC_OK) return r;
+  }
+  // weight / gamma maps (static per layer; re-encoded when the tile shape changes)
+  if (!c->tc_maps || c->tc_maps_bn != p.BN || c->tc_maps_gdn != (int)c->has_gdn) {
+    if (!c->tc_maps) c->tc_maps = (unsigned char *)aligned_alloc(128, 4 * sizeof(CUtensorMap));
+    CUtensorMap *m = (CUtensorMap *)c->tc_maps;
+    const int taps = c->kh * c->kw;
+    uint64_t dims[3] = {(uint64_t)c->Cin, (uint64_t)c->CoutPad, (uint64_t)taps};
+    uint64_t strides[2] = {(uint64_t)c->Cin * 2, (uint64_t)c->Cin * c->CoutPad * 2};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)p.BN, 1u};
+    int r = make_map(&m[0], c->w_hi, 3, dims, strides, box);
+    if (r == HESIC_OK) r = make_map(&m[1], c->w_lo, 3, dims, strides, box);
+    if (r == HESIC_OK && c->has_gdn) {
+      uint64_t gd[2] = {128, 128}, gs[1] = {256};
+      uint32_t gb[2] = {(uint32_t)BK, 128u};
+      r = make_map(&m[2], c->gdn_g_hi, 2, gd, gs, gb);
+      if (r == HESIC_OK) r = make_map(&m[3], c->gdn_g_lo, 2, gd, gs, gb);
+    } else if (r == HESIC_OK) {
+      m[2] = m[0]; m[3] = m[1];
+    }
+    if (r != HESIC_OK) return r;
+    c->tc_maps_bn = p.BN; c->tc_maps_gdn = (int)c->has_gdn;
+  }
+  const CUtensorMap *m = (const CUtensorMap *)c->tc_maps;
+  const int grid = std::min(p.n_tasks, num_sms);
+  conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], m[2], m[3], p);
+  HESIC_LAUNCHED("conv_tc_kernel");
+  return HESIC_OK;
+}
+
 }  // namespace hesic
+
+// 0 when no tcgen05 kernel has hit its watchdog since the last call; otherwise HESIC_E_CUDA with the
+// first timed-out wait in the error text (tag: 1/9 producer empty, 2 acc_empty, 3/6 full, 4 x2_full,
+// 5 norm_empty, 7 acc_full, 8 norm_full).  Synchronises the device.
+extern "C" int hesic_tc_status(void) {
+  using namespace hesic;
+  unsigned int flag = 0, dbg[8] = {0};
+  HESIC_CUDA(cudaDeviceSynchronize());
+  HESIC_CUDA(cudaMemcpyFromSymbol(&flag, tc::g_tc_abort, sizeof(flag)));
+  if (!flag) return HESIC_OK;
+  HESIC_CUDA(cudaMemcpyFromSymbol(dbg, tc::g_tc_dbg, sizeof(dbg)));
+  unsigned int zero = 0;
+  HESIC_CUDA(cudaMemcpyToSymbol(tc::g_tc_abort, &zero, sizeof(zero)));
+  set_error("tcgen05 conv watchdog: wait tag %u timed out (block %u thread %u parity %u)", dbg[0], dbg[1], dbg[2], dbg[3]);
+  return HESIC_E_CUDA;
+}

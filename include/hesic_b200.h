@@ -82,6 +82,11 @@ int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float *gamma, int
 int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, int path,
                        void *stream);
 
+/* Watchdog of the tcgen05 path: every in-kernel barrier wait is time-bounded, so a protocol error
+ * cannot hang the GPU.  Returns 0 when no wait has timed out since the last call, else HESIC_E_CUDA
+ * (details in hesic_last_error()).  Synchronises the device; meant for tests and smoke checks. */
+int hesic_tc_status(void);
+
 /* Stand-alone GDN (compressai/layers/gdn.py:55-70) with raw parameters, any C. */
 int hesic_gdn(const hesic_tensor *x, const hesic_tensor *y, const float *beta, const float *gamma, int inverse,
               float beta_min, void *stream);
