@@ -14,7 +14,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libhesic_b200.so")
 
-FMT_NCHW, FMT_NHWC, FMT_SPLIT = 0, 1, 2
+FMT_NCHW, FMT_NHWC, FMT_SPLIT, FMT_ROWPAD = 0, 1, 2, 3
+ROWPAD_Y, ROWPAD_X = 4, 8
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
 OP_COPY, OP_ABS, OP_ROUND = 0, 1, 2
@@ -138,6 +139,16 @@ def split(t, C=None, c0=0):
     C = Cs - c0 if C is None else C
     plane = B * H * W * Cs * 2
     return CTensor(t.data_ptr() + 2 * c0, t.data_ptr() + plane + 2 * c0, FMT_SPLIT, B, C, H, W, Cs)
+
+
+def rowpad(t, C=None, c0=0):
+    """Descriptor for a [2,B,H+4,W+8,8] bf16 torch tensor in ROWPAD8 split format (image at offset (2,2),
+    zero border and zero unused channel slots): the input format of the Cin <= 8 edge layers."""
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[0] == 2 and t.shape[-1] == 8
+    _, B, Hp, Wp, _ = t.shape
+    C = 8 - c0 if C is None else C
+    plane = B * Hp * Wp * 8 * 2
+    return CTensor(t.data_ptr() + 2 * c0, t.data_ptr() + plane + 2 * c0, FMT_ROWPAD, B, C, Hp - ROWPAD_Y, Wp - ROWPAD_X, 8)
 
 
 def null():

@@ -70,24 +70,28 @@ inline bool same_shape(const hesic_tensor *a, const hesic_tensor *b) {
 
 inline int check_tensor(const hesic_tensor *t, const char *name, bool allow_null_data = false) {
   HESIC_REQUIRE(t != nullptr, "%s: null tensor descriptor", name);
-  HESIC_REQUIRE(t->fmt >= 0 && t->fmt <= 2, "%s: bad format %d", name, t->fmt);
+  HESIC_REQUIRE(t->fmt >= 0 && t->fmt <= 3, "%s: bad format %d", name, t->fmt);
   HESIC_REQUIRE(t->B >= 0 && t->C >= 0 && t->H >= 0 && t->W >= 0, "%s: negative size", name);
   HESIC_REQUIRE(t->Cs == 0 || t->Cs >= t->C, "%s: Cs < C", name);
   if (!allow_null_data && (int64_t)t->B * t->C * t->H * t->W > 0) {
     HESIC_REQUIRE(t->p0 != nullptr, "%s: null data pointer", name);
-    if (t->fmt == HESIC_FMT_NHWC_SPLIT) HESIC_REQUIRE(t->p1 != nullptr, "%s: null lo plane", name);
+    if (t->fmt == HESIC_FMT_NHWC_SPLIT || t->fmt == HESIC_FMT_ROWPAD8_SPLIT)
+      HESIC_REQUIRE(t->p1 != nullptr, "%s: null lo plane", name);
+    if (t->fmt == HESIC_FMT_ROWPAD8_SPLIT) HESIC_REQUIRE(t->Cs == 8 && t->C <= 8, "%s: ROWPAD8 needs Cs == 8", name);
   }
   return HESIC_OK;
 }
 
 __device__ __forceinline__ size_t toff(const TView &t, int b, int c, int y, int x) {
   if (t.fmt == HESIC_FMT_NCHW_F32) return (((size_t)b * t.Cs + c) * t.H + y) * t.W + x;
+  if (t.fmt == HESIC_FMT_ROWPAD8_SPLIT)
+    return (((size_t)b * (t.H + HESIC_ROWPAD_Y) + y + 2) * (t.W + HESIC_ROWPAD_X) + x + 2) * 8 + c;
   return (((size_t)b * t.H + y) * t.W + x) * t.Cs + c;
 }
 
 __device__ __forceinline__ float tload(const TView &t, int b, int c, int y, int x) {
   size_t o = toff(t, b, c, y, x);
-  if (t.fmt == HESIC_FMT_NHWC_SPLIT) {
+  if (t.fmt >= HESIC_FMT_NHWC_SPLIT) {
     return __bfloat162float(((const __nv_bfloat16 *)t.p0)[o]) + __bfloat162float(((const __nv_bfloat16 *)t.p1)[o]);
   }
   return ((const float *)t.p0)[o];
@@ -101,7 +105,7 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bflo
 
 __device__ __forceinline__ void tstore(const TView &t, int b, int c, int y, int x, float v) {
   size_t o = toff(t, b, c, y, x);
-  if (t.fmt == HESIC_FMT_NHWC_SPLIT) {
+  if (t.fmt >= HESIC_FMT_NHWC_SPLIT) {
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
     ((__nv_bfloat16 *)t.p0)[o] = hi;

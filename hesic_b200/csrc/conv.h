@@ -2,6 +2,14 @@
 #pragma once
 #include "common.cuh"
 
+// Operand formulation of the tcgen05 path (decided by the layer geometry at creation):
+//   GENERIC  one GEMM k-step per (tap, 64-channel chunk); weights [tap][CoutPad][Cin]
+//   ROW      Cin <= 8, k5 (the full-resolution RGB / 6-channel layers): input in ROWPAD8 format, one k-step
+//            per kernel ROW with K = 8 pixels x 8 channel slots; weights [ky][CoutPad][64]
+//   MERGED   stride-2 k5 transposed conv with Cout <= 4 (the RGB synthesis head): the 4 sub-pixel phases
+//            become the N dimension of a 3x3 stride-1 conv; weights [3x3 shift][16 = phase*4+co][Cin]
+enum { HESIC_TC_GENERIC = 0, HESIC_TC_ROW = 1, HESIC_TC_MERGED = 2 };
+
 struct hesic_conv {
   int Cin = 0, Cout = 0, kh = 0, kw = 0, stride = 1, pad = 0, transposed = 0, out_pad = 0;
   // SIMT operand: fp32 [kh*kw*Cin][Cout] (tap-major rows, Cout contiguous)
@@ -10,6 +18,7 @@ struct hesic_conv {
   // tcgen05 operands: bf16 hi / lo planes [kh*kw][CoutPad][Cin] (K-major per tap)
   __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
   int CoutPad = 0;
+  int tc_kind = HESIC_TC_GENERIC, tc_taps = 0, tc_k = 0;   // w_hi/w_lo are [tc_taps][CoutPad][tc_k]
   bool loaded = false;
   // fused GDN
   bool has_gdn = false;

@@ -5,6 +5,8 @@
 // 3-channel GDNs -- and (2) the correctness anchor the tcgen05 path (conv_tc.cu) is validated
 // against on the device.  One kernel covers nn.Conv2d (any stride) and nn.ConvTranspose2d in gather
 // form, with bias + activation (+ GDN as a 1x1 contraction over x^2) fused.
+#include <algorithm>
+
 #include "conv.h"
 
 namespace hesic {
@@ -206,6 +208,49 @@ __global__ void pack_conv_kernel(const float *__restrict__ w, const float *__res
   }
 }
 
+// ROW formulation: [ky][CoutPad][kx*8 + c]; a stride-1 transposed conv is the correlation with the
+// kernel flipped in both axes.
+__global__ void pack_conv_row_kernel(const float *__restrict__ w, const float *__restrict__ mask, int Cin, int Cout,
+                                     int transposed, int CoutPad, __nv_bfloat16 *__restrict__ w_hi,
+                                     __nv_bfloat16 *__restrict__ w_lo) {
+  int total = 5 * CoutPad * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int e = i % 64, r = i / 64;
+    int co = r % CoutPad, ky = r / CoutPad;
+    int kx = e / 8, ci = e % 8;
+    float v = 0.f;
+    if (kx < 5 && ci < Cin && co < Cout) {
+      size_t src = transposed ? ((((size_t)ci * Cout + co) * 5 + (4 - ky)) * 5 + (4 - kx))
+                              : ((((size_t)co * Cin + ci) * 5 + ky) * 5 + kx);
+      v = w[src];
+      if (mask) v *= mask[src];
+    }
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    w_hi[i] = hi;
+    w_lo[i] = lo;
+  }
+}
+
+// MERGED formulation: [(dy+1)*3 + dx+1][n = (ry*2+rx)*4 + co][ci], tap ky = ry + 2 - 2*dy (k5, s2, p2)
+__global__ void pack_conv_merged_kernel(const float *__restrict__ w, int Cin, int Cout, __nv_bfloat16 *__restrict__ w_hi,
+                                        __nv_bfloat16 *__restrict__ w_lo) {
+  int total = 9 * 16 * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int ci = i % Cin, r = i / Cin;
+    int n = r % 16, tap = r / 16;
+    int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    int ph = n / 4, co = n % 4;
+    int ky = (ph >> 1) + 2 - 2 * dy, kx = (ph & 1) + 2 - 2 * dx;
+    float v = 0.f;
+    if (co < Cout && ky >= 0 && ky < 5 && kx >= 0 && kx < 5) v = w[(((size_t)ci * Cout + co) * 5 + ky) * 5 + kx];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    w_hi[i] = hi;
+    w_lo[i] = lo;
+  }
+}
+
 __global__ void pack_gdn_kernel(const float *__restrict__ beta, const float *__restrict__ gamma, int C, float beta_bound,
                                 float gamma_bound, float pedestal, float *__restrict__ beta_rp,
                                 float *__restrict__ w_simt, __nv_bfloat16 *__restrict__ g_hi,
@@ -266,6 +311,14 @@ extern "C" hesic_conv *hesic_conv_create(int Cin, int Cout, int kh, int kw, int 
   c->Cin = Cin; c->Cout = Cout; c->kh = kh; c->kw = kw; c->stride = stride; c->pad = pad;
   c->transposed = transposed ? 1 : 0; c->out_pad = output_padding;
   c->CoutPad = (Cout + 15) / 16 * 16;
+  c->tc_kind = HESIC_TC_GENERIC; c->tc_taps = kh * kw; c->tc_k = Cin;
+  const bool k5 = kh == 5 && kw == 5 && pad == 2;
+  if (Cin <= 8 && k5 && ((!c->transposed && (stride == 1 || stride == 2)) ||
+                         (c->transposed && stride == 1 && output_padding == 0))) {
+    c->tc_kind = HESIC_TC_ROW; c->tc_taps = 5; c->tc_k = 64;
+  } else if (c->transposed && stride == 2 && k5 && output_padding == 1 && Cout <= 4 && Cin % 8 == 0) {
+    c->tc_kind = HESIC_TC_MERGED; c->tc_taps = 9; c->tc_k = Cin;
+  }
   return c;
 }
 
@@ -284,14 +337,25 @@ extern "C" int hesic_conv_load(hesic_conv *c, const float *weight, const float *
   if (!c->w_simt) {
     HESIC_CUDA(cudaMalloc(&c->w_simt, taps * c->Cin * c->Cout * sizeof(float)));
     HESIC_CUDA(cudaMalloc(&c->bias, c->Cout * sizeof(float)));
-    HESIC_CUDA(cudaMalloc(&c->w_hi, taps * c->Cin * c->CoutPad * sizeof(__nv_bfloat16)));
-    HESIC_CUDA(cudaMalloc(&c->w_lo, taps * c->Cin * c->CoutPad * sizeof(__nv_bfloat16)));
+    size_t tc_elems = std::max(taps * c->Cin, (size_t)c->tc_taps * c->tc_k) * c->CoutPad;
+    HESIC_CUDA(cudaMalloc(&c->w_hi, tc_elems * sizeof(__nv_bfloat16)));
+    HESIC_CUDA(cudaMalloc(&c->w_lo, tc_elems * sizeof(__nv_bfloat16)));
   }
   size_t total = taps * c->Cin * c->CoutPad;
   int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   pack_conv_kernel<<<blocks, 256, 0, s>>>(weight, mask, c->Cin, c->Cout, c->kh, c->kw, c->transposed, c->CoutPad,
                                           c->w_simt, c->w_hi, c->w_lo);
   HESIC_LAUNCHED("pack_conv_kernel");
+  // the tensor-core operand planes of the ROW / MERGED formulations replace the generic ones
+  if (c->tc_kind == HESIC_TC_ROW) {
+    pack_conv_row_kernel<<<(5 * c->CoutPad * 64 + 255) / 256, 256, 0, s>>>(weight, mask, c->Cin, c->Cout, c->transposed,
+                                                                       c->CoutPad, c->w_hi, c->w_lo);
+    HESIC_LAUNCHED("pack_conv_row_kernel");
+  } else if (c->tc_kind == HESIC_TC_MERGED) {
+    HESIC_REQUIRE(mask == nullptr, "hesic_conv_load: masked transposed RGB head is not supported");
+    pack_conv_merged_kernel<<<(9 * 16 * c->Cin + 255) / 256, 256, 0, s>>>(weight, c->Cin, c->Cout, c->w_hi, c->w_lo);
+    HESIC_LAUNCHED("pack_conv_merged_kernel");
+  }
   if (bias) {
     HESIC_CUDA(cudaMemcpyAsync(c->bias, bias, c->Cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
   } else {

@@ -13,15 +13,20 @@
 //                            with the taps ky = ry+p (mod 2) (9/6/6/4 taps for k5), written to the
 //                            interleaved output positions -- no zero-insertion work
 // * fp32 parity on bf16 tensor cores: value = hi + lo (16 mantissa bits), and every k-step issues
-//   Ah*Wh + Ah*Wl + Al*Wh into one fp32 TMEM accumulator ("bf16x3").
+//   Ah*Wh into a MAIN fp32 TMEM accumulator and Ah*Wl + Al*Wh into a second, SMALL one ("bf16x3").
+//   The tensor core's fp32 accumulate truncates (measured: error grows linearly with the number of
+//   accumulate steps); keeping the 2^-8-sized correction terms out of the main accumulator cuts its
+//   step count 3x, and their own truncation is relative to their small magnitude.  The epilogue adds
+//   main + small in fp32.
 // * GDN / IGDN is a second contraction over the squared conv output: the epilogue warps square the
 //   accumulator tile, write it back to TMEM as a bf16 (hi, lo) A operand, and the MMA warp runs
 //   x^2 * gamma^T (A from TMEM, gamma from SMEM) into a norm accumulator; a second epilogue pass
 //   forms x * rsqrt(beta + norm) (or * sqrt for IGDN).  The GDN MMAs of tile t are issued in the
 //   middle of tile t+1's main loop so the tensor pipe never waits for an epilogue.
 // * persistent, warp-specialised CTA (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer and
-//   TMEM owner, warps 2-5 = epilogue.  TMEM: 2 x 128(256) accumulator columns + 128 operand + 128
-//   norm columns.
+//   TMEM owner, warps 2-5 = epilogue.  TMEM (512 columns): two buffers of {main 128, small 128}.  For
+//   GDN the epilogue keeps x in registers, overwrites main with the bf16 x^2 operand (hi 64 + lo 64
+//   columns) and the norm accumulates into small.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,7 +44,7 @@ constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
 constexpr int MAX_TAPS = 32;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_X2HI = 256, COL_X2LO = 320, COL_NORM = 384;
+constexpr uint32_t ACC_STRIDE = 256, COL_SMALL = 128;   // per-buffer TMEM layout
 constexpr int GDN_AT = 6;               // k-step of tile t+1 before which GDN(t) is issued
 constexpr int SMEM_LIMIT = 232448;      // 227 KB
 constexpr int BAR_BYTES = 256;
@@ -60,14 +65,19 @@ struct Params {
   Tap taps[MAX_TAPS];
   int kchunks;
   int in_Cs;
-  int Cout;
+  int Cout, CoutPad16;
   int out_fmt, out_Cs;
   void *y0, *y1;
   int Hout, Wout, B;
   const float *bias;
   int act;
-  int gdn;                 // 0 none, 1 GDN, 2 inverse GDN
+  int gdn;                 // 0 none, 1 GDN, 2 inverse GDN (128-channel, TMEM contraction)
   const float *beta;
+  // planar epilogue (Cout <= 4): NCHW fp32 output, optional sub-pixel phases in N, optional 3-channel GDN
+  int planar;              // 0 = channels-last epilogue, 1 = planar
+  int pl_phases, pl_os;    // N index = phase*4 + channel; output pixel = q*pl_os + (ry, rx)
+  int pl_gdn;              // 0 none, 1 GDN, 2 inverse GDN over the Cout channels (registers)
+  const float *pl_gamma;   // fp32 [Cout(j)][Cout(i)] reparametrised (hesic_conv::gdn_w_simt)
   int stages;
   uint32_t stage_bytes, b_bytes;
   int n_tasks;
@@ -180,6 +190,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -289,7 +308,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto acc_full = [&](int b) { return bar_base + 128u + 8u * b; };
   auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };
-  const uint32_t x2_full = bar_base + 160u, norm_full = bar_base + 168u, norm_empty = bar_base + 176u;
+  const uint32_t x2_full = bar_base + 160u, norm_full = bar_base + 168u;
   const uint32_t tmem_slot = bar_base + 192u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -299,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (p.gdn) { prefetch_map(&map_g_hi); prefetch_map(&map_g_lo); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
-    mbar_init(x2_full, 128); mbar_init(norm_full, 1); mbar_init(norm_empty, 128);
+    mbar_init(x2_full, 128); mbar_init(norm_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -311,7 +330,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-  const uint32_t acc_stride = p.gdn ? 128u : 256u;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -354,10 +372,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1u; } };
-      const uint32_t idesc = instr_desc(p.BN), idesc_g = instr_desc(128);
+      const uint32_t idesc_g = instr_desc(128);
       walk_schedule(
           p,
-          [&](int lt, const TaskCoord &, int, int, bool first, bool last) {
+          [&](int lt, const TaskCoord &tk, int, int, bool first, bool last) {
             const int buf = lt & 1;
             if (first) {
               mbar_wait(acc_empty(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u, 2);
@@ -365,37 +383,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             mbar_wait(full_bar(stage), phase, 3);
             tc_fence_after();
+            const uint32_t idesc = instr_desc(min(p.BN, p.CoutPad16 - tk.nt * p.BN));
             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
             const uint64_t a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_TILE_BYTES);
             const uint64_t b_hi = smem_desc(sa + 2 * A_TILE_BYTES), b_lo = smem_desc(sa + 2 * A_TILE_BYTES + p.b_bytes);
-            const uint32_t d = tmem_base + (uint32_t)buf * acc_stride;
+            const uint32_t d_main = tmem_base + (uint32_t)buf * ACC_STRIDE, d_small = d_main + COL_SMALL;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t o = (uint64_t)(k * 2);   // 32 B per K=16 step, encoded >> 4
-              mma_ss(d, a_hi + o, b_hi + o, idesc, (first && k == 0) ? 0u : 1u);
-              mma_ss(d, a_hi + o, b_lo + o, idesc, 1u);
-              mma_ss(d, a_lo + o, b_hi + o, idesc, 1u);
+              const uint32_t acc = (first && k == 0) ? 0u : 1u;
+              mma_ss(d_main, a_hi + o, b_hi + o, idesc, acc);
+              mma_ss(d_small, a_hi + o, b_lo + o, idesc, acc);
+              mma_ss(d_small, a_lo + o, b_hi + o, idesc, 1u);
             }
             tc_commit(empty_bar(stage));
             if (last) tc_commit(acc_full(buf));
             advance();
           },
           [&](int lt, int c) {
+            const int buf = lt & 1;
             if (c == 0) {
               mbar_wait(x2_full, (uint32_t)lt & 1u, 4);
-              mbar_wait(norm_empty, ((uint32_t)lt & 1u) ^ 1u, 5);
               tc_fence_after();
             }
             mbar_wait(full_bar(stage), phase, 6);
             tc_fence_after();
             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
             const uint64_t b_hi = smem_desc(sa + 2 * A_TILE_BYTES), b_lo = smem_desc(sa + 2 * A_TILE_BYTES + p.b_bytes);
-            const uint32_t d = tmem_base + COL_NORM;
+            // A operand (x^2 hi | lo, bf16) sits in this buffer's main columns; the norm overwrites small.
+            const uint32_t x2 = tmem_base + (uint32_t)buf * ACC_STRIDE, d = x2 + COL_SMALL;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t o = (uint64_t)(k * 2);
-              const uint32_t ah = tmem_base + COL_X2HI + (uint32_t)(c * 32 + k * 8);
-              const uint32_t al = tmem_base + COL_X2LO + (uint32_t)(c * 32 + k * 8);
+              const uint32_t ah = x2 + (uint32_t)(c * 32 + k * 8);
+              const uint32_t al = x2 + 64u + (uint32_t)(c * 32 + k * 8);
               mma_ts(d, ah, b_hi + o, idesc_g, (c == 0 && k == 0) ? 0u : 1u);
               mma_ts(d, ah, b_lo + o, idesc_g, 1u);
               mma_ts(d, al, b_hi + o, idesc_g, 1u);
@@ -423,42 +444,99 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const bool valid = ox < p.Wout && oy < p.Hout && b < p.B;
       const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
       const int n0 = tk.nt * p.BN;
-      const uint32_t acc = tmem_base + lane_addr + (uint32_t)buf * acc_stride;
+      const uint32_t acc = tmem_base + lane_addr + (uint32_t)buf * ACC_STRIDE;
 
       mbar_wait(acc_full(buf), ((uint32_t)lt >> 1) & 1u, 7);
       tc_fence_after();
-      if (!p.gdn) {
+      if (p.planar) {
+        uint32_t r[16], q[16];
+        tmem_ld16(acc, r);
+        tmem_ld16(acc + COL_SMALL, q);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(acc_empty(buf));   // the tile is in registers: release the accumulator early
+        const int qx = tx * p.bw + xi, qy = ty * p.bh + yi;
+        if (b < p.B) {
+          float bia[4], bet[4], gam[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            bia[c] = c < p.Cout ? __ldg(p.bias + c) : 0.f;
+            bet[c] = (p.pl_gdn && c < p.Cout) ? __ldg(p.beta + c) : 1.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gam[j * 4 + c] = (p.pl_gdn && c < p.Cout && j < p.Cout) ? __ldg(p.pl_gamma + j * p.Cout + c) : 0.f;
+          }
+#pragma unroll
+          for (int ph = 0; ph < 4; ++ph) {
+            if (ph < p.pl_phases) {
+              const int oy2 = qy * p.pl_os + (ph >> 1), ox2 = qx * p.pl_os + (ph & 1);
+              float x[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) x[c] = (__uint_as_float(r[ph * 4 + c]) + __uint_as_float(q[ph * 4 + c])) + bia[c];
+              if (p.pl_gdn) {
+                float sq[4], o[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sq[c] = x[c] * x[c];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  float nrm = bet[c];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) nrm = fmaf(gam[j * 4 + c], sq[j], nrm);
+                  o[c] = x[c] * (p.pl_gdn == 2 ? sqrtf(nrm) : rsqrtf(nrm));
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) x[c] = o[c];
+              }
+              if (oy2 < p.Hout && ox2 < p.Wout) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if (c < p.Cout)
+                    ((float *)p.y0)[(((size_t)b * p.out_Cs + c) * p.Hout + oy2) * p.Wout + ox2] = apply_act(x[c], p.act);
+              }
+            }
+          }
+        }
+      } else if (!p.gdn) {
         for (int ch = 0; ch < p.BN / 32; ++ch) {
-          uint32_t r[32];
+          const int nb = n0 + ch * 32;
+          if (nb >= p.Cout) break;
+          uint32_t r[32], q[32];
           tmem_ld32(acc + ch * 32, r);
+          tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
           float v[32];
-          const int nb = n0 + ch * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float bj = (nb + j < p.Cout) ? __ldg(p.bias + nb + j) : 0.f;
-            v[j] = apply_act(__uint_as_float(r[j]) + bj, p.act);
+            v[j] = apply_act((__uint_as_float(r[j]) + __uint_as_float(q[j])) + bj, p.act);
           }
           if (valid) store_chunk(p, v, pix, nb);
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
       } else {
-        // pass 1: x = conv + bias; x^2 -> bf16 (hi, lo) A operand in TMEM
-#pragma unroll 1
+        // pass 1: x = conv + bias (kept in registers); x^2 -> bf16 (hi | lo) A operand over the main columns
+        float xs[128];
+#pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
+          uint32_t r[32], q[32];
           tmem_ld32(acc + ch * 32, r);
+          tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            xs[ch * 32 + j] = (__uint_as_float(r[j]) + __uint_as_float(q[j])) + __ldg(p.bias + ch * 32 + j);
+        }
+        // all four chunks are in registers before main is overwritten
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(r[2 * j]) + __ldg(p.bias + ch * 32 + 2 * j);
-            float c = __uint_as_float(r[2 * j + 1]) + __ldg(p.bias + ch * 32 + 2 * j + 1);
+            const float a = xs[ch * 32 + 2 * j], c = xs[ch * 32 + 2 * j + 1];
             split_pair(a * a, c * c, hi[j], lo[j]);
           }
-          tmem_st16(tmem_base + lane_addr + COL_X2HI + ch * 16, hi);
-          tmem_st16(tmem_base + lane_addr + COL_X2LO + ch * 16, lo);
+          tmem_st16(acc + ch * 16, hi);
+          tmem_st16(acc + 64u + ch * 16, lo);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -466,24 +544,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // pass 2: y = x * rsqrt(beta + norm)   (IGDN: * sqrt)
         mbar_wait(norm_full, (uint32_t)lt & 1u, 8);
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32], q[32];
-          tmem_ld32(acc + ch * 32, r);
-          tmem_ld32(tmem_base + lane_addr + COL_NORM + ch * 32, q);
+          uint32_t q[32];
+          tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) + __ldg(p.bias + ch * 32 + j);
-            float nrm = __uint_as_float(q[j]) + __ldg(p.beta + ch * 32 + j);
-            v[j] = x * (p.gdn == 2 ? sqrtf(nrm) : rsqrtf(nrm));
+            const float nrm = __uint_as_float(q[j]) + __ldg(p.beta + ch * 32 + j);
+            v[j] = xs[ch * 32 + j] * (p.gdn == 2 ? sqrtf(nrm) : rsqrtf(nrm));
           }
           if (valid) store_chunk(p, v, pix, ch * 32);
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
-        mbar_arrive(norm_empty);
       }
     }
   }
@@ -540,36 +615,40 @@ static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 static int posmod(int a, int m) { return ((a % m) + m) % m; }
+static bool aligned16(const void *q) { return ((uintptr_t)q & 15u) == 0; }
 
-// N tile: multiple of 32, <= cap, exact divisor of round_up(Cout, 32) when possible (fewest tiles first)
-static int choose_bn(int Cout, bool gdn) {
-  if (gdn) return 128;
-  int c32 = (Cout + 31) / 32 * 32;
-  if (c32 <= 192) return c32;
-  for (int nt = 2; nt <= 16; ++nt) {
-    if (c32 % nt == 0 && (c32 / nt) % 32 == 0 && c32 / nt <= 192) return c32 / nt;
-  }
-  return 128;
+static void add_tap(Params &p, int &n, int dy, int dx, int py, int px, int w) {
+  Tap t;
+  t.dy = (int8_t)dy; t.dx = (int8_t)dx; t.py = (int8_t)py; t.px = (int8_t)px; t.w = (int16_t)w; t.pad_ = 0;
+  p.taps[n++] = t;
 }
 
-struct Plan {
-  Params p;
-  int smem_bytes;
-};
-
+// tap tables of the three operand formulations (see conv.h: hesic_conv::tc_kind)
 static int build_taps(const hesic_conv *c, Params &p) {
   int n = 0;
-  if (!c->transposed) {
-    p.n_phases = 1; p.os = 1;
-    p.tap_begin[0] = 0;
+  p.n_phases = 1; p.os = 1;
+  p.tap_begin[0] = 0;
+  if (c->tc_kind == HESIC_TC_ROW) {
+    // one tap per kernel row; the 5 x-taps x 8 channel slots are the K dimension of the box row
+    for (int ky = 0; ky < 5; ++ky) {
+      if (!c->transposed && c->stride == 2) add_tap(p, n, ky >> 1, 0, ky & 1, 0, ky);
+      else add_tap(p, n, ky, 0, 0, 0, ky);
+    }
+    p.tap_begin[1] = n;
+  } else if (c->tc_kind == HESIC_TC_MERGED) {
+    // stride-2 transposed conv as a 3x3 stride-1 conv onto N = 4 phases x 4 channel slots
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) add_tap(p, n, dy, dx, 0, 0, (dy + 1) * 3 + dx + 1);
+    p.tap_begin[1] = n;
+  } else if (!c->transposed) {
     for (int ky = 0; ky < c->kh; ++ky)
       for (int kx = 0; kx < c->kw; ++kx) {
-        int oy = ky - c->pad, ox = kx - c->pad;
-        Tap t;
-        if (c->stride == 1) { t.dy = oy; t.py = 0; t.dx = ox; t.px = 0; }
-        else { t.py = posmod(oy, 2); t.dy = (oy - t.py) / 2; t.px = posmod(ox, 2); t.dx = (ox - t.px) / 2; }
-        t.w = (int16_t)(ky * c->kw + kx); t.pad_ = 0;
-        p.taps[n++] = t;
+        const int oy = ky - c->pad, ox = kx - c->pad;
+        if (c->stride == 1) add_tap(p, n, oy, ox, 0, 0, ky * c->kw + kx);
+        else {
+          const int py = posmod(oy, 2), px = posmod(ox, 2);
+          add_tap(p, n, (oy - py) / 2, (ox - px) / 2, py, px, ky * c->kw + kx);
+        }
       }
     p.tap_begin[1] = n;
   } else {
@@ -582,10 +661,7 @@ static int build_taps(const hesic_conv *c, Params &p) {
         if (posmod(ry + c->pad - ky, s) != 0) continue;
         for (int kx = 0; kx < c->kw; ++kx) {
           if (posmod(rx + c->pad - kx, s) != 0) continue;
-          Tap t;
-          t.dy = (ry + c->pad - ky) / s; t.dx = (rx + c->pad - kx) / s; t.py = 0; t.px = 0;
-          t.w = (int16_t)(ky * c->kw + kx); t.pad_ = 0;
-          p.taps[n++] = t;
+          add_tap(p, n, (ry + c->pad - ky) / s, (rx + c->pad - kx) / s, 0, 0, ky * c->kw + kx);
         }
       }
       if (n == p.tap_begin[ph]) return -1;   // a phase without taps
@@ -595,24 +671,37 @@ static int build_taps(const hesic_conv *c, Params &p) {
   return n;
 }
 
-static bool aligned16(const void *q) { return ((uintptr_t)q & 15u) == 0; }
-
 }  // namespace tc
 
 bool conv_tc_supported(const hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y) {
   using namespace tc;
-  if (x->fmt != HESIC_FMT_NHWC_SPLIT) return false;
-  if (y->fmt != HESIC_FMT_NHWC_SPLIT && y->fmt != HESIC_FMT_NHWC_F32) return false;
   const int xCs = x->Cs > 0 ? x->Cs : x->C, yCs = y->Cs > 0 ? y->Cs : y->C;
-  if (c->Cin % 8 || c->Cin < 16 || xCs % 8 || !aligned16(x->p0) || !aligned16(x->p1)) return false;
-  if (c->Cout % 8 || c->Cout < 16 || yCs % 8 || !aligned16(y->p0)) return false;
-  if (y->fmt == HESIC_FMT_NHWC_SPLIT && !aligned16(y->p1)) return false;
-  if (c->kh * c->kw > MAX_TAPS || c->kh != c->kw) return false;
-  if (c->stride != 1 && c->stride != 2) return false;
-  if (!c->transposed && c->stride == 2 && ((x->H | x->W) & 1)) return false;
-  if (c->transposed && (c->kh < c->stride)) return false;
-  if (c->has_gdn && c->Cout != 128) return false;
   if ((int64_t)x->B * x->H * x->W == 0 || (int64_t)y->B * y->H * y->W == 0) return false;
+  if (!aligned16(x->p0) || !aligned16(x->p1)) return false;
+  const bool planar_out = c->Cout <= 4;
+  if (planar_out) {
+    if (y->fmt != HESIC_FMT_NCHW_F32) return false;
+    if (c->has_gdn && c->Cout < 2) return false;
+  } else {
+    if (y->fmt != HESIC_FMT_NHWC_SPLIT && y->fmt != HESIC_FMT_NHWC_F32) return false;
+    if (c->Cout % 8 || c->Cout < 16 || yCs % 8 || !aligned16(y->p0)) return false;
+    if (y->fmt == HESIC_FMT_NHWC_SPLIT && !aligned16(y->p1)) return false;
+    if (c->has_gdn && c->Cout != 128) return false;
+  }
+  if (c->tc_kind == HESIC_TC_ROW) {
+    if (x->fmt != HESIC_FMT_ROWPAD8_SPLIT) return false;
+    if (!c->transposed && c->stride == 2 && ((x->H | x->W) & 1)) return false;
+  } else if (c->tc_kind == HESIC_TC_MERGED) {
+    if (x->fmt != HESIC_FMT_NHWC_SPLIT || !planar_out) return false;
+    if (c->Cin % 8 || c->Cin < 16 || xCs % 8) return false;
+  } else {
+    if (x->fmt != HESIC_FMT_NHWC_SPLIT || planar_out) return false;
+    if (c->Cin % 8 || c->Cin < 16 || xCs % 8) return false;
+    if (c->kh * c->kw > MAX_TAPS || c->kh != c->kw) return false;
+    if (c->stride != 1 && c->stride != 2) return false;
+    if (!c->transposed && c->stride == 2 && ((x->H | x->W) & 1)) return false;
+    if (c->transposed && (c->kh < c->stride)) return false;
+  }
   return encode_fn() != nullptr;
 }
 
@@ -632,26 +721,36 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     attr_set = true;
   }
   const int xCs = x->Cs > 0 ? x->Cs : x->C, yCs = y->Cs > 0 ? y->Cs : y->C;
+  const bool planar = c->Cout <= 4;
   Params p;
   memset(&p, 0, sizeof(p));
   const int ntaps = build_taps(c, p);
   if (ntaps <= 0) { set_error("conv tcgen05: unsupported tap structure"); return HESIC_E_UNSUPPORTED; }
-  const int Hq = (y->H + p.os - 1) / p.os, Wq = (y->W + p.os - 1) / p.os;
+  p.planar = planar ? 1 : 0;
+  p.pl_phases = c->tc_kind == HESIC_TC_MERGED ? 4 : 1;
+  p.pl_os = c->tc_kind == HESIC_TC_MERGED ? 2 : 1;
+  const int tile_os = planar ? p.pl_os : p.os;     // output pixels per tile-space pixel, per axis
+  const int Hq = (y->H + tile_os - 1) / tile_os, Wq = (y->W + tile_os - 1) / tile_os;
   p.bw = Wq >= 16 ? 16 : pow2ceil(Wq);
   p.bh = std::min(BM / p.bw, pow2ceil(Hq));
   p.bb = BM / (p.bw * p.bh);
   p.lbw = ilog2(p.bw); p.lbh = ilog2(p.bh);
   p.tiles_x = (Wq + p.bw - 1) / p.bw; p.tiles_y = (Hq + p.bh - 1) / p.bh; p.tiles_b = (y->B + p.bb - 1) / p.bb;
-  p.BN = choose_bn(c->Cout, c->has_gdn);
-  p.n_tiles = (c->Cout + p.BN - 1) / p.BN;
-  p.kchunks = (c->Cin + BK - 1) / BK;
-  p.in_Cs = xCs;
+  // N tile: at most 128 columns (two double-buffered {main, small} accumulators fill the 512 TMEM columns);
+  // the last tile of a layer may be narrower (its MMAs are issued with the remaining N).
+  p.BN = planar ? 16 : std::min(128, (c->Cout + 31) / 32 * 32);
   p.Cout = c->Cout;
+  p.CoutPad16 = planar ? 16 : (c->Cout + 15) / 16 * 16;
+  p.n_tiles = planar ? 1 : (c->Cout + p.BN - 1) / p.BN;
+  p.kchunks = c->tc_kind == HESIC_TC_ROW ? 1 : (c->Cin + BK - 1) / BK;
+  p.in_Cs = xCs;
   p.out_fmt = y->fmt; p.out_Cs = yCs; p.y0 = y->p0; p.y1 = y->p1;
   p.Hout = y->H; p.Wout = y->W; p.B = y->B;
   p.bias = c->bias; p.act = act;
-  p.gdn = c->has_gdn ? (c->gdn_inverse ? 2 : 1) : 0;
+  p.gdn = (!planar && c->has_gdn) ? (c->gdn_inverse ? 2 : 1) : 0;
+  p.pl_gdn = (planar && c->has_gdn) ? (c->gdn_inverse ? 2 : 1) : 0;
   p.beta = c->gdn_beta;
+  p.pl_gamma = c->gdn_w_simt;
   p.b_bytes = (uint32_t)p.BN * 128u;
   p.stage_bytes = 2u * A_TILE_BYTES + 2u * p.b_bytes;
   p.stages = std::min(8, (SMEM_LIMIT - 1024 - BAR_BYTES) / (int)p.stage_bytes);
@@ -665,7 +764,17 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     uint64_t dims[5], strides[4];
     uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bw, 1u, (uint32_t)p.bh, (uint32_t)p.bb};
     const uint64_t e = 2;
-    if (!c->transposed && c->stride == 2) {
+    if (c->tc_kind == HESIC_TC_ROW) {
+      // overlapping rows: element (k, ox) = padded pixel (stride*ox + k/8), channel slot k%8
+      const uint64_t rowB = (uint64_t)(x->W + HESIC_ROWPAD_X) * 8 * e, Hp = (uint64_t)x->H + HESIC_ROWPAD_Y;
+      if (!c->transposed && c->stride == 2) {
+        dims[0] = BK; dims[1] = x->W / 2; dims[2] = 2; dims[3] = Hp / 2; dims[4] = x->B;
+        strides[0] = 16 * e; strides[1] = rowB; strides[2] = 2 * rowB; strides[3] = Hp * rowB;
+      } else {
+        dims[0] = BK; dims[1] = x->W; dims[2] = 1; dims[3] = Hp; dims[4] = x->B;
+        strides[0] = 8 * e; strides[1] = rowB; strides[2] = rowB; strides[3] = Hp * rowB;
+      }
+    } else if (c->tc_kind == HESIC_TC_GENERIC && !c->transposed && c->stride == 2) {
       dims[0] = (uint64_t)xCs + x->C; dims[1] = x->W / 2; dims[2] = 2; dims[3] = x->H / 2; dims[4] = x->B;
       strides[0] = 2ull * xCs * e; strides[1] = (uint64_t)x->W * xCs * e; strides[2] = 2ull * x->W * xCs * e;
       strides[3] = (uint64_t)x->H * x->W * xCs * e;
@@ -679,16 +788,16 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     if (r != HESIC_OK) return r;
   }
   // weight / gamma maps (static per layer; re-encoded when the tile shape changes)
-  if (!c->tc_maps || c->tc_maps_bn != p.BN || c->tc_maps_gdn != (int)c->has_gdn) {
+  const int want_gdn = p.gdn ? 1 : 0;
+  if (!c->tc_maps || c->tc_maps_bn != p.BN || c->tc_maps_gdn != want_gdn) {
     if (!c->tc_maps) c->tc_maps = (unsigned char *)aligned_alloc(128, 4 * sizeof(CUtensorMap));
     CUtensorMap *m = (CUtensorMap *)c->tc_maps;
-    const int taps = c->kh * c->kw;
-    uint64_t dims[3] = {(uint64_t)c->Cin, (uint64_t)c->CoutPad, (uint64_t)taps};
-    uint64_t strides[2] = {(uint64_t)c->Cin * 2, (uint64_t)c->Cin * c->CoutPad * 2};
+    uint64_t dims[3] = {(uint64_t)c->tc_k, (uint64_t)c->CoutPad, (uint64_t)c->tc_taps};
+    uint64_t strides[2] = {(uint64_t)c->tc_k * 2, (uint64_t)c->tc_k * c->CoutPad * 2};
     uint32_t box[3] = {(uint32_t)BK, (uint32_t)p.BN, 1u};
     int r = make_map(&m[0], c->w_hi, 3, dims, strides, box);
     if (r == HESIC_OK) r = make_map(&m[1], c->w_lo, 3, dims, strides, box);
-    if (r == HESIC_OK && c->has_gdn) {
+    if (r == HESIC_OK && want_gdn) {
       uint64_t gd[2] = {128, 128}, gs[1] = {256};
       uint32_t gb[2] = {(uint32_t)BK, 128u};
       r = make_map(&m[2], c->gdn_g_hi, 2, gd, gs, gb);
@@ -697,7 +806,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
       m[2] = m[0]; m[3] = m[1];
     }
     if (r != HESIC_OK) return r;
-    c->tc_maps_bn = p.BN; c->tc_maps_gdn = (int)c->has_gdn;
+    c->tc_maps_bn = p.BN; c->tc_maps_gdn = want_gdn;
   }
   const CUtensorMap *m = (const CUtensorMap *)c->tc_maps;
   const int grid = std::min(p.n_tasks, num_sms);
@@ -710,7 +819,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
 
 // 0 when no tcgen05 kernel has hit its watchdog since the last call; otherwise HESIC_E_CUDA with the
 // first timed-out wait in the error text (tag: 1/9 producer empty, 2 acc_empty, 3/6 full, 4 x2_full,
-// 5 norm_empty, 7 acc_full, 8 norm_full).  Synchronises the device.
+// 7 acc_full, 8 norm_full).  Synchronises the device.
 extern "C" int hesic_tc_status(void) {
   using namespace hesic;
   unsigned int flag = 0, dbg[8] = {0};

@@ -321,6 +321,28 @@ __global__ void __launch_bounds__(256) convert_kernel(const TView x, const TView
   tstore(y, b, c, yy, xx, v);
 }
 
+// NCHW fp32 (C <= 8) -> ROWPAD8 split planes: thread = pixel, one 16-byte store per plane (all 8
+// channel slots, zeros above C), reads coalesced per source plane.
+__global__ void __launch_bounds__(256) rowpad_kernel(const TView x, const TView y, int op, size_t npix) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  int xx = i % x.W; size_t r = i / x.W;
+  int yy = r % x.H; int b = r / x.H;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    v[c] = c < x.C ? ((const float *)x.p0)[(((size_t)b * x.Cs + c) * x.H + yy) * x.W + xx] : 0.f;
+    if (op == HESIC_OP_ABS) v[c] = fabsf(v[c]);
+    else if (op == HESIC_OP_ROUND) v[c] = rintf(v[c]);
+  }
+  __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) split_bf16(v[c], hi[c], lo[c]);
+  size_t o = toff(y, b, 0, yy, xx);
+  *reinterpret_cast<uint4 *>((__nv_bfloat16 *)y.p0 + o) = *reinterpret_cast<const uint4 *>(hi);
+  *reinterpret_cast<uint4 *>((__nv_bfloat16 *)y.p1 + o) = *reinterpret_cast<const uint4 *>(lo);
+}
+
 // ---------------------------------------------------------------------------------------------
 // integer preparation for the host rANS coder (bit-exact with the reference)
 __global__ void __launch_bounds__(256) symbols_kernel(const TView x, const float *__restrict__ cmeans, const TView means,
@@ -498,6 +520,14 @@ extern "C" int hesic_convert(const hesic_tensor *x, const hesic_tensor *y, int o
   HESIC_REQUIRE(op >= 0 && op <= 2, "convert: bad op");
   size_t n = numel(y);
   if (n == 0) return HESIC_OK;
+  if (y->fmt == HESIC_FMT_ROWPAD8_SPLIT && x->fmt == HESIC_FMT_NCHW_F32 && ((uintptr_t)y->p0 & 15) == 0 &&
+      ((uintptr_t)y->p1 & 15) == 0) {
+    // whole-pixel fast path (the view starts at channel slot 0 and owns all 8 slots)
+    size_t npix = (size_t)y->B * y->H * y->W;
+    rowpad_kernel<<<nblk(npix), 256, 0, as_stream(stream)>>>(view(x), view(y), op, npix);
+    HESIC_LAUNCHED("rowpad_kernel");
+    return HESIC_OK;
+  }
   convert_kernel<<<nblk(n), 256, 0, as_stream(stream)>>>(view(x), view(y), op, n);
   HESIC_LAUNCHED("convert_kernel");
   return HESIC_OK;

@@ -83,23 +83,27 @@ class ConvPlan:
 def conv2d(x, plan, act=C.ACT_NONE, path=C.PATH_AUTO):
     """NCHW fp32 in -> NCHW fp32 out through a loaded ConvPlan."""
     x = _f32(x)
-    B, _, H, W = x.shape
+    B, Cin, H, W = x.shape
     Ho, Wo = plan.out_hw(H, W)
-    y = torch.empty((B, plan.geom[1], Ho, Wo), device=x.device, dtype=torch.float32)
+    Cout = plan.geom[1]
+    y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
     if path == C.PATH_SIMT:
         plan.run(C.nchw(x), C.nchw(y), act, path)
         return y
-    # tensor-core path consumes / produces the split NHWC planes
-    xs = torch.empty((2, B, H, W, x.shape[1]), device=x.device, dtype=torch.bfloat16)
-    C.check(_lib.hesic_convert(C.ref(C.nchw(x)), C.ref(C.split(xs)), C.OP_COPY, C.stream()))
-    yn = torch.empty((B, Ho, Wo, plan.geom[1]), device=x.device, dtype=torch.float32)
-    try:
-        plan.run(C.split(xs), C.nhwc(yn), act, path)
-    except NotImplementedError:
-        if path == C.PATH_TC:
-            raise
-        plan.run(C.nchw(x), C.nchw(y), act, C.PATH_SIMT)
+    # the tensor-core path consumes bf16 (hi, lo) planes: ROWPAD8 for the <= 8-channel edge layers,
+    # channels-last otherwise
+    if Cin <= 8:
+        xin = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, 8), device=x.device, dtype=torch.bfloat16)
+        xd = C.rowpad(xin, Cin)
+    else:
+        xin = torch.empty((2, B, H, W, Cin), device=x.device, dtype=torch.bfloat16)
+        xd = C.split(xin)
+    C.check(_lib.hesic_convert(C.ref(C.nchw(x)), C.ref(xd), C.OP_COPY, C.stream()))
+    if Cout <= 4:
+        plan.run(xd, C.nchw(y), act, path)     # planar epilogue writes NCHW directly
         return y
+    yn = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+    plan.run(xd, C.nhwc(yn), act, path)
     C.check(_lib.hesic_convert(C.ref(C.nhwc(yn)), C.ref(C.nchw(y)), C.OP_COPY, C.stream()))
     return y
 

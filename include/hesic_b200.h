@@ -37,7 +37,14 @@ enum {
 /* Activation layouts in HBM.  SPLIT is the native inter-layer format of the conv stack:
  * two bf16 planes (hi, lo) with value = float(hi) + float(lo), i.e. a 16-bit-mantissa
  * decomposition of the fp32 value that feeds the bf16x3 tcgen05 path without conversion. */
-enum { HESIC_FMT_NCHW_F32 = 0, HESIC_FMT_NHWC_F32 = 1, HESIC_FMT_NHWC_SPLIT = 2 };
+enum { HESIC_FMT_NCHW_F32 = 0, HESIC_FMT_NHWC_F32 = 1, HESIC_FMT_NHWC_SPLIT = 2, HESIC_FMT_ROWPAD8_SPLIT = 3 };
+/* ROWPAD8_SPLIT is the input format of the full-resolution edge layers (Cin <= 8: the RGB images and
+ * the 6-channel concatenations of newnet1.py:643,686): bf16 (hi, lo) planes of
+ * [B][H + HESIC_ROWPAD_Y][W + HESIC_ROWPAD_X][8], image at row/column offset 2, border and unused
+ * channels zero.  One TMA box row of 64 elements = the 8 pixels x 8 channels a 5-tap kernel row
+ * needs, so the tensor-core path reads it as an implicit im2col with K = 64 per kernel row. */
+#define HESIC_ROWPAD_Y 4
+#define HESIC_ROWPAD_X 8
 
 typedef struct {
   void *p0;        /* dev: float data, or bf16 'hi' plane, already offset to channel 0 of the view */
