@@ -114,7 +114,7 @@ def run_ours(args):
     import hesic_b200
     from hesic_b200 import _capi as C
     from hesic_b200 import functional as F
-    from hesic_b200 import synth
+    from hesic_b200 import sharding, synth
     hesic_b200.install()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -142,7 +142,6 @@ def run_ours(args):
         sets.append((x1.to(dev), x2.to(dev), h.to(dev)))
     partial = torch.zeros(6, device=dev, dtype=torch.float64)   # sum log2 p (y1,y2,z1,z2), SSE view1, SSE view2
     result_host = torch.zeros(6, dtype=torch.float64).pin_memory()
-    n_pix = B * 512 * 512
 
     def step(x1, x2, h):
         out = net(x1, x2, h)
@@ -150,14 +149,12 @@ def run_ours(args):
         partial[:4].copy_(net.hesic_engine.log2_sums)
         F.sum_squared_error(out["x1_hat"], x1, partial[4:5])
         F.sum_squared_error(out["x2_hat"], x2, partial[5:6])
-        if world > 1:
-            dist.all_reduce(partial)     # the path's only collective: <= 48 bytes over NVLink
+        sharding.reduce_partials(partial)     # the path's only collective: 48 bytes over NVLink (no-op at N=1)
         return out
 
-    def metrics(p, pixels):
-        p = [float(v) for v in p]
-        return {"bpp": -(p[0] + p[1] + p[2] + p[3]) / pixels, "psnr1": 10 * math.log10(1 / (p[4] / (3 * pixels))),
-                "psnr2": 10 * math.log10(1 / (p[5] / (3 * pixels)))}
+    def metrics(p, n_pairs):
+        m = sharding.metrics_from_partials(p, n_pairs, 512, 512)
+        return {k: m[k] for k in ("bpp", "psnr1", "psnr2")}
 
     def sync():
         torch.cuda.synchronize()
@@ -186,7 +183,7 @@ def run_ours(args):
     C.lib.hesic_launch_count(1)
     ms = timed(lambda i: step(*sets[i % 2]), args.steps)
     launches = C.lib.hesic_launch_count(0)
-    m_dev = metrics(partial.cpu(), n_pix * world)
+    m_dev = metrics(partial.cpu(), B * world)
 
     # end to end through the public API: pinned host inputs -> H2D -> forward -> metric partials -> D2H
     def e2e_step(i):

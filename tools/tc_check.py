@@ -41,6 +41,13 @@ GROUPS = {
                (128, 3, 5, 2, True, 256, 256, 2, 2, 0)],
     "edge": [(3, 128, 5, 2, False, 512, 512, 16, 1, 0), (128, 3, 5, 2, True, 256, 256, 16, 2, 0), (6, 3, 5, 1, False, 512, 512, 16, 1, 0),
              (6, 3, 5, 1, True, 512, 512, 16, 0, 0)],
+    "time": [(3, 128, 5, 2, False, 512, 512, 16, 1, 0), (3, 128, 5, 2, False, 512, 512, 16, 0, 0),
+             (128, 128, 5, 2, False, 256, 256, 16, 1, 0), (128, 128, 5, 2, False, 256, 256, 16, 0, 0),
+             (128, 128, 5, 2, True, 128, 128, 16, 2, 0), (128, 128, 5, 2, True, 128, 128, 16, 0, 0),
+             (128, 128, 5, 2, True, 64, 64, 16, 2, 0), (192, 128, 5, 2, True, 32, 32, 16, 2, 0),
+             (128, 128, 5, 2, False, 128, 128, 16, 1, 0), (128, 192, 5, 2, False, 64, 64, 16, 0, 0),
+             (128, 960, 5, 1, False, 32, 32, 16, 0, 1), (320, 128, 5, 1, False, 32, 32, 16, 0, 1),
+             (128, 3, 5, 2, True, 256, 256, 16, 2, 0), (6, 3, 5, 1, False, 512, 512, 16, 1, 0)],
     "big": [(128, 128, 5, 2, False, 256, 256, 4, 1, 0), (128, 128, 5, 2, True, 128, 128, 4, 2, 0), (320, 128, 5, 1, False, 32, 32, 16, 0, 1),
             (128, 960, 5, 1, False, 32, 32, 16, 0, 1)],
 }
@@ -58,6 +65,39 @@ def to_split(x):
     C.check(C.lib.hesic_convert(C.ref(C.nchw(x)), C.ref(d), C.OP_COPY, C.stream()))
     d._keep = xs
     return d
+
+
+def time_case(case):
+    """tcgen05 path only: milliseconds per launch (split / planar output), L2 flushed between launches."""
+    Cin, Cout, k, s, tr, H, W, B, gdn, act = case
+    g = torch.Generator().manual_seed(1)
+    mod = (deconv if tr else conv)(Cin, Cout, kernel_size=k, stride=s).to(DEV)
+    plan = mod.hesic_plan()
+    if gdn:
+        plan.set_gdn(torch.ones(Cout, device=DEV), 0.1 * torch.eye(Cout, device=DEV) + 0.01, gdn == 2)
+    xd = to_split(torch.randn(B, Cin, H, W, generator=g).to(DEV))
+    Ho, Wo = plan.out_hw(H, W)
+    if Cout <= 4:
+        yt = torch.zeros((B, Cout, Ho, Wo), device=DEV); yd = C.nchw(yt)
+    else:
+        yt = torch.zeros((2, B, Ho, Wo, Cout), device=DEV, dtype=torch.bfloat16); yd = C.split(yt)
+    flush = torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
+    ts = []
+    for i in range(6):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.run(xd, yd, act, C.PATH_TC)
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            ts.append(e0.elapsed_time(e1))
+    C.check(C.lib.hesic_tc_status())
+    ms = sum(ts) / len(ts)
+    fl = 2.0 * B * Ho * Wo * Cout * Cin * k * k / (s * s if tr else 1) + (2.0 * B * Ho * Wo * Cout * Cout if gdn else 0)
+    out_b = yt.numel() * yt.element_size()
+    print(f"TIME {case} {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s(alg)  out {out_b / ms / 1e6:.0f} GB/s", flush=True)
+    return True
 
 
 def run_case(case, timing=False):
@@ -136,7 +176,7 @@ def main():
         for case in GROUPS[gname]:
             t0 = time.time()
             try:
-                ok &= run_case(case, timing)
+                ok &= time_case(case) if gname == "time" else run_case(case, timing)
             except Exception as e:  # noqa: BLE001
                 print(f"EXC {case}: {type(e).__name__}: {e}", flush=True)
                 return 1
