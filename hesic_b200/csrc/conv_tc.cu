@@ -48,6 +48,8 @@ constexpr uint32_t ACC_STRIDE = 256, COL_SMALL = 128;   // per-buffer TMEM layou
 constexpr int GDN_AT = 6;               // k-step of tile t+1 before which GDN(t) is issued
 constexpr int SMEM_LIMIT = 232448;      // 227 KB
 constexpr int BAR_BYTES = 256;
+constexpr int CHAN_BYTES = 1024;      // bias + beta tables of the current n-tile
+constexpr int STAGING_BYTES = 2 * A_TILE_BYTES;   // two [128 px][128 B] swizzled store tiles
 
 struct Tap {
   int8_t dy, dx, py, px;
@@ -78,6 +80,7 @@ struct Params {
   int pl_phases, pl_os;    // N index = phase*4 + channel; output pixel = q*pl_os + (ry, rx)
   int pl_gdn;              // 0 none, 1 GDN, 2 inverse GDN over the Cout channels (registers)
   const float *pl_gamma;   // fp32 [Cout(j)][Cout(i)] reparametrised (hesic_conv::gdn_w_simt)
+  int tma_store;           // 1: epilogue stages 128-byte-wide tiles in smem and writes them with TMA
   int stages;
   uint32_t stage_bytes, b_bytes;
   int n_tasks;
@@ -153,6 +156,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint32_t dst
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -223,12 +241,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&v);
 }
+// (a, b) -> packed bf16 pairs hi = rn(a), rn(b) and lo = rn(a - hi_a), rn(b - hi_b); a in the low half.
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
-  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  __nv_bfloat162 h;
-  h.x = ah; h.y = bh;
-  hi = *reinterpret_cast<uint32_t *>(&h);
-  lo = pack_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
+  hi = pack_bf16(a, b);
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16(a - ah, b - bh);
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// 32 consecutive per-channel constants (bias / beta) from the CTA's smem table: 8 broadcast 16-byte loads
+__device__ __forceinline__ void ld_chan32(uint32_t addr, float (&o)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = ld_shared_f4(addr + 16u * j);
+    o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
+  }
 }
 
 struct TaskCoord {
@@ -299,10 +332,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+               const __grid_constant__ CUtensorMap map_y0, const __grid_constant__ CUtensorMap map_y1,
                const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + (uint32_t)p.stages * p.stage_bytes;
+  const uint32_t stg_base = smem_base + (uint32_t)p.stages * p.stage_bytes;   // epilogue store staging (tma_store)
+  const uint32_t bar_base = stg_base + (p.tma_store ? (uint32_t)STAGING_BYTES : 0u);
   // barrier map (8 B each)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
@@ -310,12 +345,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };
   const uint32_t x2_full = bar_base + 160u, norm_full = bar_base + 168u;
   const uint32_t tmem_slot = bar_base + 192u;
+  const uint32_t bias_s = bar_base + BAR_BYTES, beta_s = bias_s + 512u;   // per-tile channel constants (fp32 x 128 each)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&map_a_hi); prefetch_map(&map_a_lo); prefetch_map(&map_w_hi); prefetch_map(&map_w_lo);
     if (p.gdn) { prefetch_map(&map_g_hi); prefetch_map(&map_g_lo); }
+    if (p.tma_store) { prefetch_map(&map_y0); prefetch_map(&map_y1); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
     mbar_init(x2_full, 128); mbar_init(norm_full, 1);
@@ -434,6 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int xi = row & (p.bw - 1), yi = (row >> p.lbw) & (p.bh - 1), bi = row >> (p.lbw + p.lbh);
     const int txy = p.tiles_x * p.tiles_y;
     int lt = 0;
+    uint32_t su = 0;   // running store-unit counter (fp32 staging slot = su & 1, across tiles)
     for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x, ++lt) {
       const TaskCoord tk = decode_task(p, task);
       const int buf = lt & 1;
@@ -445,6 +483,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
       const int n0 = tk.nt * p.BN;
       const uint32_t acc = tmem_base + lane_addr + (uint32_t)buf * ACC_STRIDE;
+
+      // Output of one 32-channel chunk.  tma_store: the chunk is written into a 128B-swizzled
+      // [128 px][128 B] staging tile (conflict-free 16-byte stores) and one thread hands full tiles to
+      // TMA, which writes whole pixel rows and clips everything outside the tensor; else each thread
+      // stores its pixel directly.
+      const bool is_issuer = threadIdx.x == 64;
+      const uint32_t row_off = stg_base + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+      const int c_fold = rx * p.out_Cs, mx = tx * p.bw, my = ty * p.bh, mb = tb * p.bb;
+      auto emit = [&](const float (&v)[32], int ch, int nb, bool last_chunk) {
+        if (!p.tma_store) {
+          if (valid) store_chunk(p, v, pix, nb);
+          return;
+        }
+        if (p.out_fmt == HESIC_FMT_NHWC_F32) {
+          const uint32_t slot = (su++ & 1u) * A_TILE_BYTES;
+          if (is_issuer) bulk_wait_read<1>();     // the store that used this slot two chunks ago has been read
+          epi_bar();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(row_off + slot + (((uint32_t)j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                         __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          fence_async_smem();
+          epi_bar();
+          if (is_issuer) {
+            tma_store_5d(&map_y0, stg_base + slot, c_fold + nb, mx, ry, my, mb);
+            bulk_commit();
+          }
+        } else {
+          const int half = ch & 1;                // two chunks fill one 64-channel (hi, lo) tile pair
+          if (half == 0) {
+            if (is_issuer) bulk_wait_read<0>();
+            epi_bar();
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split_pair(v[g * 8 + 0], v[g * 8 + 1], h0, l0);
+            split_pair(v[g * 8 + 2], v[g * 8 + 3], h1, l1);
+            split_pair(v[g * 8 + 4], v[g * 8 + 5], h2, l2);
+            split_pair(v[g * 8 + 6], v[g * 8 + 7], h3, l3);
+            const uint32_t o = row_off + (((uint32_t)(half * 4 + g) ^ sw) << 4);
+            st_shared_v4(o, h0, h1, h2, h3);
+            st_shared_v4(o + A_TILE_BYTES, l0, l1, l2, l3);
+          }
+          if (half == 1 || last_chunk) {
+            fence_async_smem();
+            epi_bar();
+            if (is_issuer) {
+              const int c0 = c_fold + nb - half * 32;
+              tma_store_5d(&map_y0, stg_base, c0, mx, ry, my, mb);
+              tma_store_5d(&map_y1, stg_base + A_TILE_BYTES, c0, mx, ry, my, mb);
+              bulk_commit();
+            }
+          }
+        }
+      };
+
+      if (!p.planar) {
+        // channel constants of this n-tile -> smem (overlaps the tile's MMAs)
+        epi_bar();
+        const int ci = (int)threadIdx.x - 64;
+        st_shared_f32(bias_s + 4u * ci, (n0 + ci < p.Cout) ? __ldg(p.bias + n0 + ci) : 0.f);
+        if (p.gdn) st_shared_f32(beta_s + 4u * ci, __ldg(p.beta + ci));
+        epi_bar();
+      }
+      // activation as max(v, slope * v): slope 1 = none, 0 = ReLU, 0.01 = LeakyReLU
+      const float act_slope = p.act == HESIC_ACT_RELU ? 0.f : (p.act == HESIC_ACT_LEAKY_RELU ? 0.01f : 1.f);
 
       mbar_wait(acc_full(buf), ((uint32_t)lt >> 1) & 1u, 7);
       tc_fence_after();
@@ -504,12 +609,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
           float v[32];
+          ld_chan32(bias_s + 128u * ch, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float bj = (nb + j < p.Cout) ? __ldg(p.bias + nb + j) : 0.f;
-            v[j] = apply_act((__uint_as_float(r[j]) + __uint_as_float(q[j])) + bj, p.act);
+            const float t = (__uint_as_float(r[j]) + __uint_as_float(q[j])) + v[j];
+            v[j] = fmaxf(t, t * act_slope);
           }
-          if (valid) store_chunk(p, v, pix, nb);
+          emit(v, ch, nb, (nb + 32 >= p.Cout) || (ch == p.BN / 32 - 1));
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
@@ -523,8 +629,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            xs[ch * 32 + j] = (__uint_as_float(r[j]) + __uint_as_float(q[j])) + __ldg(p.bias + ch * 32 + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = ld_shared_f4(bias_s + 128u * ch + 16u * j);
+            xs[ch * 32 + 4 * j + 0] = (__uint_as_float(r[4 * j + 0]) + __uint_as_float(q[4 * j + 0])) + t.x;
+            xs[ch * 32 + 4 * j + 1] = (__uint_as_float(r[4 * j + 1]) + __uint_as_float(q[4 * j + 1])) + t.y;
+            xs[ch * 32 + 4 * j + 2] = (__uint_as_float(r[4 * j + 2]) + __uint_as_float(q[4 * j + 2])) + t.z;
+            xs[ch * 32 + 4 * j + 3] = (__uint_as_float(r[4 * j + 3]) + __uint_as_float(q[4 * j + 3])) + t.w;
+          }
         }
         // all four chunks are in registers before main is overwritten
 #pragma unroll
@@ -550,12 +661,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
           float v[32];
+          ld_chan32(beta_s + 128u * ch, v);
+          if (p.gdn == 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float nrm = __uint_as_float(q[j]) + __ldg(p.beta + ch * 32 + j);
-            v[j] = xs[ch * 32 + j] * (p.gdn == 2 ? sqrtf(nrm) : rsqrtf(nrm));
+            for (int j = 0; j < 32; ++j) v[j] = xs[ch * 32 + j] * sqrtf(__uint_as_float(q[j]) + v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = xs[ch * 32 + j] * rsqrtf(__uint_as_float(q[j]) + v[j]);
           }
-          if (valid) store_chunk(p, v, pix, ch * 32);
+          emit(v, ch, ch * 32, ch == 3);
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
@@ -563,6 +677,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   }
 
+  if (p.tma_store && threadIdx.x == 64) bulk_wait_all();   // staged tiles fully written before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -591,16 +706,16 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// rank-n bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..n-1.
+// rank-n tensor map (bf16 unless stated), 128B swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..n-1.
 static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
-                    const uint32_t *box) {
+                    const uint32_t *box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return HESIC_E_CUDA; }
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -753,10 +868,40 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.pl_gamma = c->gdn_w_simt;
   p.b_bytes = (uint32_t)p.BN * 128u;
   p.stage_bytes = 2u * A_TILE_BYTES + 2u * p.b_bytes;
-  p.stages = std::min(8, (SMEM_LIMIT - 1024 - BAR_BYTES) / (int)p.stage_bytes);
+  // TMA-store epilogue: channels-last outputs; for the sub-pixel phases of a transposed conv the phase
+  // column is folded into the channel dimension of the output map, which needs whole store tiles.
+  const int store_ch = y->fmt == HESIC_FMT_NHWC_SPLIT ? 64 : 32;
+  const int esz = y->fmt == HESIC_FMT_NHWC_SPLIT ? 2 : 4;
+  p.tma_store = (!planar && (yCs * esz) % 16 == 0 &&
+                 (p.os == 1 || (p.os == 2 && c->Cout % store_ch == 0 && !((y->H | y->W) & 1)))) ? 1 : 0;
+  if (getenv("HESIC_TC_DIRECT_STORE")) p.tma_store = 0;
+  const int fixed = 1024 + BAR_BYTES + CHAN_BYTES + (p.tma_store ? STAGING_BYTES : 0);
+  p.stages = std::min(8, (SMEM_LIMIT - fixed) / (int)p.stage_bytes);
   if (p.stages < 2) { set_error("conv tcgen05: tile does not fit shared memory"); return HESIC_E_UNSUPPORTED; }
   p.n_tasks = p.tiles_x * p.tiles_y * p.tiles_b * p.n_phases * p.n_tiles;
-  const int smem_bytes = p.stages * (int)p.stage_bytes + 1024 + BAR_BYTES;
+  const int smem_bytes = p.stages * (int)p.stage_bytes + fixed;
+
+  CUtensorMap my0, my1;
+  memset(&my0, 0, sizeof(my0));
+  memset(&my1, 0, sizeof(my1));
+  if (p.tma_store) {
+    uint64_t dims[5], strides[4];
+    uint32_t box[5] = {(uint32_t)store_ch, (uint32_t)p.bw, 1u, (uint32_t)p.bh, (uint32_t)p.bb};
+    const uint64_t e = (uint64_t)esz;
+    if (p.os == 2) {
+      dims[0] = (uint64_t)yCs + y->C; dims[1] = y->W / 2; dims[2] = 2; dims[3] = y->H / 2; dims[4] = y->B;
+      strides[0] = 2ull * yCs * e; strides[1] = (uint64_t)y->W * yCs * e; strides[2] = 2ull * y->W * yCs * e;
+      strides[3] = (uint64_t)y->H * y->W * yCs * e;
+    } else {
+      dims[0] = y->C; dims[1] = y->W; dims[2] = 1; dims[3] = y->H; dims[4] = y->B;
+      strides[0] = (uint64_t)yCs * e; strides[1] = (uint64_t)y->W * yCs * e; strides[2] = (uint64_t)y->W * yCs * e;
+      strides[3] = (uint64_t)y->H * y->W * yCs * e;
+    }
+    const CUtensorMapDataType dt = esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    int r = make_map(&my0, y->p0, 5, dims, strides, box, dt);
+    if (r == HESIC_OK && esz == 2) r = make_map(&my1, y->p1, 5, dims, strides, box, dt);
+    if (r != HESIC_OK) return r;
+  }
 
   // activation maps (depend on the input pointer -> encoded per call, host-only work)
   CUtensorMap ma_hi, ma_lo;
@@ -810,7 +955,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   }
   const CUtensorMap *m = (const CUtensorMap *)c->tc_maps;
   const int grid = std::min(p.n_tasks, num_sms);
-  conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], m[2], m[3], p);
+  conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], m[2], m[3], my0, my1, p);
   HESIC_LAUNCHED("conv_tc_kernel");
   return HESIC_OK;
 }
