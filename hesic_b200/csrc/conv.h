@@ -36,6 +36,11 @@ int conv_out_size(const hesic_conv *c, int in, int k);
 int conv_forward_simt(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s);
 int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s);
 bool conv_tc_supported(const hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y);
+// conv_small.cu: exact-fp32 CUDA-core stencil for the full-resolution 6->3 / 3->3 k5 s1 layers; xb (may be
+// null) supplies the channels after xa's (torch.cat on the reference side)
+bool conv_small_supported(const hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y);
+int conv_forward_small(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y, int act,
+                       cudaStream_t s);
 int gdn_simt(const hesic_tensor *x, const hesic_tensor *y, const float *beta_rp, const float *w_simt, int inverse,
              cudaStream_t s);
 }  // namespace hesic

@@ -384,19 +384,29 @@ extern "C" int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float 
   return HESIC_OK;
 }
 
-extern "C" int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, int path,
-                                  void *stream) {
+static int conv_forward_any(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *xb, const hesic_tensor *y, int act,
+                            int path, void *stream) {
   HESIC_REQUIRE(c && c->loaded, "hesic_conv_forward: weights not loaded");
   int r;
   if ((r = check_tensor(x, "conv input")) != HESIC_OK) return r;
+  if (xb && (r = check_tensor(xb, "conv input (second part)")) != HESIC_OK) return r;
   if ((r = check_tensor(y, "conv output")) != HESIC_OK) return r;
-  HESIC_REQUIRE(x->C == c->Cin, "conv: input has %d channels, layer expects %d", x->C, c->Cin);
+  const int Cin = x->C + (xb ? xb->C : 0);
+  HESIC_REQUIRE(Cin == c->Cin, "conv: input has %d channels, layer expects %d", Cin, c->Cin);
+  if (xb) HESIC_REQUIRE(xb->B == x->B && xb->H == x->H && xb->W == x->W, "conv: the two input parts differ in shape");
   HESIC_REQUIRE(y->C == c->Cout, "conv: output has %d channels, layer produces %d", y->C, c->Cout);
   HESIC_REQUIRE(y->B == x->B, "conv: batch mismatch");
   int Ho = conv_out_size(c, x->H, c->kh), Wo = conv_out_size(c, x->W, c->kw);
   HESIC_REQUIRE(y->H == Ho && y->W == Wo, "conv: output is %dx%d, expected %dx%d", y->H, y->W, Ho, Wo);
   HESIC_REQUIRE(act >= 0 && act <= 2, "conv: bad activation %d", act);
   cudaStream_t s = as_stream(stream);
+  // full-resolution few-channel layers: exact-fp32 stencil (AUTO and SIMT both mean "CUDA cores" here)
+  if (path != HESIC_PATH_TCGEN05 && conv_small_supported(c, x, xb, y) && (path == HESIC_PATH_AUTO || xb))
+    return conv_forward_small(c, x, xb, y, act, s);
+  if (xb) {
+    set_error("conv: a two-part (concatenated) input is only supported by the few-channel stencil path");
+    return HESIC_E_UNSUPPORTED;
+  }
   bool tc_ok = conv_tc_supported(c, x, y);
   if (path == HESIC_PATH_TCGEN05 && !tc_ok) {
     set_error("conv: shape/format not supported by the tcgen05 path");
@@ -404,6 +414,17 @@ extern "C" int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const he
   }
   if (path == HESIC_PATH_TCGEN05 || (path == HESIC_PATH_AUTO && tc_ok)) return conv_forward_tc(c, x, y, act, s);
   return conv_forward_simt(c, x, y, act, s);
+}
+
+extern "C" int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, int path,
+                                  void *stream) {
+  return conv_forward_any(c, x, nullptr, y, act, path, stream);
+}
+
+extern "C" int hesic_conv_forward_cat(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y,
+                                      int act, int path, void *stream) {
+  HESIC_REQUIRE(xb != nullptr, "hesic_conv_forward_cat: null second input");
+  return conv_forward_any(c, xa, xb, y, act, path, stream);
 }
 
 extern "C" int hesic_gdn(const hesic_tensor *x, const hesic_tensor *y, const float *beta, const float *gamma,

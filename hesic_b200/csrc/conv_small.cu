@@ -1,0 +1,211 @@
+// Full-resolution few-channel 5x5 layers on CUDA cores: Encoder2.pre_conv (+pre_gdn) and
+// Decoder2.after_conv (newnet1.py:629-630,643-644,669-670,685-686), i.e. conv / stride-1 transposed
+// conv with Cin <= 8, Cout <= 4, k5, pad 2, evaluated in exact fp32 FMA.
+//
+// Why not the tensor-core path: with 3 output channels the GEMM has N = 3 (padded to 16) and every
+// 128-pixel A tile is streamed through shared memory five times (one 16 KB box per kernel row, hi and
+// lo planes) for 0.24 GFLOP per pair -- the layer is bound by L2->SM fills at ~5 TFLOP/s.  As a direct
+// stencil the whole layer is 450 FMA per output pixel and one read of the input (24 B) + one write of
+// the output (12 B): HBM-bound on paper, FMA-issue-bound in practice.
+//
+// Block = 64 x 16 output pixels, 128 threads, each thread 2 rows x 4 consecutive pixels x Cout
+// accumulators.  The zero-padded input tile (Cin x 20 x 68 fp32) and the weights ([ci][ky][kx][4], the
+// kernel flipped for the transposed form) sit in shared memory; inner loop per (ci, ky): four 16-byte
+// input loads + five 16-byte weight loads feed 120 FMAs.  torch.cat on the reference side is a second
+// input pointer (channels [Ca, Cin) come from xb), so the concatenation is never materialised.  The
+// output is NCHW fp32 or, when the consumer is the 3->128 tensor-core layer, directly its ROWPAD8
+// bf16 (hi, lo) input format.
+#include "conv.h"
+
+namespace hesic {
+namespace small {
+
+constexpr int TW = 64, TH = 16, NT = 128, PITCH = TW + 4, ROWS = TH + 4;
+
+struct Args {
+  const float *xa, *xb;   // NCHW fp32; channels [0, Ca) from xa, [Ca, Cin) from xb
+  int Ca, CsA, CsB;
+  int B, H, W;
+  const float *w;         // hesic_conv::w_simt  [(ky*5+kx)*Cin + ci][Cout]
+  const float *bias;
+  int transposed;
+  int gdn;                // 0 none, 1 GDN, 2 inverse GDN over the Cout channels
+  const float *beta, *gamma;   // reparametrised beta [Cout]; gamma as [j][i] (hesic_conv::gdn_w_simt)
+  int act;
+  int out_fmt, out_Cs;    // NCHW fp32 (channel slice of out_Cs) or ROWPAD8 split
+  void *y0, *y1;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(NT) conv_small_kernel(const Args a) {
+  extern __shared__ __align__(16) float sm[];
+  float *wsm = sm;                       // [CIN*25][4]
+  float *in = sm + CIN * 25 * 4;         // [CIN][ROWS][PITCH]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+
+  for (int i = tid; i < CIN * 25 * 4; i += NT) {
+    const int co = i & 3, t = i >> 2;
+    const int kx = t % 5, ky = (t / 5) % 5, ci = t / 25;
+    const int tap = a.transposed ? (4 - ky) * 5 + (4 - kx) : ky * 5 + kx;
+    wsm[i] = co < COUT ? __ldg(a.w + (size_t)(tap * CIN + ci) * COUT + co) : 0.f;
+  }
+  for (int i = tid; i < CIN * ROWS * PITCH; i += NT) {
+    const int col = i % PITCH, r = (i / PITCH) % ROWS, c = i / (PITCH * ROWS);
+    const int gy = y0 - 2 + r, gx = x0 - 2 + col;
+    float v = 0.f;
+    if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+      const float *src = c < a.Ca ? a.xa + ((size_t)b * a.CsA + c) * a.H * a.W
+                                  : a.xb + ((size_t)b * a.CsB + (c - a.Ca)) * a.H * a.W;
+      v = __ldg(src + (size_t)gy * a.W + gx);
+    }
+    in[i] = v;
+  }
+  __syncthreads();
+
+  float acc[2][4][COUT];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) acc[r][p][co] = 0.f;
+
+#pragma unroll 1
+  for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      float v[2][8];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float *row = in + ((size_t)ci * ROWS + ty + 8 * r + ky) * PITCH + 4 * tx;
+        const float4 q0 = *reinterpret_cast<const float4 *>(row), q1 = *reinterpret_cast<const float4 *>(row + 4);
+        v[r][0] = q0.x; v[r][1] = q0.y; v[r][2] = q0.z; v[r][3] = q0.w;
+        v[r][4] = q1.x; v[r][5] = q1.y; v[r][6] = q1.z; v[r][7] = q1.w;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const float4 wq = *reinterpret_cast<const float4 *>(wsm + ((ci * 5 + ky) * 5 + kx) * 4);
+        const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[r][p][co] = fmaf(v[r][p + kx], wv[co], acc[r][p][co]);
+      }
+    }
+  }
+
+  float bia[COUT], bet[COUT], gam[COUT][COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    bia[c] = __ldg(a.bias + c);
+    bet[c] = a.gdn ? __ldg(a.beta + c) : 1.f;
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) gam[j][c] = a.gdn ? __ldg(a.gamma + j * COUT + c) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int oy = y0 + ty + 8 * r;
+    if (oy >= a.H) continue;
+    float o[COUT][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float x[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) x[c] = acc[r][p][c] + bia[c];
+      if (a.gdn) {
+        float sq[COUT], t[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) sq[c] = x[c] * x[c];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          float nrm = bet[c];
+#pragma unroll
+          for (int j = 0; j < COUT; ++j) nrm = fmaf(gam[j][c], sq[j], nrm);
+          t[c] = x[c] * (a.gdn == 2 ? sqrtf(nrm) : rsqrtf(nrm));
+        }
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) x[c] = t[c];
+      }
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) o[c][p] = apply_act(x[c], a.act);
+    }
+    const int ox = x0 + 4 * tx;
+    if (ox >= a.W) continue;
+    if (a.out_fmt == HESIC_FMT_NCHW_F32) {
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        float *dst = (float *)a.y0 + (((size_t)b * a.out_Cs + c) * a.H + oy) * a.W + ox;
+        if (ox + 3 < a.W && (((uintptr_t)dst) & 15u) == 0) {
+          *reinterpret_cast<float4 *>(dst) = make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (ox + p < a.W) dst[p] = o[c][p];
+        }
+      }
+    } else {   // ROWPAD8 split: one 16-byte (8 channel slots) store per pixel and plane
+      const size_t base = (((size_t)b * (a.H + HESIC_ROWPAD_Y) + oy + 2) * (a.W + HESIC_ROWPAD_X) + ox + 2) * 8;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (ox + p >= a.W) continue;
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < COUT) split_bf16(o[c < COUT ? c : 0][p], hi[c], lo[c]);
+          else { hi[c] = __float2bfloat16_rn(0.f); lo[c] = hi[c]; }
+        }
+        *reinterpret_cast<uint4 *>((__nv_bfloat16 *)a.y0 + base + (size_t)p * 8) = *reinterpret_cast<const uint4 *>(hi);
+        *reinterpret_cast<uint4 *>((__nv_bfloat16 *)a.y1 + base + (size_t)p * 8) = *reinterpret_cast<const uint4 *>(lo);
+      }
+    }
+  }
+}
+
+template <int CIN, int COUT>
+static int launch(const Args &a, cudaStream_t s) {
+  const int smem = (CIN * 25 * 4 + CIN * ROWS * PITCH) * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    HESIC_CUDA(cudaFuncSetAttribute(conv_small_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B);
+  conv_small_kernel<CIN, COUT><<<grid, NT, smem, s>>>(a);
+  HESIC_LAUNCHED("conv_small_kernel");
+  return HESIC_OK;
+}
+
+}  // namespace small
+
+bool conv_small_supported(const hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y) {
+  if (c->kh != 5 || c->kw != 5 || c->pad != 2 || c->stride != 1 || c->out_pad != 0) return false;
+  if (!((c->Cin == 6 && c->Cout == 3) || (c->Cin == 3 && c->Cout == 3))) return false;
+  if (xa->fmt != HESIC_FMT_NCHW_F32 || (xb && xb->fmt != HESIC_FMT_NCHW_F32)) return false;
+  if (y->fmt == HESIC_FMT_ROWPAD8_SPLIT) {
+    if ((((uintptr_t)y->p0 | (uintptr_t)y->p1) & 15u) != 0) return false;
+  } else if (y->fmt != HESIC_FMT_NCHW_F32) {
+    return false;
+  }
+  return (int64_t)y->B * y->H * y->W > 0 && y->B <= 65535 && (y->H + small::TH - 1) / small::TH <= 65535;
+}
+
+int conv_forward_small(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y, int act,
+                       cudaStream_t s) {
+  small::Args a;
+  a.xa = (const float *)xa->p0; a.Ca = xa->C; a.CsA = xa->Cs > 0 ? xa->Cs : xa->C;
+  a.xb = xb ? (const float *)xb->p0 : nullptr; a.CsB = xb ? (xb->Cs > 0 ? xb->Cs : xb->C) : 0;
+  a.B = y->B; a.H = y->H; a.W = y->W;
+  a.w = c->w_simt; a.bias = c->bias; a.transposed = c->transposed;
+  a.gdn = c->has_gdn ? (c->gdn_inverse ? 2 : 1) : 0;
+  a.beta = c->gdn_beta; a.gamma = c->gdn_w_simt;
+  if (c->has_gdn && act != HESIC_ACT_NONE) { set_error("activation after fused GDN is not supported"); return HESIC_E_UNSUPPORTED; }
+  a.act = act;
+  a.out_fmt = y->fmt; a.out_Cs = y->Cs > 0 ? y->Cs : y->C; a.y0 = y->p0; a.y1 = y->p1;
+  if (c->Cin == 6) return small::launch<6, 3>(a, s);
+  return small::launch<3, 3>(a, s);
+}
+
+}  // namespace hesic

@@ -24,7 +24,7 @@
 //   forms x * rsqrt(beta + norm) (or * sqrt for IGDN).  The GDN MMAs of tile t are issued in the
 //   middle of tile t+1's main loop so the tensor pipe never waits for an epilogue.
 // * persistent, warp-specialised CTA (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer and
-//   TMEM owner, warps 2-5 = epilogue.  TMEM (512 columns): two buffers of {main 128, small 128}.  For
+//   TMEM owner, warps 2-9 = epilogue (two groups of four, splitting the tile's columns).  TMEM (512 columns): two buffers of {main 128, small 128}.  For
 //   GDN the epilogue keeps x in registers, overwrites main with the bf16 x^2 operand (hi 64 + lo 64
 //   columns) and the norm accumulates into small.
 #include <cuda.h>
@@ -41,7 +41,8 @@ namespace tc {
 constexpr int BM = 128;                 // pixels per tile (UMMA M)
 constexpr int BK = 64;                  // channels per k-step: 128 B of bf16 = one SW128 row
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;     // TMA warp + MMA warp + 2 x 4 epilogue warps
+constexpr int EPI_THREADS = 256;
 constexpr int MAX_TAPS = 32;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t ACC_STRIDE = 256, COL_SMALL = 128;   // per-buffer TMEM layout
@@ -167,7 +168,7 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -247,6 +248,17 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t &hi, uint3
   const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
   lo = pack_bf16(a - ah, b - bh);
 }
+// MUFU-only reciprocal square root / square root (the arguments are beta + norm >= beta_min > 0, never denormal)
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -267,12 +279,15 @@ __device__ __forceinline__ void ld_chan32(uint32_t addr, float (&o)[32]) {
 struct TaskCoord {
   int mt, ph, nt;
 };
+// Tasks are dealt round-robin to the persistent CTAs.  The sub-pixel phases of a transposed conv have
+// different lengths (9/6/6/4 taps for k5 s2) and the grid size is a multiple of 4, so the phase is rotated
+// by the pixel-tile index: every CTA then sees all four phases instead of always the same one.
 __device__ __forceinline__ TaskCoord decode_task(const Params &p, int task) {
   TaskCoord t;
   t.nt = task % p.n_tiles;
   int r = task / p.n_tiles;
-  t.ph = r % p.n_phases;
   t.mt = r / p.n_phases;
+  t.ph = (r + t.mt) % p.n_phases;
   return t;
 }
 
@@ -354,8 +369,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (p.gdn) { prefetch_map(&map_g_hi); prefetch_map(&map_g_lo); }
     if (p.tma_store) { prefetch_map(&map_y0); prefetch_map(&map_y1); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
-    mbar_init(x2_full, 128); mbar_init(norm_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), p.planar ? 128 : EPI_THREADS); }
+    mbar_init(x2_full, EPI_THREADS); mbar_init(norm_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -463,15 +478,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             advance();
           });
     }
-  } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
-    const int quad = warp & 3;
+  } else if (!(p.planar && warp >= 6)) {
+    // ===================== epilogue =====================
+    // Two groups of four warps; warp w reads TMEM lane quadrant w % 4 (= 32 pixels of the tile) and group
+    // g = (w - 2) / 4 takes the 32-channel chunks g, g + 2 of the tile's columns, so a thread holds at most
+    // 64 channels of one pixel.  (One group doing all 128 channels ran 2900 straight-line instructions per
+    // tile alone on its scheduler and stalled on instruction fetch; two groups halve the code per warp and
+    // give every scheduler two warps.)  The planar path (Cout <= 4) needs one group only.
+    const int quad = warp & 3, grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int xi = row & (p.bw - 1), yi = (row >> p.lbw) & (p.bh - 1), bi = row >> (p.lbw + p.lbh);
     const int txy = p.tiles_x * p.tiles_y;
+    const int nchunks = p.BN / 32, npairs = (nchunks + 1) / 2;
+    const bool is_issuer = threadIdx.x == 64;
+    const uint32_t row_off = stg_base + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    // activation as max(v, slope * v): slope 1 = none, 0 = ReLU, 0.01 = LeakyReLU
+    const float act_slope = p.act == HESIC_ACT_RELU ? 0.f : (p.act == HESIC_ACT_LEAKY_RELU ? 0.01f : 1.f);
     int lt = 0;
-    uint32_t su = 0;   // running store-unit counter (fp32 staging slot = su & 1, across tiles)
     for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x, ++lt) {
       const TaskCoord tk = decode_task(p, task);
       const int buf = lt & 1;
@@ -483,59 +507,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
       const int n0 = tk.nt * p.BN;
       const uint32_t acc = tmem_base + lane_addr + (uint32_t)buf * ACC_STRIDE;
-
-      // Output of one 32-channel chunk.  tma_store: the chunk is written into a 128B-swizzled
-      // [128 px][128 B] staging tile (conflict-free 16-byte stores) and one thread hands full tiles to
-      // TMA, which writes whole pixel rows and clips everything outside the tensor; else each thread
-      // stores its pixel directly.
-      const bool is_issuer = threadIdx.x == 64;
-      const uint32_t row_off = stg_base + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
       const int c_fold = rx * p.out_Cs, mx = tx * p.bw, my = ty * p.bh, mb = tb * p.bb;
-      auto emit = [&](const float (&v)[32], int ch, int nb, bool last_chunk) {
+
+      // Output of chunk pair i (chunks 2i and 2i+1, one per group; `active` = this thread's chunk exists).
+      // tma_store: both groups write their halves into 128B-swizzled [128 px][128 B] staging tiles
+      // (conflict-free 16-byte stores), one thread hands the tiles to TMA, which writes whole pixel rows and
+      // clips everything outside the tensor; else each thread stores its pixel directly.
+      auto emit = [&](const float (&v)[32], int i, bool active) {
+        const int nb = n0 + (2 * i + grp) * 32;
         if (!p.tma_store) {
-          if (valid) store_chunk(p, v, pix, nb);
+          if (valid && active) store_chunk(p, v, pix, nb);
           return;
         }
+        if (is_issuer) bulk_wait_read<0>();     // the previous pair's tiles have been read by TMA
+        epi_bar();
         if (p.out_fmt == HESIC_FMT_NHWC_F32) {
-          const uint32_t slot = (su++ & 1u) * A_TILE_BYTES;
-          if (is_issuer) bulk_wait_read<1>();     // the store that used this slot two chunks ago has been read
-          epi_bar();
+          // one [128 px][32 ch fp32] tile per group
+          if (active) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            st_shared_v4(row_off + slot + (((uint32_t)j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                         __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(row_off + (uint32_t)grp * A_TILE_BYTES + (((uint32_t)j ^ sw) << 4), __float_as_uint(v[4 * j]),
+                           __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          }
           fence_async_smem();
           epi_bar();
           if (is_issuer) {
-            tma_store_5d(&map_y0, stg_base + slot, c_fold + nb, mx, ry, my, mb);
+            const int nb0 = n0 + 2 * i * 32;
+            tma_store_5d(&map_y0, stg_base, c_fold + nb0, mx, ry, my, mb);
+            if (2 * i + 1 < nchunks && nb0 + 32 < p.Cout)
+              tma_store_5d(&map_y0, stg_base + A_TILE_BYTES, c_fold + nb0 + 32, mx, ry, my, mb);
             bulk_commit();
           }
         } else {
-          const int half = ch & 1;                // two chunks fill one 64-channel (hi, lo) tile pair
-          if (half == 0) {
-            if (is_issuer) bulk_wait_read<0>();
-            epi_bar();
-          }
+          // the pair fills one 64-channel (hi, lo) tile pair: group g owns bytes [64g, 64g + 64) of every row
+          if (active) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-            split_pair(v[g * 8 + 0], v[g * 8 + 1], h0, l0);
-            split_pair(v[g * 8 + 2], v[g * 8 + 3], h1, l1);
-            split_pair(v[g * 8 + 4], v[g * 8 + 5], h2, l2);
-            split_pair(v[g * 8 + 6], v[g * 8 + 7], h3, l3);
-            const uint32_t o = row_off + (((uint32_t)(half * 4 + g) ^ sw) << 4);
-            st_shared_v4(o, h0, h1, h2, h3);
-            st_shared_v4(o + A_TILE_BYTES, l0, l1, l2, l3);
-          }
-          if (half == 1 || last_chunk) {
-            fence_async_smem();
-            epi_bar();
-            if (is_issuer) {
-              const int c0 = c_fold + nb - half * 32;
-              tma_store_5d(&map_y0, stg_base, c0, mx, ry, my, mb);
-              tma_store_5d(&map_y1, stg_base + A_TILE_BYTES, c0, mx, ry, my, mb);
-              bulk_commit();
+            for (int g = 0; g < 4; ++g) {
+              uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+              split_pair(v[g * 8 + 0], v[g * 8 + 1], h0, l0);
+              split_pair(v[g * 8 + 2], v[g * 8 + 3], h1, l1);
+              split_pair(v[g * 8 + 4], v[g * 8 + 5], h2, l2);
+              split_pair(v[g * 8 + 6], v[g * 8 + 7], h3, l3);
+              const uint32_t o = row_off + (((uint32_t)(grp * 4 + g) ^ sw) << 4);
+              st_shared_v4(o, h0, h1, h2, h3);
+              st_shared_v4(o + A_TILE_BYTES, l0, l1, l2, l3);
             }
+          }
+          fence_async_smem();
+          epi_bar();
+          if (is_issuer) {
+            const int c0 = c_fold + n0 + 2 * i * 32;
+            tma_store_5d(&map_y0, stg_base, c0, mx, ry, my, mb);
+            tma_store_5d(&map_y1, stg_base + A_TILE_BYTES, c0, mx, ry, my, mb);
+            bulk_commit();
           }
         }
       };
@@ -544,12 +568,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // channel constants of this n-tile -> smem (overlaps the tile's MMAs)
         epi_bar();
         const int ci = (int)threadIdx.x - 64;
-        st_shared_f32(bias_s + 4u * ci, (n0 + ci < p.Cout) ? __ldg(p.bias + n0 + ci) : 0.f);
-        if (p.gdn) st_shared_f32(beta_s + 4u * ci, __ldg(p.beta + ci));
+        if (ci < 128) {
+          st_shared_f32(bias_s + 4u * ci, (n0 + ci < p.Cout) ? __ldg(p.bias + n0 + ci) : 0.f);
+          if (p.gdn) st_shared_f32(beta_s + 4u * ci, __ldg(p.beta + ci));
+        }
         epi_bar();
       }
-      // activation as max(v, slope * v): slope 1 = none, 0 = ReLU, 0.01 = LeakyReLU
-      const float act_slope = p.act == HESIC_ACT_RELU ? 0.f : (p.act == HESIC_ACT_LEAKY_RELU ? 0.01f : 1.f);
 
       mbar_wait(acc_full(buf), ((uint32_t)lt >> 1) & 1u, 7);
       tc_fence_after();
@@ -601,29 +625,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       } else if (!p.gdn) {
-        for (int ch = 0; ch < p.BN / 32; ++ch) {
-          const int nb = n0 + ch * 32;
-          if (nb >= p.Cout) break;
-          uint32_t r[32], q[32];
-          tmem_ld32(acc + ch * 32, r);
-          tmem_ld32(acc + COL_SMALL + ch * 32, q);
-          tmem_ld_wait();
+#pragma unroll 1
+        for (int i = 0; i < npairs; ++i) {
+          if (n0 + 2 * i * 32 >= p.Cout) break;
+          const int ch = 2 * i + grp;
+          const bool active = ch < nchunks && n0 + ch * 32 < p.Cout;
           float v[32];
-          ld_chan32(bias_s + 128u * ch, v);
+          if (active) {
+            uint32_t r[32], q[32];
+            tmem_ld32(acc + ch * 32, r);
+            tmem_ld32(acc + COL_SMALL + ch * 32, q);
+            tmem_ld_wait();
+            ld_chan32(bias_s + 128u * ch, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = (__uint_as_float(r[j]) + __uint_as_float(q[j])) + v[j];
-            v[j] = fmaxf(t, t * act_slope);
+            for (int j = 0; j < 32; ++j) {
+              const float t = (__uint_as_float(r[j]) + __uint_as_float(q[j])) + v[j];
+              v[j] = fmaxf(t, t * act_slope);
+            }
           }
-          emit(v, ch, nb, (nb + 32 >= p.Cout) || (ch == p.BN / 32 - 1));
+          emit(v, i, active);
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
       } else {
         // pass 1: x = conv + bias (kept in registers); x^2 -> bf16 (hi | lo) A operand over the main columns
-        float xs[128];
+        float xs[64];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int i = 0; i < 2; ++i) {
+          const int ch = 2 * i + grp;
           uint32_t r[32], q[32];
           tmem_ld32(acc + ch * 32, r);
           tmem_ld32(acc + COL_SMALL + ch * 32, q);
@@ -631,19 +660,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 t = ld_shared_f4(bias_s + 128u * ch + 16u * j);
-            xs[ch * 32 + 4 * j + 0] = (__uint_as_float(r[4 * j + 0]) + __uint_as_float(q[4 * j + 0])) + t.x;
-            xs[ch * 32 + 4 * j + 1] = (__uint_as_float(r[4 * j + 1]) + __uint_as_float(q[4 * j + 1])) + t.y;
-            xs[ch * 32 + 4 * j + 2] = (__uint_as_float(r[4 * j + 2]) + __uint_as_float(q[4 * j + 2])) + t.z;
-            xs[ch * 32 + 4 * j + 3] = (__uint_as_float(r[4 * j + 3]) + __uint_as_float(q[4 * j + 3])) + t.w;
+            xs[i * 32 + 4 * j + 0] = (__uint_as_float(r[4 * j + 0]) + __uint_as_float(q[4 * j + 0])) + t.x;
+            xs[i * 32 + 4 * j + 1] = (__uint_as_float(r[4 * j + 1]) + __uint_as_float(q[4 * j + 1])) + t.y;
+            xs[i * 32 + 4 * j + 2] = (__uint_as_float(r[4 * j + 2]) + __uint_as_float(q[4 * j + 2])) + t.z;
+            xs[i * 32 + 4 * j + 3] = (__uint_as_float(r[4 * j + 3]) + __uint_as_float(q[4 * j + 3])) + t.w;
           }
         }
-        // all four chunks are in registers before main is overwritten
+        // every thread of both groups has its chunks in registers before main is overwritten
+        tc_fence_before();
+        epi_bar();
+        tc_fence_after();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int i = 0; i < 2; ++i) {
+          const int ch = 2 * i + grp;
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = xs[ch * 32 + 2 * j], c = xs[ch * 32 + 2 * j + 1];
+            const float a = xs[i * 32 + 2 * j], c = xs[i * 32 + 2 * j + 1];
             split_pair(a * a, c * c, hi[j], lo[j]);
           }
           tmem_st16(acc + ch * 16, hi);
@@ -656,7 +689,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mbar_wait(norm_full, (uint32_t)lt & 1u, 8);
         tc_fence_after();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int i = 0; i < 2; ++i) {
+          const int ch = 2 * i + grp;
           uint32_t q[32];
           tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
@@ -664,12 +698,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           ld_chan32(beta_s + 128u * ch, v);
           if (p.gdn == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = xs[ch * 32 + j] * sqrtf(__uint_as_float(q[j]) + v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = xs[i * 32 + j] * sqrt_approx(__uint_as_float(q[j]) + v[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = xs[ch * 32 + j] * rsqrtf(__uint_as_float(q[j]) + v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = xs[i * 32 + j] * rsqrt_approx(__uint_as_float(q[j]) + v[j]);
           }
-          emit(v, ch, ch * 32, ch == 3);
+          emit(v, i, true);
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));

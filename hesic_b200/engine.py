@@ -71,9 +71,10 @@ class HesicEngine:
             plan.set_gdn(None, None, False)
         return plan
 
-    def _run(self, conv_mod, x_desc, B, H, W, kind, act=C.ACT_NONE, gdn=None, dst=None):
-        """Convolve and return (tensor, descriptor).  kind: 'split' | 'nhwc' | 'nchw'.
-        dst=(tensor, c0) writes a channel slice of an existing concat buffer of that kind."""
+    def _run(self, conv_mod, x_desc, B, H, W, kind, act=C.ACT_NONE, gdn=None, dst=None, xb_desc=None):
+        """Convolve and return (tensor, descriptor).  kind: 'split' | 'nhwc' | 'nchw' | 'rowpad'.
+        dst=(tensor, c0) writes a channel slice of an existing concat buffer of that kind;
+        xb_desc: the input is cat((x, xb), 1), never materialised."""
         plan = self._plan(conv_mod, gdn)
         Ho, Wo = plan.out_hw(H, W)
         Cout = plan.geom[1]
@@ -83,17 +84,22 @@ class HesicEngine:
         else:
             c0 = 0
             t = {"split": _split, "nhwc": _nhwc}[kind](B, Ho, Wo, Cout, dev) if kind != "nchw" else _nchw(B, Cout, Ho, Wo, dev)
-        d = {"split": C.split, "nhwc": C.nhwc, "nchw": C.nchw}[kind](t, Cout, c0)
-        plan.run(x_desc, d, act, self.path)
+        d = {"split": C.split, "nhwc": C.nhwc, "nchw": C.nchw, "rowpad": C.rowpad}[kind](t, Cout, c0)
+        plan.run(x_desc, d, act, self.path, xb_desc)
         return t, d, Ho, Wo
 
-    def _rowpad(self, slot, src_desc, B, Cn, H, W):
-        """NCHW fp32 view (<= 8 channels) -> cached ROWPAD8 buffer (its zero border is written once)."""
+    def _rowpad_buf(self, slot, B, H, W):
+        """Cached ROWPAD8 buffer (zero border and zero unused channel slots written once)."""
         key = (slot, B, H, W, str(self.dev))
         t = self._rowpads.get(key)
         if t is None:
             t = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, 8), device=self.dev, dtype=torch.bfloat16)
             self._rowpads[key] = t
+        return t
+
+    def _rowpad(self, slot, src_desc, B, Cn, H, W):
+        """NCHW fp32 view (<= 8 channels) -> cached ROWPAD8 buffer (its zero border is written once)."""
+        t = self._rowpad_buf(slot, B, H, W)
         d = C.rowpad(t, Cn)
         self._convert(src_desc, d)
         return d
@@ -200,14 +206,23 @@ class HesicEngine:
         x1_hat, _, _, _ = self._synthesis(m.decoder1, y1h_split_d, B, Hy, Wy)
 
         # ---- view 2 analysis -------------------------------------------------------------
-        cat_in = _nchw(B, 6, H, W, dev)    # cat(x1_warp, x2)            newnet1.py:643
+        x1_warp = _nchw(B, 3, H, W, dev)
         cat_out = _nchw(B, 6, H, W, dev)   # cat(after_gdn(..), x1_hat_warp)  newnet1.py:686
-        self._warp(C.nchw(x1), h, C.nchw(cat_in, 3, 0))
-        self._convert(C.nchw(x2), C.nchw(cat_in, 3, 3))
+        self._warp(C.nchw(x1), h, C.nchw(x1_warp))
         enc2 = m.encoder2
-        pre, pre_d, _, _ = self._run(enc2.pre_conv, self._rowpad("cat_in", C.nchw(cat_in), B, 6, H, W), B, H, W, "nchw",
-                                     gdn=enc2.pre_gdn)
-        y2, y2_d, _, _ = self._analysis(enc2, self._rowpad("pre", pre_d, B, 3, H, W), B, H, W)
+        # pre_gdn(pre_conv(cat(x1_warp, x2)))  (newnet1.py:643-644): fp32 stencil over the two sources, written
+        # straight into the ROWPAD8 input planes of g_a_conv1
+        if self.path == C.PATH_AUTO:
+            _, pre_d, _, _ = self._run(enc2.pre_conv, C.nchw(x1_warp), B, H, W, "rowpad", gdn=enc2.pre_gdn,
+                                       dst=(self._rowpad_buf("pre", B, H, W), 0), xb_desc=C.nchw(x2))
+        else:
+            cat_in = _nchw(B, 6, H, W, dev)
+            self._convert(C.nchw(x1_warp), C.nchw(cat_in, 3, 0))
+            self._convert(C.nchw(x2), C.nchw(cat_in, 3, 3))
+            cin_d = C.nchw(cat_in) if self.path == C.PATH_SIMT else self._rowpad("cat_in", C.nchw(cat_in), B, 6, H, W)
+            _, pre_nchw_d, _, _ = self._run(enc2.pre_conv, cin_d, B, H, W, "nchw", gdn=enc2.pre_gdn)
+            pre_d = self._rowpad("pre", pre_nchw_d, B, 3, H, W)
+        y2, y2_d, _, _ = self._analysis(enc2, pre_d, B, H, W)
         x1hw_d = C.nchw(cat_out, 3, 3)
         self._warp(C.nchw(x1_hat), h, x1hw_d)          # newnet1.py:753 and :767 (identical) run once
 
@@ -250,7 +265,11 @@ class HesicEngine:
         # ---- view 2 synthesis ---------------------------------------------------------------
         dec2 = m.decoder2
         self._synthesis(dec2, y2h_split_d, B, Hy, Wy, last_kind="nchw", last_gdn=dec2.after_gdn, last_dst=(cat_out, 0))
-        x2_hat, _, _, _ = self._run(dec2.after_conv, self._rowpad("cat_out", C.nchw(cat_out), B, 6, H, W), B, H, W, "nchw")
+        if self.path == C.PATH_TC:
+            co_d = self._rowpad("cat_out", C.nchw(cat_out), B, 6, H, W)
+        else:
+            co_d = C.nchw(cat_out)     # CUDA-core stencil reads the NCHW concatenation buffer directly
+        x2_hat, _, _, _ = self._run(dec2.after_conv, co_d, B, H, W, "nchw")
 
         out = {"x1_hat": x1_hat, "x2_hat": x2_hat}
         if self.variant != "newnet9":

@@ -76,8 +76,12 @@ class ConvPlan:
             return (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
         return (H - 1) * s - 2 * p + kh + op, (W - 1) * s - 2 * p + kw + op
 
-    def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO):
-        C.check(_lib.hesic_conv_forward(self.h, C.ref(x_desc), C.ref(y_desc), act, path, C.stream()))
+    def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO, xb_desc=None):
+        """xb_desc: second part of a channel concatenation (torch.cat((x, xb), 1) on the reference side)."""
+        if xb_desc is not None:
+            C.check(_lib.hesic_conv_forward_cat(self.h, C.ref(x_desc), C.ref(xb_desc), C.ref(y_desc), act, path, C.stream()))
+        else:
+            C.check(_lib.hesic_conv_forward(self.h, C.ref(x_desc), C.ref(y_desc), act, path, C.stream()))
 
 
 def conv2d(x, plan, act=C.ACT_NONE, path=C.PATH_AUTO):
@@ -87,8 +91,8 @@ def conv2d(x, plan, act=C.ACT_NONE, path=C.PATH_AUTO):
     Ho, Wo = plan.out_hw(H, W)
     Cout = plan.geom[1]
     y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
-    if path == C.PATH_SIMT:
-        plan.run(C.nchw(x), C.nchw(y), act, path)
+    if path == C.PATH_SIMT or (path == C.PATH_AUTO and Cin <= 8 and Cout <= 4 and plan.geom[4] == 1):
+        plan.run(C.nchw(x), C.nchw(y), act, path)     # CUDA-core paths read and write NCHW fp32 directly
         return y
     # the tensor-core path consumes bf16 (hi, lo) planes: ROWPAD8 for the <= 8-channel edge layers,
     # channels-last otherwise

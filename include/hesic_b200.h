@@ -88,6 +88,12 @@ int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float *gamma, int
                        void *stream);
 int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, int path,
                        void *stream);
+/* Same layer applied to torch.cat((xa, xb), dim=1) without materialising the concatenation
+ * (newnet1.py:643-644 pre_conv(cat(x1_warp, x2)), :686 after_conv(cat(.., x1_hat_warp))): the
+ * layer's input channels [0, xa->C) are read from xa, the rest from xb.  NCHW fp32 inputs,
+ * full-resolution few-channel k5 s1 layers only (else HESIC_E_UNSUPPORTED). */
+int hesic_conv_forward_cat(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y,
+                           int act, int path, void *stream);
 
 /* Watchdog of the tcgen05 path: every in-kernel barrier wait is time-bounded, so a protocol error
  * cannot hang the GPU.  Returns 0 when no wait has timed out since the last call, else HESIC_E_CUDA

@@ -44,7 +44,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "-".join(map(str, c)))
-@pytest.mark.parametrize("path", ["simt", "auto"])
+@pytest.mark.parametrize("path", ["simt", "auto", "tc"])
 def test_conv_parity(case, path):
     from hesic_b200 import _capi as C
     from hesic_b200 import functional as F
@@ -57,10 +57,56 @@ def test_conv_parity(case, path):
     ref = O.deconv(x, w, b, stride=s) if tr else O.conv(x, w, b, stride=s)
     mod.load_state_dict({"weight": w, "bias": b})
     mod = mod.to(DEV)
+    pth = {"simt": C.PATH_SIMT, "auto": C.PATH_AUTO, "tc": C.PATH_TC}[path]
     for act, fn in ((C.ACT_NONE, lambda t: t), (C.ACT_LEAKY, torch.nn.functional.leaky_relu)):
-        y = F.conv2d(x.to(DEV), mod.hesic_plan(), act=act, path=C.PATH_SIMT if path == "simt" else C.PATH_AUTO)
+        try:
+            y = F.conv2d(x.to(DEV), mod.hesic_plan(), act=act, path=pth)
+        except NotImplementedError:
+            assert path == "tc"
+            pytest.skip("shape not on the tcgen05 path")
         assert y.shape == ref.shape
         assert_close(y, fn(ref), 1e-4, what=f"conv {case} act={act} path={path}")
+
+
+@pytest.mark.parametrize("size", [(2, 40, 24), (1, 64, 128), (2, 70, 67)])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_few_channel_stencil_cat_gdn_rowpad(size, transposed):
+    """pre_gdn(pre_conv(cat(a, b))) / after_conv(cat(a, b)) (newnet1.py:643-644,686): the exact-fp32 stencil fed two
+    sources, with the fused 3-channel GDN, writing NCHW and the ROWPAD8 (hi, lo) planes of the next layer."""
+    from hesic_b200 import _capi as C
+    from compressai.layers import GDN
+    from compressai.models.utils import conv, deconv
+    B, H, W = size
+    mod = (deconv if transposed else conv)(6, 3, kernel_size=5, stride=1)
+    w = _rand(tuple(mod.weight.shape), 11, 0.1)
+    b = _rand((3,), 12, 0.1)
+    mod.load_state_dict({"weight": w, "bias": b})
+    g = GDN(3, inverse=transposed)
+    g.load_state_dict({"beta": torch.rand(3) + 0.5, "gamma": torch.rand(3, 3) * 0.2}, strict=False)
+    xa, xb = _rand((B, 3, H, W), 13), _rand((B, 3, H, W), 14)
+    xin = torch.cat((xa, xb), 1)
+    ref_c = O.deconv(xin, w, b, stride=1) if transposed else O.conv(xin, w, b, stride=1)
+    ref_g = O.gdn(ref_c, g.beta.detach(), g.gamma.detach(), inverse=transposed)
+    mod, g = mod.to(DEV), g.to(DEV)
+    plan = mod.hesic_plan()
+    xa_d, xb_d = xa.to(DEV), xb.to(DEV)
+    # (1) plain conv, cat input, NCHW output (channel slice of a wider buffer)
+    plan.set_gdn(None, None, False)
+    out = torch.zeros((B, 5, H, W), device=DEV)
+    plan.run(C.nchw(xa_d), C.nchw(out, 3, 1), C.ACT_NONE, C.PATH_AUTO, C.nchw(xb_d))
+    assert_close(out[:, 1:4], ref_c, 2e-6, what="stencil conv (cat)")
+    assert float(out[:, 0].abs().max()) == 0 and float(out[:, 4].abs().max()) == 0
+    # (2) fused GDN, ROWPAD8 output
+    plan.set_gdn(g.beta, g.gamma, g.inverse, g.beta_min)
+    rp = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, 8), device=DEV, dtype=torch.bfloat16)
+    plan.run(C.nchw(xa_d), C.rowpad(rp, 3), C.ACT_NONE, C.PATH_AUTO, C.nchw(xb_d))
+    val = (rp[0].float() + rp[1].float())
+    inner = val[:, 2:2 + H, 2:2 + W, :3].permute(0, 3, 1, 2)
+    assert_close(inner, ref_g, 2e-5, what="stencil conv + GDN -> ROWPAD8")
+    border = val.clone()
+    border[:, 2:2 + H, 2:2 + W, :3] = 0
+    assert float(border.abs().max()) == 0
+    plan.set_gdn(None, None, False)
 
 
 def test_conv_linearity_property():

@@ -64,10 +64,10 @@ def tdesc(ref):
 orig_run = F.ConvPlan.run
 
 
-def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO):
+def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO, xb_desc=None):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    orig_run(self, x_desc, y_desc, act, path)
+    orig_run(self, x_desc, y_desc, act, path, xb_desc)
     e.record()
     Cin, Cout, kh, kw, st, p, tr, op = self.geom
     gdn = "+gdn" if self._gdn_key is not None else ""
