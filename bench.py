@@ -162,12 +162,15 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, whole=False):
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
-            fn(i)
+        if whole:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(i)
         e1.record()
         sync()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -185,18 +188,21 @@ def run_ours(args):
     launches = C.lib.hesic_launch_count(0)
     m_dev = metrics(partial.cpu(), B * world)
 
-    # end to end through the public API: pinned host inputs -> H2D -> forward -> metric partials -> D2H
-    def e2e_step(i):
-        hx1, hx2, hh = host[i % 2]
-        dx1, dx2, dh = sets[i % 2]
-        dx1.copy_(hx1, non_blocking=True)
-        dx2.copy_(hx2, non_blocking=True)
-        dh.copy_(hh, non_blocking=True)
+    # end to end through the public API: pinned host inputs -> H2D -> forward -> metric partials -> D2H.
+    # Every step's inputs are copied inside the timed region; hostfeed.HostFeed copies batch i+1 on a side
+    # stream while batch i computes.
+    from hesic_b200.hostfeed import HostFeed
+    feed = HostFeed(dev, host[0])
+
+    def e2e_one(dx1, dx2, dh):
         step(dx1, dx2, dh)
         result_host.copy_(partial, non_blocking=True)
 
-    e2e_step(0)
-    ms_e2e = timed(e2e_step, args.steps)
+    def e2e_all(steps):
+        feed.run([host[i % 2] for i in range(steps)], e2e_one)
+
+    e2e_all(2)
+    ms_e2e = timed(e2e_all, args.steps, whole=True)
     clocks = sampler.stop() if sampler else None
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
@@ -257,7 +263,9 @@ def run_ours(args):
                    "gflop_per_pair": GFLOP_PER_PAIR[args.model], "conv_path": path_used,
                    "parity_metrics": m_dev},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 48,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "how": "hesic_b200.hostfeed.HostFeed: pinned host batch -> H2D on a copy stream (double-buffered, batch i+1 "
+                       "copies while batch i computes; K copies inside the timed region) -> HSIC.forward -> partial sums -> D2H"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",

@@ -6,9 +6,10 @@
 //   GENERIC  one GEMM k-step per (tap, 64-channel chunk); weights [tap][CoutPad][Cin]
 //   ROW      Cin <= 8, k5 (the full-resolution RGB / 6-channel layers): input in ROWPAD8 format, one k-step
 //            per kernel ROW with K = 8 pixels x 8 channel slots; weights [ky][CoutPad][64]
-//   MERGED   stride-2 k5 transposed conv with Cout <= 4 (the RGB synthesis head): the 4 sub-pixel phases
-//            become the N dimension of a 3x3 stride-1 conv; weights [3x3 shift][16 = phase*4+co][Cin]
-enum { HESIC_TC_GENERIC = 0, HESIC_TC_ROW = 1, HESIC_TC_MERGED = 2 };
+//   SCATTER  stride-2 k5 transposed conv with Cout <= 4 (the RGB synthesis head): one GEMM per input pixel onto
+//            its 5x5xCout output patch, overlap-add in the epilogue (conv_head.cuh); weights [NPAD = 25*Cout
+//            rounded up to 16][Cin], row n = (ky*5 + kx)*Cout + co
+enum { HESIC_TC_GENERIC = 0, HESIC_TC_ROW = 1, HESIC_TC_SCATTER = 2 };
 
 struct hesic_conv {
   int Cin = 0, Cout = 0, kh = 0, kw = 0, stride = 1, pad = 0, transposed = 0, out_pad = 0;

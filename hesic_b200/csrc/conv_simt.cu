@@ -232,18 +232,17 @@ __global__ void pack_conv_row_kernel(const float *__restrict__ w, const float *_
   }
 }
 
-// MERGED formulation: [(dy+1)*3 + dx+1][n = (ry*2+rx)*4 + co][ci], tap ky = ry + 2 - 2*dy (k5, s2, p2)
-__global__ void pack_conv_merged_kernel(const float *__restrict__ w, int Cin, int Cout, __nv_bfloat16 *__restrict__ w_hi,
-                                        __nv_bfloat16 *__restrict__ w_lo) {
-  int total = 9 * 16 * Cin;
+// SCATTER formulation (RGB synthesis head): [n = (ky*5 + kx)*Cout + co][ci], rows >= 25*Cout zero
+__global__ void pack_conv_scatter_kernel(const float *__restrict__ w, int Cin, int Cout, int NPAD,
+                                         __nv_bfloat16 *__restrict__ w_hi, __nv_bfloat16 *__restrict__ w_lo) {
+  int total = NPAD * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int ci = i % Cin, r = i / Cin;
-    int n = r % 16, tap = r / 16;
-    int dy = tap / 3 - 1, dx = tap % 3 - 1;
-    int ph = n / 4, co = n % 4;
-    int ky = (ph >> 1) + 2 - 2 * dy, kx = (ph & 1) + 2 - 2 * dx;
+    int ci = i % Cin, n = i / Cin;
     float v = 0.f;
-    if (co < Cout && ky >= 0 && ky < 5 && kx >= 0 && kx < 5) v = w[(((size_t)ci * Cout + co) * 5 + ky) * 5 + kx];
+    if (n < 25 * Cout) {
+      int tap = n / Cout, co = n % Cout;
+      v = w[((size_t)ci * Cout + co) * 25 + tap];   // ConvTranspose2d weight [Cin][Cout][5][5]
+    }
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
     w_hi[i] = hi;
@@ -316,8 +315,8 @@ extern "C" hesic_conv *hesic_conv_create(int Cin, int Cout, int kh, int kw, int 
   if (Cin <= 8 && k5 && ((!c->transposed && (stride == 1 || stride == 2)) ||
                          (c->transposed && stride == 1 && output_padding == 0))) {
     c->tc_kind = HESIC_TC_ROW; c->tc_taps = 5; c->tc_k = 64;
-  } else if (c->transposed && stride == 2 && k5 && output_padding == 1 && Cout <= 4 && Cin % 8 == 0) {
-    c->tc_kind = HESIC_TC_MERGED; c->tc_taps = 9; c->tc_k = Cin;
+  } else if (c->transposed && stride == 2 && k5 && output_padding == 1 && Cout <= 4 && Cin % 64 == 0 && Cin <= 256) {
+    c->tc_kind = HESIC_TC_SCATTER; c->tc_taps = 1; c->tc_k = Cin;
   }
   return c;
 }
@@ -346,15 +345,16 @@ extern "C" int hesic_conv_load(hesic_conv *c, const float *weight, const float *
   pack_conv_kernel<<<blocks, 256, 0, s>>>(weight, mask, c->Cin, c->Cout, c->kh, c->kw, c->transposed, c->CoutPad,
                                           c->w_simt, c->w_hi, c->w_lo);
   HESIC_LAUNCHED("pack_conv_kernel");
-  // the tensor-core operand planes of the ROW / MERGED formulations replace the generic ones
+  // the tensor-core operand planes of the ROW / SCATTER formulations replace the generic ones
   if (c->tc_kind == HESIC_TC_ROW) {
     pack_conv_row_kernel<<<(5 * c->CoutPad * 64 + 255) / 256, 256, 0, s>>>(weight, mask, c->Cin, c->Cout, c->transposed,
                                                                        c->CoutPad, c->w_hi, c->w_lo);
     HESIC_LAUNCHED("pack_conv_row_kernel");
-  } else if (c->tc_kind == HESIC_TC_MERGED) {
+  } else if (c->tc_kind == HESIC_TC_SCATTER) {
     HESIC_REQUIRE(mask == nullptr, "hesic_conv_load: masked transposed RGB head is not supported");
-    pack_conv_merged_kernel<<<(9 * 16 * c->Cin + 255) / 256, 256, 0, s>>>(weight, c->Cin, c->Cout, c->w_hi, c->w_lo);
-    HESIC_LAUNCHED("pack_conv_merged_kernel");
+    const int NPAD = (25 * c->Cout + 15) / 16 * 16;
+    pack_conv_scatter_kernel<<<(NPAD * c->Cin + 255) / 256, 256, 0, s>>>(weight, c->Cin, c->Cout, NPAD, c->w_hi, c->w_lo);
+    HESIC_LAUNCHED("pack_conv_scatter_kernel");
   }
   if (bias) {
     HESIC_CUDA(cudaMemcpyAsync(c->bias, bias, c->Cout * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -264,6 +264,11 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -720,6 +725,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
 }
 
+}  // namespace tc
+}  // namespace hesic
+#include "conv_head.cuh"
+namespace hesic {
+namespace tc {
+
 // ---------------------------------------------------------------------------------------------
 // host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -784,11 +795,6 @@ static int build_taps(const hesic_conv *c, Params &p) {
       else add_tap(p, n, ky, 0, 0, 0, ky);
     }
     p.tap_begin[1] = n;
-  } else if (c->tc_kind == HESIC_TC_MERGED) {
-    // stride-2 transposed conv as a 3x3 stride-1 conv onto N = 4 phases x 4 channel slots
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx) add_tap(p, n, dy, dx, 0, 0, (dy + 1) * 3 + dx + 1);
-    p.tap_begin[1] = n;
   } else if (!c->transposed) {
     for (int ky = 0; ky < c->kh; ++ky)
       for (int kx = 0; kx < c->kw; ++kx) {
@@ -840,9 +846,9 @@ bool conv_tc_supported(const hesic_conv *c, const hesic_tensor *x, const hesic_t
   if (c->tc_kind == HESIC_TC_ROW) {
     if (x->fmt != HESIC_FMT_ROWPAD8_SPLIT) return false;
     if (!c->transposed && c->stride == 2 && ((x->H | x->W) & 1)) return false;
-  } else if (c->tc_kind == HESIC_TC_MERGED) {
+  } else if (c->tc_kind == HESIC_TC_SCATTER) {
     if (x->fmt != HESIC_FMT_NHWC_SPLIT || !planar_out) return false;
-    if (c->Cin % 8 || c->Cin < 16 || xCs % 8) return false;
+    if (c->Cin % 64 || c->Cin > 256 || xCs % 8) return false;
   } else {
     if (x->fmt != HESIC_FMT_NHWC_SPLIT || planar_out) return false;
     if (c->Cin % 8 || c->Cin < 16 || xCs % 8) return false;
@@ -854,11 +860,74 @@ bool conv_tc_supported(const hesic_conv *c, const hesic_tensor *x, const hesic_t
   return encode_fn() != nullptr;
 }
 
+// RGB synthesis head (conv_head.cuh)
+template <int COUT>
+static int launch_head(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s) {
+  using namespace tc;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    HESIC_CUDA(cudaGetDevice(&dev));
+    HESIC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    HESIC_CUDA(cudaFuncSetAttribute(head::conv_head_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  }
+  const int xCs = x->Cs > 0 ? x->Cs : x->C;
+  head::HParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = x->H; p.W = x->W; p.B = x->B;
+  p.tiles_x = (x->W + head::IN_W - 1) / head::IN_W; p.tiles_y = (x->H + head::IN_H - 1) / head::IN_H;
+  p.n_tasks = p.tiles_x * p.tiles_y * x->B;
+  p.NPAD = (25 * COUT + 15) / 16 * 16;
+  p.kchunks = c->Cin / BK;
+  p.y = (float *)y->p0; p.out_Cs = y->Cs > 0 ? y->Cs : y->C;
+  p.bias = c->bias; p.act = act;
+  p.gdn = c->has_gdn ? (c->gdn_inverse ? 2 : 1) : 0;
+  p.beta = c->gdn_beta; p.gamma = c->gdn_w_simt;
+  const int fixed = 1024 + 256 + p.kchunks * 2 * p.NPAD * 128 + BM * (p.NPAD + 1) * 4;
+  p.stages = std::min(8, (SMEM_LIMIT - fixed) / head::STAGE_BYTES);
+  if (p.stages < 2) { set_error("conv head: operands do not fit shared memory"); return HESIC_E_UNSUPPORTED; }
+  const int smem_bytes = fixed + p.stages * head::STAGE_BYTES;
+  CUtensorMap ma_hi, ma_lo;
+  {
+    const uint64_t e = 2;
+    uint64_t dims[5] = {(uint64_t)x->C, (uint64_t)x->W, 1, (uint64_t)x->H, (uint64_t)x->B};
+    uint64_t strides[4] = {(uint64_t)xCs * e, (uint64_t)x->W * xCs * e, (uint64_t)x->W * xCs * e,
+                           (uint64_t)x->H * x->W * xCs * e};
+    uint32_t box[5] = {(uint32_t)BK, (uint32_t)head::TILE_W, 1u, (uint32_t)head::TILE_H, 1u};
+    int r = make_map(&ma_hi, x->p0, 5, dims, strides, box);
+    if (r == HESIC_OK) r = make_map(&ma_lo, x->p1, 5, dims, strides, box);
+    if (r != HESIC_OK) return r;
+  }
+  if (!c->tc_maps || c->tc_maps_bn != p.NPAD) {
+    if (!c->tc_maps) c->tc_maps = (unsigned char *)aligned_alloc(128, 4 * sizeof(CUtensorMap));
+    CUtensorMap *m = (CUtensorMap *)c->tc_maps;
+    uint64_t dims[2] = {(uint64_t)c->Cin, (uint64_t)p.NPAD}, strides[1] = {(uint64_t)c->Cin * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)p.NPAD};
+    int r = make_map(&m[0], c->w_hi, 2, dims, strides, box);
+    if (r == HESIC_OK) r = make_map(&m[1], c->w_lo, 2, dims, strides, box);
+    if (r != HESIC_OK) return r;
+    c->tc_maps_bn = p.NPAD;
+  }
+  const CUtensorMap *m = (const CUtensorMap *)c->tc_maps;
+  const int grid = std::min(p.n_tasks, num_sms);
+  head::conv_head_kernel<COUT><<<grid, head::NT, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], p);
+  HESIC_LAUNCHED("conv_head_kernel");
+  return HESIC_OK;
+}
+
 int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s) {
   using namespace tc;
   if (c->has_gdn && act != HESIC_ACT_NONE) {
     set_error("activation after fused GDN is not supported");
     return HESIC_E_UNSUPPORTED;
+  }
+  if (c->tc_kind == HESIC_TC_SCATTER) {
+    switch (c->Cout) {
+      case 1: return launch_head<1>(c, x, y, act, s);
+      case 2: return launch_head<2>(c, x, y, act, s);
+      case 3: return launch_head<3>(c, x, y, act, s);
+      default: return launch_head<4>(c, x, y, act, s);
+    }
   }
   static int num_sms = 0;
   static bool attr_set = false;
@@ -876,8 +945,8 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   const int ntaps = build_taps(c, p);
   if (ntaps <= 0) { set_error("conv tcgen05: unsupported tap structure"); return HESIC_E_UNSUPPORTED; }
   p.planar = planar ? 1 : 0;
-  p.pl_phases = c->tc_kind == HESIC_TC_MERGED ? 4 : 1;
-  p.pl_os = c->tc_kind == HESIC_TC_MERGED ? 2 : 1;
+  p.pl_phases = 1;
+  p.pl_os = 1;
   const int tile_os = planar ? p.pl_os : p.os;     // output pixels per tile-space pixel, per axis
   const int Hq = (y->H + tile_os - 1) / tile_os, Wq = (y->W + tile_os - 1) / tile_os;
   p.bw = Wq >= 16 ? 16 : pow2ceil(Wq);

@@ -109,6 +109,41 @@ def test_few_channel_stencil_cat_gdn_rowpad(size, transposed):
     plan.set_gdn(None, None, False)
 
 
+@pytest.mark.parametrize("size", [(2, 16, 16), (3, 7, 5), (1, 20, 36), (1, 64, 64)])
+@pytest.mark.parametrize("igdn", [False, True])
+def test_rgb_head_scatter_form(size, igdn):
+    """deconv(128 -> 3, k5, s2) (+ after_gdn) of Decoder1/Decoder2 (newnet1.py:612,670,685): the scatter-form tcgen05
+    kernel (GEMM onto 5x5x3 patches + overlap-add), ragged tile edges, output written as a channel slice."""
+    from hesic_b200 import _capi as C
+    from compressai.layers import GDN
+    from compressai.models.utils import deconv
+    B, H, W = size
+    mod = deconv(128, 3, kernel_size=5, stride=2)
+    w = _rand(tuple(mod.weight.shape), 21, (2.0 / (128 * 25 / 4)) ** 0.5)
+    b = _rand((3,), 22, 0.1)
+    mod.load_state_dict({"weight": w, "bias": b})
+    x = _rand((B, 128, H, W), 23)
+    ref = O.deconv(x, w, b, stride=2)
+    g = GDN(3, inverse=True)
+    g.load_state_dict({"beta": torch.rand(3) + 0.5, "gamma": torch.rand(3, 3) * 0.2}, strict=False)
+    if igdn:
+        ref = O.gdn(ref, g.beta.detach(), g.gamma.detach(), inverse=True)
+    mod, g = mod.to(DEV), g.to(DEV)
+    plan = mod.hesic_plan()
+    if igdn:
+        plan.set_gdn(g.beta, g.gamma, True, g.beta_min)
+    else:
+        plan.set_gdn(None, None, False)
+    xs = torch.empty((2, B, H, W, 128), device=DEV, dtype=torch.bfloat16)
+    C.check(C.lib.hesic_convert(C.ref(C.nchw(x.to(DEV))), C.ref(C.split(xs)), C.OP_COPY, C.stream()))
+    out = torch.zeros((B, 6, 2 * H, 2 * W), device=DEV)
+    plan.run(C.split(xs), C.nchw(out, 3, 2), C.ACT_NONE, C.PATH_TC)
+    C.check(C.lib.hesic_tc_status())
+    assert_close(out[:, 2:5], ref, 1e-4, what="RGB head")
+    assert float(out[:, :2].abs().max()) == 0 and float(out[:, 5].abs().max()) == 0
+    plan.set_gdn(None, None, False)
+
+
 def test_conv_linearity_property():
     """conv(a + b) - conv(a) - conv(b) + conv(0) == 0 at a BASELINE-size layer (size-independent check)."""
     from hesic_b200 import functional as F

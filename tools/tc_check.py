@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device-side check of the tcgen05 conv path against the SIMT fp32 path on identical split inputs.
 
-    python tools/tc_check.py [group ...]      groups: s1 s2 deconv gdn row merged big edge
+    python tools/tc_check.py [group ...]      groups: s1 s2 deconv gdn row head big edge
 
 Prints one line per case: max |tc - simt| relative to rms(simt).  Exit code 1 on any mismatch.
 Run each group in its own process (a trapped kernel poisons the CUDA context)."""
@@ -37,7 +37,7 @@ GROUPS = {
             (192, 128, 5, 2, True, 8, 8, 4, 2, 0), (128, 128, 5, 2, False, 128, 128, 4, 1, 0)],
     "row": [(3, 128, 5, 2, False, 64, 64, 2, 1, 0), (3, 128, 5, 2, False, 32, 48, 1, 0, 2), (6, 3, 5, 1, False, 40, 24, 2, 1, 0),
             (6, 3, 5, 1, True, 24, 40, 1, 0, 0), (3, 3, 5, 1, False, 16, 16, 1, 2, 0), (3, 128, 5, 2, False, 512, 512, 2, 1, 0)],
-    "merged": [(128, 3, 5, 2, True, 16, 16, 2, 0, 0), (128, 3, 5, 2, True, 32, 24, 1, 2, 0), (192, 3, 5, 2, True, 8, 8, 3, 1, 0),
+    "head": [(128, 3, 5, 2, True, 16, 16, 2, 0, 0), (128, 3, 5, 2, True, 32, 24, 1, 2, 0), (192, 3, 5, 2, True, 8, 8, 3, 1, 0),
                (128, 3, 5, 2, True, 256, 256, 2, 2, 0)],
     "edge": [(3, 128, 5, 2, False, 512, 512, 16, 1, 0), (128, 3, 5, 2, True, 256, 256, 16, 2, 0), (6, 3, 5, 1, False, 512, 512, 16, 1, 0),
              (6, 3, 5, 1, True, 512, 512, 16, 0, 0)],
