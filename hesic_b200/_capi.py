@@ -55,10 +55,10 @@ _sig = {
     "hesic_conv_forward_cat": ([c_void_p, _TP, _TP, _TP, c_int, c_int, c_void_p], c_int),
     "hesic_tc_status": ([], c_int),
     "hesic_gdn": ([_TP, _TP, c_void_p, c_void_p, c_int, c_float, c_void_p], c_int),
-    "hesic_warp_perspective": ([_TP, c_void_p, _TP, c_int, c_void_p], c_int),
+    "hesic_warp_perspective": ([_TP, c_void_p, _TP, _TP, c_int, c_void_p], c_int),
     "hesic_eb_pack": ([POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_int, c_void_p, c_void_p], c_int),
     "hesic_entropy_bottleneck": ([_TP, c_void_p, c_float, _TP, _TP, c_void_p, c_void_p], c_int),
-    "hesic_gaussian_conditional": ([_TP, _TP, _TP, c_void_p, c_int, c_int, c_float, c_float, _TP, _TP, c_void_p, c_void_p], c_int),
+    "hesic_gaussian_conditional": ([_TP, _TP, _TP, c_void_p, c_int, c_int, c_float, c_float, _TP, _TP, _TP, c_void_p, c_void_p], c_int),
     "hesic_spatial_max": ([_TP, c_void_p, c_void_p], c_int),
     "hesic_mixture_weights": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "hesic_upsample_bilinear": ([_TP, _TP, c_int, c_void_p], c_int),
@@ -143,13 +143,18 @@ def split(t, C=None, c0=0):
 
 
 def rowpad(t, C=None, c0=0):
-    """Descriptor for a [2,B,H+4,W+8,8] bf16 torch tensor in ROWPAD8 split format (image at offset (2,2),
-    zero border and zero unused channel slots): the input format of the Cin <= 8 edge layers."""
-    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[0] == 2 and t.shape[-1] == 8
-    _, B, Hp, Wp, _ = t.shape
-    C = 8 - c0 if C is None else C
-    plane = B * Hp * Wp * 8 * 2
-    return CTensor(t.data_ptr() + 2 * c0, t.data_ptr() + plane + 2 * c0, FMT_ROWPAD, B, C, Hp - ROWPAD_Y, Wp - ROWPAD_X, 8)
+    """Descriptor for a [2,B,H+4,W+8,S] bf16 torch tensor in ROWPAD split format, S = 8 or 4 channel slots (image
+    at offset (2,2), zero border and zero unused channel slots): the input format of the Cin <= 8 edge layers."""
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[0] == 2 and t.shape[-1] in (4, 8)
+    _, B, Hp, Wp, S = t.shape
+    C = S - c0 if C is None else C
+    plane = B * Hp * Wp * S * 2
+    return CTensor(t.data_ptr() + 2 * c0, t.data_ptr() + plane + 2 * c0, FMT_ROWPAD, B, C, Hp - ROWPAD_Y, Wp - ROWPAD_X, S)
+
+
+def rowpad_slots(Cin, stride, transposed):
+    """Channel slots of the ROWPAD input a k5 layer with Cin <= 8 reads on the tensor-core path (conv.h: ROW2 / ROW)."""
+    return 4 if (Cin <= 4 and stride == 2 and not transposed) else 8
 
 
 def null():

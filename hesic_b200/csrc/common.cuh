@@ -77,15 +77,24 @@ inline int check_tensor(const hesic_tensor *t, const char *name, bool allow_null
     HESIC_REQUIRE(t->p0 != nullptr, "%s: null data pointer", name);
     if (t->fmt == HESIC_FMT_NHWC_SPLIT || t->fmt == HESIC_FMT_ROWPAD8_SPLIT)
       HESIC_REQUIRE(t->p1 != nullptr, "%s: null lo plane", name);
-    if (t->fmt == HESIC_FMT_ROWPAD8_SPLIT) HESIC_REQUIRE(t->Cs == 8 && t->C <= 8, "%s: ROWPAD8 needs Cs == 8", name);
+    if (t->fmt == HESIC_FMT_ROWPAD8_SPLIT)
+      HESIC_REQUIRE((t->Cs == 8 || (t->Cs == 4 && (t->H & 1) == 0)) && t->C <= t->Cs,
+                    "%s: ROWPAD needs Cs == 8 or 4 channel slots (4: even height)", name);
   }
   return HESIC_OK;
 }
 
+// ROWPAD element offset of channel slot 0 of pixel (y, x).  Cs = 8: [B][H+4][W+8][8].  Cs = 4: rows are
+// interleaved in pairs, [B][(H+4)/2][W+8][2][4], so that 8 pixels x 2 rows x 4 slots are 64 contiguous elements.
+__device__ __forceinline__ size_t rowpad_off(const TView &t, int b, int y, int x) {
+  const int Wp = t.W + HESIC_ROWPAD_X, Hp = t.H + HESIC_ROWPAD_Y;
+  if (t.Cs == 8) return (((size_t)b * Hp + y + 2) * Wp + x + 2) * 8;
+  return (((size_t)b * (Hp / 2) + ((y + 2) >> 1)) * Wp + x + 2) * 8 + ((y + 2) & 1) * 4;
+}
+
 __device__ __forceinline__ size_t toff(const TView &t, int b, int c, int y, int x) {
   if (t.fmt == HESIC_FMT_NCHW_F32) return (((size_t)b * t.Cs + c) * t.H + y) * t.W + x;
-  if (t.fmt == HESIC_FMT_ROWPAD8_SPLIT)
-    return (((size_t)b * (t.H + HESIC_ROWPAD_Y) + y + 2) * (t.W + HESIC_ROWPAD_X) + x + 2) * 8 + c;
+  if (t.fmt == HESIC_FMT_ROWPAD8_SPLIT) return rowpad_off(t, b, y, x) + c;
   return (((size_t)b * t.H + y) * t.W + x) * t.Cs + c;
 }
 
@@ -114,6 +123,36 @@ __device__ __forceinline__ void tstore(const TView &t, int b, int c, int y, int 
     ((float *)t.p0)[o] = v;
   }
 }
+
+// One whole pixel of a ROWPAD tensor (all Cs = 8 or 4 channel slots, zeros above n): one 16- or 8-byte store
+// per plane.  v holds n <= Cs values.
+template <int N>
+__device__ __forceinline__ void store_rowpad_pixel(const TView &t, int b, int y, int x, const float (&v)[N]) {
+  const size_t o = rowpad_off(t, b, y, x);
+  __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c < N) split_bf16(v[c < N ? c : 0], hi[c], lo[c]);
+    else { hi[c] = __float2bfloat16_rn(0.f); lo[c] = hi[c]; }
+  }
+  if (t.Cs == 8) {
+    *reinterpret_cast<uint4 *>((__nv_bfloat16 *)t.p0 + o) = *reinterpret_cast<const uint4 *>(hi);
+    *reinterpret_cast<uint4 *>((__nv_bfloat16 *)t.p1 + o) = *reinterpret_cast<const uint4 *>(lo);
+  } else {
+    *reinterpret_cast<uint2 *>((__nv_bfloat16 *)t.p0 + o) = *reinterpret_cast<const uint2 *>(hi);
+    *reinterpret_cast<uint2 *>((__nv_bfloat16 *)t.p1 + o) = *reinterpret_cast<const uint2 *>(lo);
+  }
+}
+
+// Asynchronous global -> shared copies (LDGSTS): all of a block's staging loads are in flight at once instead
+// of one load->store round trip per element.  pred == false writes zeros (src-size 0) without touching src.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = pred ? BYTES : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(gsrc), "n"(BYTES), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == HESIC_ACT_RELU) return fmaxf(v, 0.f);

@@ -9,7 +9,10 @@
 //   SCATTER  stride-2 k5 transposed conv with Cout <= 4 (the RGB synthesis head): one GEMM per input pixel onto
 //            its 5x5xCout output patch, overlap-add in the epilogue (conv_head.cuh); weights [NPAD = 25*Cout
 //            rounded up to 16][Cin], row n = (ky*5 + kx)*Cout + co
-enum { HESIC_TC_GENERIC = 0, HESIC_TC_ROW = 1, HESIC_TC_SCATTER = 2 };
+//   ROW2     Cin <= 4, k5, stride 2 (the first analysis layer, RGB -> N): input in ROWPAD format with 4 channel
+//            slots; one k-step per PAIR of kernel rows, K = 2 rows x 8 pixels x 4 slots, 3 k-steps instead of 5;
+//            weights [3][CoutPad][64] stay resident in shared memory for the whole kernel
+enum { HESIC_TC_GENERIC = 0, HESIC_TC_ROW = 1, HESIC_TC_SCATTER = 2, HESIC_TC_ROW2 = 3 };
 
 struct hesic_conv {
   int Cin = 0, Cout = 0, kh = 0, kw = 0, stride = 1, pad = 0, transposed = 0, out_pad = 0;

@@ -206,7 +206,7 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               float nrm = bet[c];
 #pragma unroll
               for (int j = 0; j < COUT; ++j) nrm = fmaf(gam[j][c], sq[j], nrm);
-              t[c] = x[c] * (p.gdn == 2 ? sqrtf(nrm) : rsqrtf(nrm));
+              t[c] = x[c] * (p.gdn == 2 ? sqrt_approx(nrm) : rsqrt_approx(nrm));
             }
 #pragma unroll
             for (int c = 0; c < COUT; ++c) x[c] = t[c];

@@ -232,6 +232,27 @@ __global__ void pack_conv_row_kernel(const float *__restrict__ w, const float *_
   }
 }
 
+// ROW2 formulation: [s = kernel-row pair][CoutPad][kx*8 + r*4 + c], ky = 2*s + r (rows >= 5 and kx >= 5 zero)
+__global__ void pack_conv_row2_kernel(const float *__restrict__ w, const float *__restrict__ mask, int Cin, int Cout,
+                                      int CoutPad, __nv_bfloat16 *__restrict__ w_hi, __nv_bfloat16 *__restrict__ w_lo) {
+  int total = 3 * CoutPad * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int e = i % 64, r = i / 64;
+    int co = r % CoutPad, s = r / CoutPad;
+    int ky = 2 * s + (e % 8) / 4, kx = e / 8, ci = e % 4;
+    float v = 0.f;
+    if (ky < 5 && kx < 5 && ci < Cin && co < Cout) {
+      size_t src = (((size_t)co * Cin + ci) * 5 + ky) * 5 + kx;
+      v = w[src];
+      if (mask) v *= mask[src];
+    }
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    w_hi[i] = hi;
+    w_lo[i] = lo;
+  }
+}
+
 // SCATTER formulation (RGB synthesis head): [n = (ky*5 + kx)*Cout + co][ci], rows >= 25*Cout zero
 __global__ void pack_conv_scatter_kernel(const float *__restrict__ w, int Cin, int Cout, int NPAD,
                                          __nv_bfloat16 *__restrict__ w_hi, __nv_bfloat16 *__restrict__ w_lo) {
@@ -312,7 +333,9 @@ extern "C" hesic_conv *hesic_conv_create(int Cin, int Cout, int kh, int kw, int 
   c->CoutPad = (Cout + 15) / 16 * 16;
   c->tc_kind = HESIC_TC_GENERIC; c->tc_taps = kh * kw; c->tc_k = Cin;
   const bool k5 = kh == 5 && kw == 5 && pad == 2;
-  if (Cin <= 8 && k5 && ((!c->transposed && (stride == 1 || stride == 2)) ||
+  if (Cin <= 4 && k5 && !c->transposed && stride == 2) {
+    c->tc_kind = HESIC_TC_ROW2; c->tc_taps = 3; c->tc_k = 64;
+  } else if (Cin <= 8 && k5 && ((!c->transposed && (stride == 1 || stride == 2)) ||
                          (c->transposed && stride == 1 && output_padding == 0))) {
     c->tc_kind = HESIC_TC_ROW; c->tc_taps = 5; c->tc_k = 64;
   } else if (c->transposed && stride == 2 && k5 && output_padding == 1 && Cout <= 4 && Cin % 64 == 0 && Cin <= 256) {
@@ -350,6 +373,10 @@ extern "C" int hesic_conv_load(hesic_conv *c, const float *weight, const float *
     pack_conv_row_kernel<<<(5 * c->CoutPad * 64 + 255) / 256, 256, 0, s>>>(weight, mask, c->Cin, c->Cout, c->transposed,
                                                                        c->CoutPad, c->w_hi, c->w_lo);
     HESIC_LAUNCHED("pack_conv_row_kernel");
+  } else if (c->tc_kind == HESIC_TC_ROW2) {
+    pack_conv_row2_kernel<<<(3 * c->CoutPad * 64 + 255) / 256, 256, 0, s>>>(weight, mask, c->Cin, c->Cout, c->CoutPad,
+                                                                        c->w_hi, c->w_lo);
+    HESIC_LAUNCHED("pack_conv_row2_kernel");
   } else if (c->tc_kind == HESIC_TC_SCATTER) {
     HESIC_REQUIRE(mask == nullptr, "hesic_conv_load: masked transposed RGB head is not supported");
     const int NPAD = (25 * c->Cout + 15) / 16 * 16;

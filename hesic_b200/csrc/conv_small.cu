@@ -32,7 +32,7 @@ struct Args {
   int gdn;                // 0 none, 1 GDN, 2 inverse GDN over the Cout channels
   const float *beta, *gamma;   // reparametrised beta [Cout]; gamma as [j][i] (hesic_conv::gdn_w_simt)
   int act;
-  int out_fmt, out_Cs;    // NCHW fp32 (channel slice of out_Cs) or ROWPAD8 split
+  int out_fmt, out_Cs;    // NCHW fp32 (channel slice of out_Cs) or ROWPAD split (out_Cs = 8 or 4 slots)
   void *y0, *y1;
 };
 
@@ -50,16 +50,35 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const Args a) {
     const int tap = a.transposed ? (4 - ky) * 5 + (4 - kx) : ky * 5 + kx;
     wsm[i] = co < COUT ? __ldg(a.w + (size_t)(tap * CIN + ci) * COUT + co) : 0.f;
   }
-  for (int i = tid; i < CIN * ROWS * PITCH; i += NT) {
-    const int col = i % PITCH, r = (i / PITCH) % ROWS, c = i / (PITCH * ROWS);
-    const int gy = y0 - 2 + r, gx = x0 - 2 + col;
-    float v = 0.f;
-    if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-      const float *src = c < a.Ca ? a.xa + ((size_t)b * a.CsA + c) * a.H * a.W
-                                  : a.xb + ((size_t)b * a.CsB + (c - a.Ca)) * a.H * a.W;
-      v = __ldg(src + (size_t)gy * a.W + gx);
+  // input tile: one warp per (channel, row), lanes along x.  The tile starts at x0 - 2 (even), so with an even
+  // image width every float2 is 8-byte aligned and entirely inside or outside the image.
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool vec2 = (a.W & 1) == 0 && ((((uintptr_t)a.xa) | ((uintptr_t)a.xb)) & 7u) == 0;
+    for (int cr = warp; cr < CIN * ROWS; cr += NT / 32) {
+      const int c = cr / ROWS, r = cr - c * ROWS;
+      const int gy = y0 - 2 + r;
+      float *dst = in + (size_t)cr * PITCH;
+      const float *src = nullptr;
+      if (gy >= 0 && gy < a.H)
+        src = (c < a.Ca ? a.xa + ((size_t)b * a.CsA + c) * a.H * a.W : a.xb + ((size_t)b * a.CsB + (c - a.Ca)) * a.H * a.W) +
+              (size_t)gy * a.W;
+      const float *safe = a.xa;   // any valid address for the zero-fill form
+      if (vec2) {
+        for (int col = 2 * lane; col < PITCH; col += 64) {
+          const int gx = x0 - 2 + col;
+          const bool ok = src && gx >= 0 && gx < a.W;
+          cp_async<8>(dst + col, ok ? src + gx : safe, ok);
+        }
+      } else {
+        for (int col = lane; col < PITCH; col += 32) {
+          const int gx = x0 - 2 + col;
+          const bool ok = src && gx >= 0 && gx < a.W;
+          cp_async<4>(dst + col, ok ? src + gx : safe, ok);
+        }
+      }
     }
-    in[i] = v;
+    cp_async_wait_all();
   }
   __syncthreads();
 
@@ -146,19 +165,16 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const Args a) {
             if (ox + p < a.W) dst[p] = o[c][p];
         }
       }
-    } else {   // ROWPAD8 split: one 16-byte (8 channel slots) store per pixel and plane
-      const size_t base = (((size_t)b * (a.H + HESIC_ROWPAD_Y) + oy + 2) * (a.W + HESIC_ROWPAD_X) + ox + 2) * 8;
+    } else {   // ROWPAD split: one store of all channel slots per pixel and plane
+      TView yv;
+      yv.p0 = a.y0; yv.p1 = a.y1; yv.fmt = HESIC_FMT_ROWPAD8_SPLIT; yv.B = a.B; yv.C = COUT; yv.H = a.H; yv.W = a.W; yv.Cs = a.out_Cs;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         if (ox + p >= a.W) continue;
-        __align__(16) __nv_bfloat16 hi[8], lo[8];
+        float v[COUT];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (c < COUT) split_bf16(o[c < COUT ? c : 0][p], hi[c], lo[c]);
-          else { hi[c] = __float2bfloat16_rn(0.f); lo[c] = hi[c]; }
-        }
-        *reinterpret_cast<uint4 *>((__nv_bfloat16 *)a.y0 + base + (size_t)p * 8) = *reinterpret_cast<const uint4 *>(hi);
-        *reinterpret_cast<uint4 *>((__nv_bfloat16 *)a.y1 + base + (size_t)p * 8) = *reinterpret_cast<const uint4 *>(lo);
+        for (int c = 0; c < COUT; ++c) v[c] = o[c][p];
+        store_rowpad_pixel(yv, b, oy, ox + p, v);
       }
     }
   }
@@ -185,7 +201,7 @@ bool conv_small_supported(const hesic_conv *c, const hesic_tensor *xa, const hes
   if (!((c->Cin == 6 && c->Cout == 3) || (c->Cin == 3 && c->Cout == 3))) return false;
   if (xa->fmt != HESIC_FMT_NCHW_F32 || (xb && xb->fmt != HESIC_FMT_NCHW_F32)) return false;
   if (y->fmt == HESIC_FMT_ROWPAD8_SPLIT) {
-    if ((((uintptr_t)y->p0 | (uintptr_t)y->p1) & 15u) != 0) return false;
+    if ((((uintptr_t)y->p0 | (uintptr_t)y->p1) & 15u) != 0 || c->Cout > y->Cs) return false;
   } else if (y->fmt != HESIC_FMT_NCHW_F32) {
     return false;
   }

@@ -82,6 +82,8 @@ struct Params {
   int pl_gdn;              // 0 none, 1 GDN, 2 inverse GDN over the Cout channels (registers)
   const float *pl_gamma;   // fp32 [Cout(j)][Cout(i)] reparametrised (hesic_conv::gdn_w_simt)
   int tma_store;           // 1: epilogue stages 128-byte-wide tiles in smem and writes them with TMA
+  int w_resident;          // all weight tiles ([tap][kchunk][hi, lo]) are loaded once and stay in smem
+  int n_wtiles;            // taps * kchunks (w_resident)
   int stages;
   uint32_t stage_bytes, b_bytes;
   int n_tasks;
@@ -355,7 +357,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const __grid_constant__ CUtensorMap map_y0, const __grid_constant__ CUtensorMap map_y1,
                const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // resident weights (w_resident)
+  const uint32_t smem_base = w_base + (p.w_resident ? (uint32_t)p.n_wtiles * 2u * p.b_bytes : 0u);
+  const uint32_t b_off = p.w_resident ? 0u : 2u * A_TILE_BYTES;             // B operand inside a stage
   const uint32_t stg_base = smem_base + (uint32_t)p.stages * p.stage_bytes;   // epilogue store staging (tma_store)
   const uint32_t bar_base = stg_base + (p.tma_store ? (uint32_t)STAGING_BYTES : 0u);
   // barrier map (8 B each)
@@ -363,7 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto acc_full = [&](int b) { return bar_base + 128u + 8u * b; };
   auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };
-  const uint32_t x2_full = bar_base + 160u, norm_full = bar_base + 168u;
+  const uint32_t x2_full = bar_base + 160u, norm_full = bar_base + 168u, w_full = bar_base + 176u;
   const uint32_t tmem_slot = bar_base + 192u;
   const uint32_t bias_s = bar_base + BAR_BYTES, beta_s = bias_s + 512u;   // per-tile channel constants (fp32 x 128 each)
 
@@ -375,7 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (p.tma_store) { prefetch_map(&map_y0); prefetch_map(&map_y1); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), p.planar ? 128 : EPI_THREADS); }
-    mbar_init(x2_full, EPI_THREADS); mbar_init(norm_full, 1);
+    mbar_init(x2_full, EPI_THREADS); mbar_init(norm_full, 1); mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -395,13 +399,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1u; } };
       const int txy = p.tiles_x * p.tiles_y;
+      if (p.w_resident) {
+        mbar_expect_tx(w_full, (uint32_t)p.n_wtiles * 2u * p.b_bytes);
+        for (int i = 0; i < p.n_wtiles; ++i) {
+          const int t = i / p.kchunks, kc = i - t * p.kchunks;
+          tma_load_3d(&map_w_hi, w_base + (uint32_t)(2 * i) * p.b_bytes, w_full, kc * BK, 0, p.taps[t].w);
+          tma_load_3d(&map_w_lo, w_base + (uint32_t)(2 * i + 1) * p.b_bytes, w_full, kc * BK, 0, p.taps[t].w);
+        }
+      }
       walk_schedule(
           p,
           [&](int, const TaskCoord &tk, int t, int kc, bool, bool) {
             mbar_wait(empty_bar(stage), phase ^ 1u, 1);
             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
             const uint32_t fb = full_bar(stage);
-            mbar_expect_tx(fb, 2u * A_TILE_BYTES + 2u * p.b_bytes);
+            mbar_expect_tx(fb, 2u * A_TILE_BYTES + (p.w_resident ? 0u : 2u * p.b_bytes));
             const int tb = tk.mt / txy, rr = tk.mt - tb * txy;
             const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
             const Tap tap = p.taps[t];
@@ -409,8 +421,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int x = tx * p.bw + tap.dx, y = ty * p.bh + tap.dy, b = tb * p.bb;
             tma_load_5d(&map_a_hi, sa, fb, c, x, tap.py, y, b);
             tma_load_5d(&map_a_lo, sa + A_TILE_BYTES, fb, c, x, tap.py, y, b);
-            tma_load_3d(&map_w_hi, sa + 2 * A_TILE_BYTES, fb, kc * BK, tk.nt * p.BN, tap.w);
-            tma_load_3d(&map_w_lo, sa + 2 * A_TILE_BYTES + p.b_bytes, fb, kc * BK, tk.nt * p.BN, tap.w);
+            if (!p.w_resident) {
+              tma_load_3d(&map_w_hi, sa + 2 * A_TILE_BYTES, fb, kc * BK, tk.nt * p.BN, tap.w);
+              tma_load_3d(&map_w_lo, sa + 2 * A_TILE_BYTES + p.b_bytes, fb, kc * BK, tk.nt * p.BN, tap.w);
+            }
             advance();
           },
           [&](int, int c) {
@@ -418,8 +432,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
             const uint32_t fb = full_bar(stage);
             mbar_expect_tx(fb, 2u * 128u * 128u);
-            tma_load_2d(&map_g_hi, sa + 2 * A_TILE_BYTES, fb, c * BK, 0);
-            tma_load_2d(&map_g_lo, sa + 2 * A_TILE_BYTES + p.b_bytes, fb, c * BK, 0);
+            tma_load_2d(&map_g_hi, sa + b_off, fb, c * BK, 0);
+            tma_load_2d(&map_g_lo, sa + b_off + p.b_bytes, fb, c * BK, 0);
             advance();
           });
     }
@@ -430,9 +444,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1u; } };
       const uint32_t idesc_g = instr_desc(128);
+      if (p.w_resident) {
+        mbar_wait(w_full, 0, 5);
+        tc_fence_after();
+      }
       walk_schedule(
           p,
-          [&](int lt, const TaskCoord &tk, int, int, bool first, bool last) {
+          [&](int lt, const TaskCoord &tk, int t, int kc, bool first, bool last) {
             const int buf = lt & 1;
             if (first) {
               mbar_wait(acc_empty(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u, 2);
@@ -443,7 +461,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t idesc = instr_desc(min(p.BN, p.CoutPad16 - tk.nt * p.BN));
             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
             const uint64_t a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_TILE_BYTES);
-            const uint64_t b_hi = smem_desc(sa + 2 * A_TILE_BYTES), b_lo = smem_desc(sa + 2 * A_TILE_BYTES + p.b_bytes);
+            const uint32_t sb = p.w_resident ? w_base + (uint32_t)(2 * (t * p.kchunks + kc)) * p.b_bytes : sa + 2 * A_TILE_BYTES;
+            const uint64_t b_hi = smem_desc(sb), b_lo = smem_desc(sb + p.b_bytes);
             const uint32_t d_main = tmem_base + (uint32_t)buf * ACC_STRIDE, d_small = d_main + COL_SMALL;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
@@ -466,7 +485,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_wait(full_bar(stage), phase, 6);
             tc_fence_after();
             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
-            const uint64_t b_hi = smem_desc(sa + 2 * A_TILE_BYTES), b_lo = smem_desc(sa + 2 * A_TILE_BYTES + p.b_bytes);
+            const uint64_t b_hi = smem_desc(sa + b_off), b_lo = smem_desc(sa + b_off + p.b_bytes);
             // A operand (x^2 hi | lo, bf16) sits in this buffer's main columns; the norm overwrites small.
             const uint32_t x2 = tmem_base + (uint32_t)buf * ACC_STRIDE, d = x2 + COL_SMALL;
 #pragma unroll
@@ -690,7 +709,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(x2_full);
-        // pass 2: y = x * rsqrt(beta + norm)   (IGDN: * sqrt)
+        // pass 2: y = x * rsqrt(beta + norm)   (IGDN: * sqrt), formed in place so that the accumulator buffer
+        // can be handed back to the MMA warp before the (longer) store phase
         mbar_wait(norm_full, (uint32_t)lt & 1u, 8);
         tc_fence_after();
 #pragma unroll
@@ -703,15 +723,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           ld_chan32(beta_s + 128u * ch, v);
           if (p.gdn == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = xs[i * 32 + j] * sqrt_approx(__uint_as_float(q[j]) + v[j]);
+            for (int j = 0; j < 32; ++j) xs[i * 32 + j] *= sqrt_approx(__uint_as_float(q[j]) + v[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = xs[i * 32 + j] * rsqrt_approx(__uint_as_float(q[j]) + v[j]);
+            for (int j = 0; j < 32; ++j) xs[i * 32 + j] *= rsqrt_approx(__uint_as_float(q[j]) + v[j]);
           }
-          emit(v, i, true);
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = xs[i * 32 + j];
+          emit(v, i, true);
+        }
       }
     }
   }
@@ -788,7 +814,11 @@ static int build_taps(const hesic_conv *c, Params &p) {
   int n = 0;
   p.n_phases = 1; p.os = 1;
   p.tap_begin[0] = 0;
-  if (c->tc_kind == HESIC_TC_ROW) {
+  if (c->tc_kind == HESIC_TC_ROW2) {
+    // one tap per pair of kernel rows (ky = 2s, 2s + 1): box row origin = output row + s in units of two rows
+    for (int s2 = 0; s2 < 3; ++s2) add_tap(p, n, s2, 0, 0, 0, s2);
+    p.tap_begin[1] = n;
+  } else if (c->tc_kind == HESIC_TC_ROW) {
     // one tap per kernel row; the 5 x-taps x 8 channel slots are the K dimension of the box row
     for (int ky = 0; ky < 5; ++ky) {
       if (!c->transposed && c->stride == 2) add_tap(p, n, ky >> 1, 0, ky & 1, 0, ky);
@@ -843,8 +873,10 @@ bool conv_tc_supported(const hesic_conv *c, const hesic_tensor *x, const hesic_t
     if (y->fmt == HESIC_FMT_NHWC_SPLIT && !aligned16(y->p1)) return false;
     if (c->has_gdn && c->Cout != 128) return false;
   }
-  if (c->tc_kind == HESIC_TC_ROW) {
-    if (x->fmt != HESIC_FMT_ROWPAD8_SPLIT) return false;
+  if (c->tc_kind == HESIC_TC_ROW2) {
+    if (x->fmt != HESIC_FMT_ROWPAD8_SPLIT || x->Cs != 4 || ((x->H | x->W) & 1)) return false;
+  } else if (c->tc_kind == HESIC_TC_ROW) {
+    if (x->fmt != HESIC_FMT_ROWPAD8_SPLIT || x->Cs != 8) return false;
     if (!c->transposed && c->stride == 2 && ((x->H | x->W) & 1)) return false;
   } else if (c->tc_kind == HESIC_TC_SCATTER) {
     if (x->fmt != HESIC_FMT_NHWC_SPLIT || !planar_out) return false;
@@ -960,7 +992,8 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.Cout = c->Cout;
   p.CoutPad16 = planar ? 16 : (c->Cout + 15) / 16 * 16;
   p.n_tiles = planar ? 1 : (c->Cout + p.BN - 1) / p.BN;
-  p.kchunks = c->tc_kind == HESIC_TC_ROW ? 1 : (c->Cin + BK - 1) / BK;
+  const bool rowk = c->tc_kind == HESIC_TC_ROW || c->tc_kind == HESIC_TC_ROW2;
+  p.kchunks = rowk ? 1 : (c->Cin + BK - 1) / BK;
   p.in_Cs = xCs;
   p.out_fmt = y->fmt; p.out_Cs = yCs; p.y0 = y->p0; p.y1 = y->p1;
   p.Hout = y->H; p.Wout = y->W; p.B = y->B;
@@ -970,7 +1003,12 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.beta = c->gdn_beta;
   p.pl_gamma = c->gdn_w_simt;
   p.b_bytes = (uint32_t)p.BN * 128u;
-  p.stage_bytes = 2u * A_TILE_BYTES + 2u * p.b_bytes;
+  // ROW2: the whole weight set (3 tiles, hi + lo) fits next to the pipeline -> loaded once per CTA; a stage then
+  // carries only the A tiles (or, for a GDN step, the gamma tiles in the same space)
+  p.n_wtiles = ntaps * p.kchunks;
+  p.w_resident = (c->tc_kind == HESIC_TC_ROW2 && p.n_tiles == 1 && p.b_bytes <= (uint32_t)A_TILE_BYTES) ? 1 : 0;
+  if (getenv("HESIC_TC_NO_RESIDENT")) p.w_resident = 0;
+  p.stage_bytes = 2u * A_TILE_BYTES + (p.w_resident ? 0u : 2u * p.b_bytes);
   // TMA-store epilogue: channels-last outputs; for the sub-pixel phases of a transposed conv the phase
   // column is folded into the channel dimension of the output map, which needs whole store tiles.
   const int store_ch = y->fmt == HESIC_FMT_NHWC_SPLIT ? 64 : 32;
@@ -978,7 +1016,8 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.tma_store = (!planar && (yCs * esz) % 16 == 0 &&
                  (p.os == 1 || (p.os == 2 && c->Cout % store_ch == 0 && !((y->H | y->W) & 1)))) ? 1 : 0;
   if (getenv("HESIC_TC_DIRECT_STORE")) p.tma_store = 0;
-  const int fixed = 1024 + BAR_BYTES + CHAN_BYTES + (p.tma_store ? STAGING_BYTES : 0);
+  const int fixed = 1024 + BAR_BYTES + CHAN_BYTES + (p.tma_store ? STAGING_BYTES : 0) +
+                    (p.w_resident ? p.n_wtiles * 2 * (int)p.b_bytes : 0);
   p.stages = std::min(8, (SMEM_LIMIT - fixed) / (int)p.stage_bytes);
   if (p.stages < 2) { set_error("conv tcgen05: tile does not fit shared memory"); return HESIC_E_UNSUPPORTED; }
   p.n_tasks = p.tiles_x * p.tiles_y * p.tiles_b * p.n_phases * p.n_tiles;
@@ -1012,7 +1051,13 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     uint64_t dims[5], strides[4];
     uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bw, 1u, (uint32_t)p.bh, (uint32_t)p.bb};
     const uint64_t e = 2;
-    if (c->tc_kind == HESIC_TC_ROW) {
+    if (c->tc_kind == HESIC_TC_ROW2) {
+      // row-pair interleaved ROWPAD (4 slots): element (k, ox, pair) = padded pixel 2*ox + k/8, padded row
+      // 2*pair + (k%8)/4, channel slot k%4 -- 64 contiguous elements = 8 pixels x 2 rows x 4 slots
+      const uint64_t pairB = (uint64_t)(x->W + HESIC_ROWPAD_X) * 8 * e, Hp2 = ((uint64_t)x->H + HESIC_ROWPAD_Y) / 2;
+      dims[0] = BK; dims[1] = x->W / 2; dims[2] = 1; dims[3] = Hp2; dims[4] = x->B;
+      strides[0] = 16 * e; strides[1] = pairB; strides[2] = pairB; strides[3] = Hp2 * pairB;
+    } else if (c->tc_kind == HESIC_TC_ROW) {
       // overlapping rows: element (k, ox) = padded pixel (stride*ox + k/8), channel slot k%8
       const uint64_t rowB = (uint64_t)(x->W + HESIC_ROWPAD_X) * 8 * e, Hp = (uint64_t)x->H + HESIC_ROWPAD_Y;
       if (!c->transposed && c->stride == 2) {

@@ -1,6 +1,9 @@
 // HBM-bound kernels of the HESIC forward path: homography warp, entropy-model quantise/likelihood,
 // global max + mixture softmax, bilinear upsample, layout conversion, symbol/index preparation and
 // the rate-distortion partial sums.  All sm_100a, all asynchronous on the caller's stream.
+#include <limits.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace hesic {
@@ -29,78 +32,169 @@ __device__ __forceinline__ void block_add_double(double v, double *acc) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// kornia.warp_perspective.  Thread = one destination pixel, all channels.  The 3x3 chain
-// N_dst * M * N_src^-1 and its inverse are evaluated once per block, and the per-pixel sampling
-// coordinate (normalised grid -> S*g -> divide -> grid_sample unnormalise) per thread, both in fp64;
-// the bilinear blend itself is fp32 like grid_sample's.
-__global__ void __launch_bounds__(256) warp_kernel(const TView src, const float *__restrict__ Mx, const TView dst,
-                                                  int align_corners) {
-  __shared__ double S[9];
+// kornia.warp_perspective.  Block = 32 x 8 destination pixels of one image, thread = one pixel, all channels.
+//  * The 3x3 chain N_dst * M * N_src^-1 and its inverse are evaluated once per block in fp64; the per-pixel
+//    sampling coordinate (normalised grid -> S*g -> divide -> grid_sample unnormalise) is fp64 as well (at
+//    512x512 the fp32 chain loses ~2e-4 px, visible at the 1e-4 level on textured images) but costs ~35 DP
+//    instructions: FMA form, and 1/z by two Newton steps on a MUFU seed instead of an IEEE division.
+//  * Gather staged through shared memory: every thread packs its top-left source tap (x0, y0) into one word,
+//    warp shuffles (redux) reduce the packed words to the warp's source bounding box, the 8 warps merge theirs
+//    with shared-memory atomics, and the block then copies that source window (all channels) row by row with
+//    coalesced loads; the 4 x C bilinear taps read shared memory.  Windows larger than the staging buffer
+//    (strong perspective / minification) fall back to gathering straight from global memory.
+//  * The blend itself is fp32 in grid_sample's order.  Optional second output in ROWPAD format: the warped
+//    image is the input of the next 3->128 tensor-core layer (newnet1.py:753-754), which saves a repack pass.
+constexpr int WARP_STAGE_FLOATS = 6144;   // 24 KB: e.g. 3 channels x 40 x 51 source pixels
+constexpr int WARP_TILE = 32, WARP_ROWS = 4;   // block = 32 x 32 destination pixels, 4 rows per thread
+
+__global__ void __launch_bounds__(256, 3) warp_kernel(const TView src, const float *__restrict__ Mx, const TView dst,
+                                                  const TView dst2, int align_corners) {
+  __shared__ double T[9], S[12];
+  __shared__ int bbox[4];   // min x0, min y0, max x0, max y0 over the block's finite pixels
+  __shared__ float stage[WARP_STAGE_FLOATS];
   const int b = blockIdx.z;
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  // S = (N_dst * M * N_src^-1)^-1 in fp64, nine threads in parallel (one matrix entry each)
+  if (tid < 9) {
+    const int i = tid / 3, j = tid - 3 * i;
     const float *m = Mx + b * 9;
-    double h = src.H, w = src.W, ho = dst.H, wo = dst.W;
-    // A = M * N_src^-1
-    double nsi[9] = {(w - 1) / 2, 0, (w - 1) / 2, 0, (h - 1) / 2, (h - 1) / 2, 0, 0, 1};
-    double nd[9] = {2 / (wo - 1), 0, -1, 0, 2 / (ho - 1), -1, 0, 0, 1};
-    double A[9], T[9];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        double s = 0;
-        for (int k = 0; k < 3; ++k) s += (double)m[i * 3 + k] * nsi[k * 3 + j];
-        A[i * 3 + j] = s;
-      }
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        double s = 0;
-        for (int k = 0; k < 3; ++k) s += nd[i * 3 + k] * A[k * 3 + j];
-        T[i * 3 + j] = s;
-      }
-    double c00 = T[4] * T[8] - T[5] * T[7], c01 = T[5] * T[6] - T[3] * T[8], c02 = T[3] * T[7] - T[4] * T[6];
-    double det = T[0] * c00 + T[1] * c01 + T[2] * c02;
-    double id = 1.0 / det;
-    S[0] = (c00 * id); S[1] = ((T[2] * T[7] - T[1] * T[8]) * id); S[2] = ((T[1] * T[5] - T[2] * T[4]) * id);
-    S[3] = (c01 * id); S[4] = ((T[0] * T[8] - T[2] * T[6]) * id); S[5] = ((T[2] * T[3] - T[0] * T[5]) * id);
-    S[6] = (c02 * id); S[7] = ((T[1] * T[6] - T[0] * T[7]) * id); S[8] = ((T[0] * T[4] - T[1] * T[3]) * id);
+    const double h = src.H, w = src.W, ho = dst.H, wo = dst.W;
+    const double nsi[9] = {(w - 1) / 2, 0, (w - 1) / 2, 0, (h - 1) / 2, (h - 1) / 2, 0, 0, 1};
+    const double nd[9] = {2 / (wo - 1), 0, -1, 0, 2 / (ho - 1), -1, 0, 0, 1};
+    double t = 0;
+    for (int k = 0; k < 3; ++k) {
+      double a = 0;   // (M * N_src^-1)[k][j]
+      for (int l = 0; l < 3; ++l) a += (double)m[k * 3 + l] * nsi[l * 3 + j];
+      t += nd[i * 3 + k] * a;
+    }
+    T[tid] = t;
+  }
+  if (tid == 0) { bbox[0] = bbox[1] = INT_MAX; bbox[2] = bbox[3] = INT_MIN; }
+  __syncthreads();
+  if (tid < 9) {
+    const int i = tid / 3, j = tid - 3 * i;
+    auto cof = [&](int r, int c) {   // cofactor of T[r][c] (cyclic form, sign included)
+      const int r1 = (r + 1) % 3, r2 = (r + 2) % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+      return T[r1 * 3 + c1] * T[r2 * 3 + c2] - T[r1 * 3 + c2] * T[r2 * 3 + c1];
+    };
+    const double det = T[0] * cof(0, 0) + T[1] * cof(0, 1) + T[2] * cof(0, 2);
+    S[tid] = cof(j, i) / det;       // inverse = adjugate / det
+  } else if (tid == 9) {
+    S[9] = dst.W > 1 ? 2.0 / (double)(dst.W - 1) : 0.0;
+  } else if (tid == 10) {
+    S[10] = dst.H > 1 ? 2.0 / (double)(dst.H - 1) : 0.0;
   }
   __syncthreads();
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= dst.W || y >= dst.H) return;
-  // Sampling coordinates in fp64: at 512x512 the fp32 chain ((u+1)/2)*(W-1) alone loses ~2e-4 px,
-  // which is visible at the 1e-4 level on textured images; the fp64 evaluation is exact to ~1e-12 px.
-  double gx = dst.W > 1 ? -1.0 + 2.0 * x / (double)(dst.W - 1) : -1.0;
-  double gy = dst.H > 1 ? -1.0 + 2.0 * y / (double)(dst.H - 1) : -1.0;
-  double u = gx * S[0] + gy * S[1] + S[2];
-  double v = gx * S[3] + gy * S[4] + S[5];
-  double z = gx * S[6] + gy * S[7] + S[8];
-  double sc = fabs(z) > 1e-8 ? 1.0 / z : 1.0;
-  u *= sc; v *= sc;
-  double ix, iy;
-  if (align_corners) {
-    ix = ((u + 1.0) / 2.0) * (double)(src.W - 1);
-    iy = ((v + 1.0) / 2.0) * (double)(src.H - 1);
-  } else {
-    ix = ((u + 1.0) * (double)src.W - 1.0) / 2.0;
-    iy = ((v + 1.0) * (double)src.H - 1.0) / 2.0;
-  }
-  bool finite = isfinite(ix) && isfinite(iy) && fabs(ix) < 1e9 && fabs(iy) < 1e9;
-  double fx = finite ? floor(ix) : 0.0, fy = finite ? floor(iy) : 0.0;
-  int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
-  float ax = (float)(ix - fx), ay = (float)(iy - fy);
-  float wnw = (1.f - ax) * (1.f - ay), wne = ax * (1.f - ay);
-  float wsw = (1.f - ax) * ay, wse = ax * ay;
-  bool vx0 = x0 >= 0 && x0 < src.W, vx1 = x1 >= 0 && x1 < src.W;
-  bool vy0 = y0 >= 0 && y0 < src.H, vy1 = y1 >= 0 && y1 < src.H;
-  for (int c = 0; c < src.C; ++c) {
-    float o = 0.f;
-    if (finite) {
-      if (vy0 && vx0) o += tload(src, b, c, y0, x0) * wnw;
-      if (vy0 && vx1) o += tload(src, b, c, y0, x1) * wne;
-      if (vy1 && vx0) o += tload(src, b, c, y1, x0) * wsw;
-      if (vy1 && vx1) o += tload(src, b, c, y1, x1) * wse;
+  const int x = blockIdx.x * WARP_TILE + threadIdx.x;
+  const double gx = fma((double)x, S[9], -1.0);
+  const double hw = align_corners ? 0.5 * (double)(src.W - 1) : 0.5 * (double)src.W;
+  const double hh = align_corners ? 0.5 * (double)(src.H - 1) : 0.5 * (double)src.H;
+  int x0[WARP_ROWS], y0[WARP_ROWS];
+  float ax[WARP_ROWS], ay[WARP_ROWS];
+  bool fin[WARP_ROWS];
+  unsigned minx = 0xffffu, miny = 0xffffu, maxx = 0u, maxy = 0u;
+  const unsigned bias = 4u;   // x0, y0 >= -2 for finite pixels
+#pragma unroll
+  for (int k = 0; k < WARP_ROWS; ++k) {
+    const int y = blockIdx.y * WARP_TILE + threadIdx.y + 8 * k;
+    const double gy = fma((double)y, S[10], -1.0);
+    double u = fma(gx, S[0], fma(gy, S[1], S[2]));
+    double v = fma(gx, S[3], fma(gy, S[4], S[5]));
+    const double z = fma(gx, S[6], fma(gy, S[7], S[8]));
+    if (fabs(z) > 1e-8) {
+      double r = (double)(1.0f / (float)z);      // 24-bit seed, two Newton steps -> full double precision
+      r = r * (2.0 - z * r);
+      r = r * (2.0 - z * r);
+      u *= r; v *= r;
     }
-    tstore(dst, b, c, y, x, o);
+    // align_corners: ((u+1)/2)*(W-1);  else ((u+1)*W - 1)/2
+    const double ix = align_corners ? (u + 1.0) * hw : fma(u + 1.0, hw, -0.5);
+    const double iy = align_corners ? (v + 1.0) * hh : fma(v + 1.0, hh, -0.5);
+    // samples further than one pixel outside the source contribute nothing; the range test keeps the ints small
+    fin[k] = x < dst.W && y < dst.H && ix > -2.0 && iy > -2.0 && ix < (double)src.W + 1.0 && iy < (double)src.H + 1.0;
+    const double fx = fin[k] ? floor(ix) : 0.0, fy = fin[k] ? floor(iy) : 0.0;
+    x0[k] = (int)fx; y0[k] = (int)fy;
+    ax[k] = (float)(ix - fx); ay[k] = (float)(iy - fy);
+    if (fin[k]) {
+      minx = min(minx, (unsigned)(x0[k] + bias)); maxx = max(maxx, (unsigned)(x0[k] + bias));
+      miny = min(miny, (unsigned)(y0[k] + bias)); maxy = max(maxy, (unsigned)(y0[k] + bias));
+    }
+  }
+  // source window of the block: the (x, y) extremes are packed two to a word and reduced with warp shuffles
+  // (min of the low halves via 0xffff - v), then merged across the 8 warps with shared-memory atomics
+  {
+    unsigned lo = (minx << 16) | miny, hi = (maxx << 16) | maxy;
+    const unsigned minx_w = __reduce_min_sync(0xffffffffu, lo) >> 16, maxx_w = __reduce_max_sync(0xffffffffu, hi) >> 16;
+    const unsigned miny_w = __reduce_min_sync(0xffffffffu, (miny << 16) | minx) >> 16;
+    const unsigned maxy_w = __reduce_max_sync(0xffffffffu, (maxy << 16) | maxx) >> 16;
+    if (threadIdx.x == 0 && maxx_w >= minx_w && minx_w != 0xffffu) {
+      atomicMin(&bbox[0], (int)minx_w - (int)bias); atomicMin(&bbox[1], (int)miny_w - (int)bias);
+      atomicMax(&bbox[2], (int)maxx_w - (int)bias); atomicMax(&bbox[3], (int)maxy_w - (int)bias);
+    }
+  }
+  __syncthreads();
+  // window clipped to the image: columns [wx0, wx0 + ww), rows [wy0, wy0 + wh)
+  int wx0 = 0, wy0 = 0, ww = 0, wh = 0;
+  if (bbox[2] >= bbox[0]) {   // at least one finite pixel
+    wx0 = max(bbox[0], 0); wy0 = max(bbox[1], 0);
+    ww = min(bbox[2] + 1, src.W - 1) - wx0 + 1; wh = min(bbox[3] + 1, src.H - 1) - wy0 + 1;
+  }
+  const bool staged = ww > 0 && wh > 0 && src.fmt == HESIC_FMT_NCHW_F32 &&
+                      (size_t)ww * wh * src.C <= (size_t)WARP_STAGE_FLOATS;
+  if (staged) {
+    const int rows = wh * src.C;
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      const int c = r / wh, yy = wy0 + (r - c * wh);
+      const float *g = (const float *)src.p0 + (((size_t)b * src.Cs + c) * src.H + yy) * src.W + wx0;
+      for (int col = threadIdx.x; col < ww; col += 32) cp_async<4>(stage + r * ww + col, g + col, true);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  if (x >= dst.W) return;
+  const int nc = src.C, plane = wh * ww;
+  const bool nchw_out = dst.fmt == HESIC_FMT_NCHW_F32;
+  const size_t dplane = (size_t)dst.H * dst.W;
+#pragma unroll
+  for (int k = 0; k < WARP_ROWS; ++k) {
+    const int y = blockIdx.y * WARP_TILE + threadIdx.y + 8 * k;
+    if (y >= dst.H) break;
+    const int x1 = x0[k] + 1, y1 = y0[k] + 1;
+    const float wnw = (1.f - ax[k]) * (1.f - ay[k]), wne = ax[k] * (1.f - ay[k]);
+    const float wsw = (1.f - ax[k]) * ay[k], wse = ax[k] * ay[k];
+    const bool vx0 = x0[k] >= 0 && x0[k] < src.W, vx1 = x1 >= 0 && x1 < src.W;
+    const bool vy0 = y0[k] >= 0 && y0[k] < src.H, vy1 = y1 >= 0 && y1 < src.H;
+    const bool t00 = fin[k] && vy0 && vx0, t01 = fin[k] && vy0 && vx1, t10 = fin[k] && vy1 && vx0, t11 = fin[k] && vy1 && vx1;
+    const int o00 = (y0[k] - wy0) * ww + (x0[k] - wx0);   // tap offset inside the staged window
+    auto sample = [&](int c) {
+      float o = 0.f;
+      if (staged) {
+        const float *t = stage + c * plane + o00;
+        if (t00) o += t[0] * wnw;
+        if (t01) o += t[1] * wne;
+        if (t10) o += t[ww] * wsw;
+        if (t11) o += t[ww + 1] * wse;
+      } else {
+        if (t00) o += tload(src, b, c, y0[k], x0[k]) * wnw;
+        if (t01) o += tload(src, b, c, y0[k], x1) * wne;
+        if (t10) o += tload(src, b, c, y1, x0[k]) * wsw;
+        if (t11) o += tload(src, b, c, y1, x1) * wse;
+      }
+      return o;
+    };
+    float *dp = nchw_out ? (float *)dst.p0 + ((size_t)b * dst.Cs * dst.H + y) * dst.W + x : nullptr;
+    float out[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      out[c] = 0.f;
+      if (c < nc) {
+        out[c] = sample(c);
+        if (nchw_out) dp[c * dplane] = out[c];
+        else tstore(dst, b, c, y, x, out[c]);
+      }
+    }
+    for (int c = 8; c < nc; ++c) tstore(dst, b, c, y, x, sample(c));
+    if (dst2.p0) store_rowpad_pixel(dst2, b, y, x, out);
   }
 }
 
@@ -228,6 +322,104 @@ __global__ void __launch_bounds__(256) gaussian_kernel(const TView y, const TVie
   if (log2_sum) block_add_double(lg, log2_sum);
 }
 
+// Tiled form for the layout the forward path uses: y / scales / means channels-last fp32 (read once with
+// 128-bit loads, 4 channels per thread), y_hat / likelihood returned NCHW fp32 like the reference.  A block
+// owns 32 pixels x 64 channels; results cross from channel-major registers to pixel-major stores through a
+// padded shared-memory tile, so both the reads (256 B per pixel) and the writes (128 B per channel row) are
+// whole lines.  Optionally also emits y_hat as bf16 (hi, lo) channels-last planes -- the synthesis stack's
+// input -- saving a separate conversion pass.  Arithmetic identical to gaussian_kernel.
+template <bool MIX>
+__global__ void __launch_bounds__(256) gaussian_tile_kernel(const TView y, const TView scales, const TView means,
+                                                           const float *__restrict__ weights, int K, float scale_bound,
+                                                           float lik_bound, const TView y_hat, const TView lik,
+                                                           const TView y_hat2, double *log2_sum) {
+  __shared__ float s_q[64][33], s_l[64][33];
+  const int HW = y.H * y.W, M = y.C;
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  const int cg = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int c = c0 + cg * 4;
+  double lg = 0.0;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int px = p0 + pl + 16 * it;
+    if (px < HW && c < M) {
+      const size_t pix = (size_t)b * HW + px;
+      const float4 v4 = *reinterpret_cast<const float4 *>((const float *)y.p0 + pix * y.Cs + c);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      float q[4], l[4];
+      if (MIX) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { q[j] = rintf(v[j]); l[j] = 0.f; }
+        for (int k = 0; k < K; ++k) {
+          const int ck = k * M + c;
+          const float4 m4 = *reinterpret_cast<const float4 *>((const float *)means.p0 + pix * means.Cs + ck);
+          const float4 s4 = *reinterpret_cast<const float4 *>((const float *)scales.p0 + pix * scales.Cs + ck);
+          const float4 w4 = *reinterpret_cast<const float4 *>(weights + (size_t)b * K * M + ck);
+          const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, sg[4] = {s4.x, s4.y, s4.z, s4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float d = fabsf(q[j] - mu[j]);
+            const float sc = fmaxf(sg[j], scale_bound);
+            const float term = (std_cumulative((0.5f - d) / sc) - std_cumulative((-0.5f - d) / sc)) * w[j];
+            l[j] = k == 0 ? term : l[j] + term;
+          }
+        }
+      } else {
+        const float4 s4 = *reinterpret_cast<const float4 *>((const float *)scales.p0 + pix * scales.Cs + c);
+        const float sg[4] = {s4.x, s4.y, s4.z, s4.w};
+        float mu[4] = {0.f, 0.f, 0.f, 0.f};
+        if (means.p0) {
+          const float4 m4 = *reinterpret_cast<const float4 *>((const float *)means.p0 + pix * means.Cs + c);
+          mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d;
+          if (means.p0) {
+            const float r = rintf(v[j] - mu[j]);
+            q[j] = r + mu[j];
+            d = fabsf(q[j] - mu[j]);
+          } else {
+            q[j] = rintf(v[j]);
+            d = fabsf(q[j]);
+          }
+          const float sc = fmaxf(sg[j], scale_bound);
+          l[j] = std_cumulative((0.5f - d) / sc) - std_cumulative((-0.5f - d) / sc);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (lik_bound > 0.f) l[j] = fmaxf(l[j], lik_bound);
+        s_q[cg * 4 + j][pl + 16 * it] = q[j];
+        s_l[cg * 4 + j][pl + 16 * it] = l[j];
+        lg += (double)log2f(l[j]);
+      }
+      if (y_hat2.p0) {
+        __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_bf16(q[j], hi[j], lo[j]);
+        const size_t o = pix * y_hat2.Cs + c;
+        *reinterpret_cast<uint2 *>((__nv_bfloat16 *)y_hat2.p0 + o) = *reinterpret_cast<const uint2 *>(hi);
+        *reinterpret_cast<uint2 *>((__nv_bfloat16 *)y_hat2.p1 + o) = *reinterpret_cast<const uint2 *>(lo);
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int px = p0 + lane;
+  if (px < HW) {
+    for (int r = wrp; r < 64; r += 8) {
+      const int ch = c0 + r;
+      if (ch >= M) break;
+      const size_t o = ((size_t)b * y_hat.Cs + ch) * HW + px;
+      if (y_hat.p0) ((float *)y_hat.p0)[((size_t)b * y_hat.Cs + ch) * HW + px] = s_q[r][lane];
+      if (lik.p0) ((float *)lik.p0)[((size_t)b * lik.Cs + ch) * HW + px] = s_l[r][lane];
+      (void)o;
+    }
+  }
+  if (log2_sum) block_add_double(lg, log2_sum);
+}
+
 // ---------------------------------------------------------------------------------------------
 // spatial_pool2d: global max per (b, c).
 // NHWC: block = 32 channels x 8 pixel lanes (a warp reads 32 consecutive channels of one pixel).
@@ -321,8 +513,8 @@ __global__ void __launch_bounds__(256) convert_kernel(const TView x, const TView
   tstore(y, b, c, yy, xx, v);
 }
 
-// NCHW fp32 (C <= 8) -> ROWPAD8 split planes: thread = pixel, one 16-byte store per plane (all 8
-// channel slots, zeros above C), reads coalesced per source plane.
+// NCHW fp32 (C <= 8) -> ROWPAD split planes: thread = pixel, one 16- or 8-byte store per plane (all channel
+// slots, zeros above C), reads coalesced per source plane.
 __global__ void __launch_bounds__(256) rowpad_kernel(const TView x, const TView y, int op, size_t npix) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= npix) return;
@@ -335,12 +527,7 @@ __global__ void __launch_bounds__(256) rowpad_kernel(const TView x, const TView 
     if (op == HESIC_OP_ABS) v[c] = fabsf(v[c]);
     else if (op == HESIC_OP_ROUND) v[c] = rintf(v[c]);
   }
-  __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) split_bf16(v[c], hi[c], lo[c]);
-  size_t o = toff(y, b, 0, yy, xx);
-  *reinterpret_cast<uint4 *>((__nv_bfloat16 *)y.p0 + o) = *reinterpret_cast<const uint4 *>(hi);
-  *reinterpret_cast<uint4 *>((__nv_bfloat16 *)y.p1 + o) = *reinterpret_cast<const uint4 *>(lo);
+  store_rowpad_pixel(y, b, yy, xx, v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -398,16 +585,26 @@ static inline unsigned nblk(size_t n) { return (unsigned)((n + 255) / 256); }
 using namespace hesic;
 
 extern "C" int hesic_warp_perspective(const hesic_tensor *src, const float *M, const hesic_tensor *dst,
-                                      int align_corners, void *stream) {
+                                      const hesic_tensor *dst_rowpad, int align_corners, void *stream) {
   int r;
   if ((r = check_tensor(src, "warp src")) != HESIC_OK) return r;
   if ((r = check_tensor(dst, "warp dst")) != HESIC_OK) return r;
+  TView d2;
+  memset(&d2, 0, sizeof(d2));
+  if (dst_rowpad && dst_rowpad->p0) {
+    if ((r = check_tensor(dst_rowpad, "warp dst_rowpad")) != HESIC_OK) return r;
+    HESIC_REQUIRE(dst_rowpad->fmt == HESIC_FMT_ROWPAD8_SPLIT && same_shape(dst, dst_rowpad) && dst->C <= dst_rowpad->Cs,
+                  "warp: dst_rowpad must be a ROWPAD tensor shaped like dst");
+    HESIC_REQUIRE((((uintptr_t)dst_rowpad->p0 | (uintptr_t)dst_rowpad->p1) & 15u) == 0, "warp: dst_rowpad is misaligned");
+    d2 = view(dst_rowpad);
+  }
   HESIC_REQUIRE(M != nullptr, "warp: null homography");
   HESIC_REQUIRE(src->B == dst->B && src->C == dst->C, "warp: batch/channel mismatch");
   HESIC_REQUIRE(src->p0 != dst->p0, "warp: in-place is not supported");
   if (numel(dst) == 0) return HESIC_OK;
-  dim3 blk(32, 8), grid((dst->W + 31) / 32, (dst->H + 7) / 8, dst->B);
-  warp_kernel<<<grid, blk, 0, as_stream(stream)>>>(view(src), M, view(dst), align_corners);
+  HESIC_REQUIRE(src->H < 60000 && src->W < 60000, "warp: source image too large");
+  dim3 blk(32, 8), grid((dst->W + WARP_TILE - 1) / WARP_TILE, (dst->H + WARP_TILE - 1) / WARP_TILE, dst->B);
+  warp_kernel<<<grid, blk, 0, as_stream(stream)>>>(view(src), M, view(dst), d2, align_corners);
   HESIC_LAUNCHED("warp_kernel");
   return HESIC_OK;
 }
@@ -444,10 +641,15 @@ extern "C" int hesic_entropy_bottleneck(const hesic_tensor *z, const float *para
   return HESIC_OK;
 }
 
+static bool vec4_ok(const hesic_tensor *t) {
+  const int Cs = t->Cs > 0 ? t->Cs : t->C;
+  return t->fmt == HESIC_FMT_NHWC_F32 && (Cs & 3) == 0 && ((uintptr_t)t->p0 & 15u) == 0;
+}
+
 extern "C" int hesic_gaussian_conditional(const hesic_tensor *y, const hesic_tensor *scales, const hesic_tensor *means,
                                           const float *weights, int K, int mixture, float scale_bound,
                                           float likelihood_bound, const hesic_tensor *y_hat, const hesic_tensor *lik,
-                                          double *log2_sum, void *stream) {
+                                          const hesic_tensor *y_hat_split, double *log2_sum, void *stream) {
   int r;
   if ((r = check_tensor(y, "gaussian input")) != HESIC_OK) return r;
   if ((r = check_tensor(scales, "gaussian scales")) != HESIC_OK) return r;
@@ -465,11 +667,38 @@ extern "C" int hesic_gaussian_conditional(const hesic_tensor *y, const hesic_ten
   if (mu->p0) HESIC_REQUIRE(mu->B == y->B && mu->H == y->H && mu->W == y->W, "gaussian: means shape mismatch");
   if (yh->p0) HESIC_REQUIRE(same_shape(y, yh), "gaussian: y_hat shape mismatch");
   if (lk->p0) HESIC_REQUIRE(same_shape(y, lk), "gaussian: likelihood shape mismatch");
+  const hesic_tensor *y2 = y_hat_split ? y_hat_split : &nt;
+  if (y2->p0) {
+    HESIC_REQUIRE(same_shape(y, y2) && y2->fmt == HESIC_FMT_NHWC_SPLIT, "gaussian: y_hat_split must be a SPLIT tensor like y");
+    int r2;
+    if ((r2 = check_tensor(y2, "gaussian y_hat_split")) != HESIC_OK) return r2;
+  }
   size_t n = numel(y);
   if (n == 0) return HESIC_OK;
+  // the forward path's layout: channels-last inputs read with 128-bit loads, NCHW outputs through a smem transpose
+  const bool tiled = vec4_ok(y) && vec4_ok(scales) && (!mu->p0 || vec4_ok(mu)) && (y->C & 3) == 0 &&
+                     (!yh->p0 || yh->fmt == HESIC_FMT_NCHW_F32) && (!lk->p0 || lk->fmt == HESIC_FMT_NCHW_F32) &&
+                     (!mixture || ((uintptr_t)weights & 15u) == 0) && y->B <= 65535 &&
+                     (!y2->p0 || (((y2->Cs > 0 ? y2->Cs : y2->C) & 3) == 0 && (((uintptr_t)y2->p0 | (uintptr_t)y2->p1) & 7u) == 0));
+  if (tiled) {
+    dim3 grid((y->H * y->W + 31) / 32, (y->C + 63) / 64, y->B);
+    if (mixture)
+      gaussian_tile_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(view(y), view(scales), view(mu), weights, K, scale_bound,
+                                                                    likelihood_bound, view(yh), view(lk), view(y2), log2_sum);
+    else
+      gaussian_tile_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(view(y), view(scales), view(mu), weights, K, scale_bound,
+                                                                     likelihood_bound, view(yh), view(lk), view(y2), log2_sum);
+    HESIC_LAUNCHED("gaussian_tile_kernel");
+    return HESIC_OK;
+  }
   gaussian_kernel<<<nblk(n), 256, 0, as_stream(stream)>>>(view(y), view(scales), view(mu), weights, K, mixture,
                                                          scale_bound, likelihood_bound, view(yh), view(lk), log2_sum, n);
   HESIC_LAUNCHED("gaussian_kernel");
+  if (y2->p0) {
+    // generic path: second copy of y_hat by conversion
+    HESIC_REQUIRE(yh->p0 != nullptr, "gaussian: y_hat_split needs y_hat on the generic path");
+    return hesic_convert(yh, y2, HESIC_OP_COPY, stream);
+  }
   return HESIC_OK;
 }
 

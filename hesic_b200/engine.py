@@ -88,18 +88,19 @@ class HesicEngine:
         plan.run(x_desc, d, act, self.path, xb_desc)
         return t, d, Ho, Wo
 
-    def _rowpad_buf(self, slot, B, H, W):
-        """Cached ROWPAD8 buffer (zero border and zero unused channel slots written once)."""
-        key = (slot, B, H, W, str(self.dev))
+    def _rowpad_buf(self, slot, B, H, W, slots=4):
+        """Cached ROWPAD buffer (zero border and zero unused channel slots written once).  slots = 4: input of the
+        3 -> N stride-2 first analysis layer; 8: 6-channel concatenations on the tensor-core path."""
+        key = (slot, B, H, W, slots, str(self.dev))
         t = self._rowpads.get(key)
         if t is None:
-            t = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, 8), device=self.dev, dtype=torch.bfloat16)
+            t = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, slots), device=self.dev, dtype=torch.bfloat16)
             self._rowpads[key] = t
         return t
 
     def _rowpad(self, slot, src_desc, B, Cn, H, W):
         """NCHW fp32 view (<= 8 channels) -> cached ROWPAD8 buffer (its zero border is written once)."""
-        t = self._rowpad_buf(slot, B, H, W)
+        t = self._rowpad_buf(slot, B, H, W, 4 if Cn <= 4 else 8)
         d = C.rowpad(t, Cn)
         self._convert(src_desc, d)
         return d
@@ -107,8 +108,10 @@ class HesicEngine:
     def _convert(self, src_desc, dst_desc, op=C.OP_COPY):
         C.check(_lib.hesic_convert(C.ref(src_desc), C.ref(dst_desc), op, C.stream()))
 
-    def _warp(self, src_desc, h, dst_desc):
-        C.check(_lib.hesic_warp_perspective(C.ref(src_desc), C.ptr(h), C.ref(dst_desc), int(self.align_corners), C.stream()))
+    def _warp(self, src_desc, h, dst_desc, dst_rowpad=None):
+        C.check(_lib.hesic_warp_perspective(C.ref(src_desc), C.ptr(h), C.ref(dst_desc),
+                                            C.ref(dst_rowpad) if dst_rowpad is not None else None,
+                                            int(self.align_corners), C.stream()))
 
     # ---- sub-networks ---------------------------------------------------------------------
     def _analysis(self, enc, x_desc, B, H, W):
@@ -155,12 +158,14 @@ class HesicEngine:
         return out
 
     def _gmm(self, gm, y_d, s_d, m_d, w, B, H, W, M, K, acc):
+        """-> y_hat (NCHW, returned to the caller), likelihood (NCHW), y_hat as SPLIT planes (synthesis input)."""
         y_hat = _nchw(B, M, H, W, self.dev)
         lik = _nchw(B, M, H, W, self.dev)
+        yh_split_d = C.split(_split(B, H, W, M, self.dev))
         C.check(_lib.hesic_gaussian_conditional(C.ref(y_d), C.ref(s_d), C.ref(m_d), C.ptr(w), K, 1, gm._scale_bound_value(),
-                                                gm._lik_bound(), C.ref(C.nchw(y_hat)), C.ref(C.nchw(lik)), C.ptr(acc),
-                                                C.stream()))
-        return y_hat, lik
+                                                gm._lik_bound(), C.ref(C.nchw(y_hat)), C.ref(C.nchw(lik)), C.ref(yh_split_d),
+                                                C.ptr(acc), C.stream()))
+        return y_hat, lik, yh_split_d
 
     # ---- forward --------------------------------------------------------------------------
     @torch.no_grad()
@@ -199,10 +204,7 @@ class HesicEngine:
             _, s_d, _, _ = self._seq3(hs.gmm_sigma, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_RELU), z1h_d, B, Hz, Wz, "nhwc")
             _, m_d, _, _ = self._seq3(hs.gmm_means, (0, 2, 4), (C.ACT_LEAKY, C.ACT_LEAKY, C.ACT_NONE), z1h_d, B, Hz, Wz, "nhwc")
             w1 = self._mixture_head(hs.gmm_weights, z1h_d, B, Hz, Wz, K, M)
-            y1_hat, y1_lik = self._gmm(m.gaussian1, y1_d, s_d, m_d, w1, B, Hy, Wy, M, K, a(0))
-            y1h_split = _split(B, Hy, Wy, M, dev)
-            y1h_split_d = C.split(y1h_split)
-            self._convert(C.nchw(y1_hat), y1h_split_d)
+            y1_hat, y1_lik, y1h_split_d = self._gmm(m.gaussian1, y1_d, s_d, m_d, w1, B, Hy, Wy, M, K, a(0))
         x1_hat, _, _, _ = self._synthesis(m.decoder1, y1h_split_d, B, Hy, Wy)
 
         # ---- view 2 analysis -------------------------------------------------------------
@@ -224,7 +226,10 @@ class HesicEngine:
             pre_d = self._rowpad("pre", pre_nchw_d, B, 3, H, W)
         y2, y2_d, _, _ = self._analysis(enc2, pre_d, B, H, W)
         x1hw_d = C.nchw(cat_out, 3, 3)
-        self._warp(C.nchw(x1_hat), h, x1hw_d)          # newnet1.py:753 and :767 (identical) run once
+        x1hw_rp = None
+        if self.variant != "newnet9":                  # "twiceLeft": the warped reconstruction is re-encoded
+            x1hw_rp = C.rowpad(self._rowpad_buf("x1hw", B, H, W), 3)
+        self._warp(C.nchw(x1_hat), h, x1hw_d, x1hw_rp)  # newnet1.py:753 and :767 (identical) run once
 
         # ---- conditioning on the left view ----------------------------------------------
         if joint:
@@ -238,7 +243,7 @@ class HesicEngine:
         if self.variant == "newnet9":
             self._convert(y1h_split_d, cond_slice)
         else:
-            yw, yw_d, _, _ = self._analysis(m.encoder1, self._rowpad("x1hw", x1hw_d, B, 3, H, W), B, H, W)   # "twiceLeft"
+            yw, yw_d, _, _ = self._analysis(m.encoder1, x1hw_rp, B, H, W)   # "twiceLeft"
             self._convert(yw_d, cond_slice, C.OP_ROUND)
 
         # ---- view 2 entropy model ---------------------------------------------------------
@@ -257,10 +262,7 @@ class HesicEngine:
             _, s_d, _, _ = self._seq3(hs.gmm_sigma, (0, 2, 4), (r3, r3, r3), cd, B, Hy, Wy, "nhwc")
             _, m_d, _, _ = self._seq3(hs.gmm_means, (0, 2, 4), (r2, r2, C.ACT_NONE), cd, B, Hy, Wy, "nhwc")
             w2 = self._mixture_head(hs.gmm_weights, cd, B, Hy, Wy, K, M)
-            y2_hat, y2_lik = self._gmm(m.gaussian2, y2_d, s_d, m_d, w2, B, Hy, Wy, M, K, a(1))
-            y2h_split = _split(B, Hy, Wy, M, dev)
-            y2h_split_d = C.split(y2h_split)
-            self._convert(C.nchw(y2_hat), y2h_split_d)
+            y2_hat, y2_lik, y2h_split_d = self._gmm(m.gaussian2, y2_d, s_d, m_d, w2, B, Hy, Wy, M, K, a(1))
 
         # ---- view 2 synthesis ---------------------------------------------------------------
         dec2 = m.decoder2
@@ -314,6 +316,6 @@ class HesicEngine:
         lik = _nchw(B, M, Hy, Wy, dev)
         gc = m.gaussian_conditional1                  # the reference uses conditional1 for both views (:725)
         C.check(_lib.hesic_gaussian_conditional(C.ref(y_d), C.ref(scales_d), C.ref(means_d), None, 1, 0,
-                                                gc._scale_bound_value(), gc._lik_bound(), None, C.ref(C.nchw(lik)),
+                                                gc._scale_bound_value(), gc._lik_bound(), None, C.ref(C.nchw(lik)), None,
                                                 C.ptr(acc_y), C.stream()))
         return y_hat, lik, yh_d

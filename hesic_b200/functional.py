@@ -97,7 +97,8 @@ def conv2d(x, plan, act=C.ACT_NONE, path=C.PATH_AUTO):
     # the tensor-core path consumes bf16 (hi, lo) planes: ROWPAD8 for the <= 8-channel edge layers,
     # channels-last otherwise
     if Cin <= 8:
-        xin = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, 8), device=x.device, dtype=torch.bfloat16)
+        slots = C.rowpad_slots(Cin, plan.geom[4], plan.geom[6])
+        xin = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, slots), device=x.device, dtype=torch.bfloat16)
         xd = C.rowpad(xin, Cin)
     else:
         xin = torch.empty((2, B, H, W, Cin), device=x.device, dtype=torch.bfloat16)
@@ -130,7 +131,7 @@ def warp_perspective(src, M, dsize, align_corners=True, out=None):
         raise ValueError(f"warp_perspective: M must be [B,3,3], got {tuple(M.shape)}")
     if out is None:
         out = torch.empty((src.shape[0], src.shape[1], int(dsize[0]), int(dsize[1])), device=src.device, dtype=torch.float32)
-    C.check(_lib.hesic_warp_perspective(C.ref(C.nchw(src)), C.ptr(M), C.ref(C.nchw(out)), int(bool(align_corners)), C.stream()))
+    C.check(_lib.hesic_warp_perspective(C.ref(C.nchw(src)), C.ptr(M), C.ref(C.nchw(out)), None, int(bool(align_corners)), C.stream()))
     return out
 
 
@@ -165,7 +166,7 @@ def gaussian_mixture_conditional(y, scales, means, weights, K, scale_bound=0.11,
     lik = torch.empty_like(y)
     C.check(_lib.hesic_gaussian_conditional(C.ref(C.nchw(y)), C.ref(C.nchw(scales)), C.ref(C.nchw(means)), C.ptr(w), K, 1,
                                             float(scale_bound), float(likelihood_bound), C.ref(C.nchw(y_hat)),
-                                            C.ref(C.nchw(lik)), C.ptr(log2_acc), C.stream()))
+                                            C.ref(C.nchw(lik)), None, C.ptr(log2_acc), C.stream()))
     return y_hat, lik
 
 
@@ -177,7 +178,7 @@ def gaussian_conditional(y, scales, means=None, scale_bound=0.11, likelihood_bou
     lik = torch.empty_like(y)
     C.check(_lib.hesic_gaussian_conditional(C.ref(C.nchw(y)), C.ref(C.nchw(scales)), C.ref(mu), None, 1, 0,
                                             float(scale_bound), float(likelihood_bound), C.ref(C.nchw(y_hat)),
-                                            C.ref(C.nchw(lik)), C.ptr(log2_acc), C.stream()))
+                                            C.ref(C.nchw(lik)), None, C.ptr(log2_acc), C.stream()))
     return y_hat, lik
 
 

@@ -40,8 +40,9 @@ enum {
 enum { HESIC_FMT_NCHW_F32 = 0, HESIC_FMT_NHWC_F32 = 1, HESIC_FMT_NHWC_SPLIT = 2, HESIC_FMT_ROWPAD8_SPLIT = 3 };
 /* ROWPAD8_SPLIT is the input format of the full-resolution edge layers (Cin <= 8: the RGB images and
  * the 6-channel concatenations of newnet1.py:643,686): bf16 (hi, lo) planes of
- * [B][H + HESIC_ROWPAD_Y][W + HESIC_ROWPAD_X][8], image at row/column offset 2, border and unused
- * channels zero.  One TMA box row of 64 elements = the 8 pixels x 8 channels a 5-tap kernel row
+ * [B][H + HESIC_ROWPAD_Y][W + HESIC_ROWPAD_X][8] (Cs = 8 channel slots), image at row/column offset 2, border
+ * and unused channels zero.  Cs = 4 (<= 4 channels, even H; input of the 3 -> N stride-2 first layer) interleaves
+ * rows in pairs: [B][(H + 4) / 2][W + 8][2][4], so 8 pixels x 2 rows x 4 slots are 64 contiguous elements.  One TMA box row of 64 elements = the 8 pixels x 8 channels a 5-tap kernel row
  * needs, so the tensor-core path reads it as an implicit im2col with K = 64 per kernel row. */
 #define HESIC_ROWPAD_Y 4
 #define HESIC_ROWPAD_X 8
@@ -108,9 +109,11 @@ int hesic_gdn(const hesic_tensor *x, const hesic_tensor *y, const float *beta, c
  * kornia.warp_perspective(src, M, dsize) as called at newnet1.py:746,753,767,1287,1291:
  * dst(x,y) = bilinear(src, M^-1 (x,y,1)), zero padding, kornia's normalise/invert/denormalise
  * arithmetic, align_corners selectable (1 = the convention used throughout this repository).
- * M: dev fp32 [B,3,3].  src/dst: NCHW fp32 (dst may be a channel slice). */
-int hesic_warp_perspective(const hesic_tensor *src, const float *M, const hesic_tensor *dst, int align_corners,
-                           void *stream);
+ * M: dev fp32 [B,3,3].  src/dst: NCHW fp32 (dst may be a channel slice).  dst_rowpad (may be NULL): the
+ * same result written a second time in ROWPAD format, for the warped image that feeds the next 3->128
+ * layer (newnet1.py:753-754). */
+int hesic_warp_perspective(const hesic_tensor *src, const float *M, const hesic_tensor *dst,
+                           const hesic_tensor *dst_rowpad, int align_corners, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * EntropyBottleneck.forward, eval mode (compressai/entropy_models/entropy_models.py:384-411,
@@ -132,11 +135,12 @@ int hesic_entropy_bottleneck(const hesic_tensor *z, const float *params, float l
  * lik = sum_k w[k*M+m] * (Phi((.5-|y_hat-mu|)/s) - Phi((-.5-|y_hat-mu|)/s)), s = max(sigma, bound).
  * scales/means: [B, K*M, H, W]; weights: dev fp32 [B, K*M].  K = 1 with weights == NULL is
  * GaussianConditional.forward (entropy_models.py:528-554): y_hat = round(y - mu) + mu (mu may be
- * absent: means->p0 == NULL). */
+ * absent: means->p0 == NULL).  y_hat_split (may be NULL): a second copy of y_hat as SPLIT planes, the
+ * input format of the synthesis stack that consumes it (newnet1.py:744,762). */
 int hesic_gaussian_conditional(const hesic_tensor *y, const hesic_tensor *scales, const hesic_tensor *means,
                                const float *weights, int K, int mixture, float scale_bound,
                                float likelihood_bound, const hesic_tensor *y_hat, const hesic_tensor *lik,
-                               double *log2_sum, void *stream);
+                               const hesic_tensor *y_hat_split, double *log2_sum, void *stream);
 
 /* spatial_pool2d (newnet1.py:441-453) + LeakyReLU + conv1x1(K*M -> K*M) + softmax over the K
  * components (newnet1.py:498-512,572-574).  x: [B, K*M, H, W]; w1x1: dev fp32 [K*M, K*M] (the

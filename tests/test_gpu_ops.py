@@ -27,6 +27,8 @@ def _rand(shape, seed, scale=1.0):
 CONV_CASES = [
     # Cin, Cout, k, stride, transposed, H, W, B
     (3, 128, 5, 2, False, 64, 64, 2),      # encoder first layer
+    (3, 128, 5, 2, False, 40, 24, 3),      # ... ragged tiles
+    (3, 64, 5, 2, False, 16, 32, 1),       # ... narrower N tile
     (128, 128, 5, 2, False, 32, 48, 2),    # main analysis layer (ragged W tile)
     (128, 192, 5, 2, False, 16, 16, 1),
     (192, 128, 5, 1, False, 8, 8, 3),      # encode_hyper first conv
@@ -69,8 +71,8 @@ def test_conv_parity(case, path):
 
 
 @pytest.mark.parametrize("size", [(2, 40, 24), (1, 64, 128), (2, 70, 67)])
-@pytest.mark.parametrize("transposed", [False, True])
-def test_few_channel_stencil_cat_gdn_rowpad(size, transposed):
+@pytest.mark.parametrize("transposed,slots", [(False, 4), (False, 8), (True, 8)])
+def test_few_channel_stencil_cat_gdn_rowpad(size, transposed, slots):
     """pre_gdn(pre_conv(cat(a, b))) / after_conv(cat(a, b)) (newnet1.py:643-644,686): the exact-fp32 stencil fed two
     sources, with the fused 3-channel GDN, writing NCHW and the ROWPAD8 (hi, lo) planes of the next layer."""
     from hesic_b200 import _capi as C
@@ -98,9 +100,11 @@ def test_few_channel_stencil_cat_gdn_rowpad(size, transposed):
     assert float(out[:, 0].abs().max()) == 0 and float(out[:, 4].abs().max()) == 0
     # (2) fused GDN, ROWPAD8 output
     plan.set_gdn(g.beta, g.gamma, g.inverse, g.beta_min)
-    rp = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, 8), device=DEV, dtype=torch.bfloat16)
+    rp = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, slots), device=DEV, dtype=torch.bfloat16)
     plan.run(C.nchw(xa_d), C.rowpad(rp, 3), C.ACT_NONE, C.PATH_AUTO, C.nchw(xb_d))
     val = (rp[0].float() + rp[1].float())
+    if slots == 4:   # rows interleaved in pairs: [B][(H+4)/2][W+8][2][4]
+        val = val.reshape(B, (H + 4) // 2, W + 8, 2, 4).permute(0, 1, 3, 2, 4).reshape(B, H + 4, W + 8, 4)
     inner = val[:, 2:2 + H, 2:2 + W, :3].permute(0, 3, 1, 2)
     assert_close(inner, ref_g, 2e-5, what="stencil conv + GDN -> ROWPAD8")
     border = val.clone()

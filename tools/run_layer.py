@@ -20,7 +20,7 @@ mod = (T.deconv if tr else T.conv)(Cin, Cout, kernel_size=k, stride=s).to(T.DEV)
 plan = mod.hesic_plan()
 if gdn:
     plan.set_gdn(torch.ones(Cout, device=T.DEV), 0.1 * torch.eye(Cout, device=T.DEV) + 0.01, gdn == 2)
-xd = T.to_split(torch.randn(B, Cin, H, W).to(T.DEV))
+xd = T.to_split(torch.randn(B, Cin, H, W).to(T.DEV), s, tr)
 Ho, Wo = plan.out_hw(H, W)
 if Cout <= 4:
     yt = torch.zeros((B, Cout, Ho, Wo), device=T.DEV); yd = C.nchw(yt)

@@ -53,11 +53,12 @@ GROUPS = {
 }
 
 
-def to_split(x):
-    """-> descriptor of the bf16 (hi, lo) planes the tensor-core path reads (ROWPAD8 for <= 8 channels)."""
+def to_split(x, stride=1, transposed=False):
+    """-> descriptor of the bf16 (hi, lo) planes the tensor-core path reads (ROWPAD, 4 or 8 slots, for <= 8 channels)."""
     B, Cn, H, W = x.shape
     if Cn <= 8:
-        xs = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, 8), device=x.device, dtype=torch.bfloat16)
+        slots = C.rowpad_slots(Cn, stride, transposed)
+        xs = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, slots), device=x.device, dtype=torch.bfloat16)
         d = C.rowpad(xs, Cn)
     else:
         xs = torch.empty((2, B, H, W, Cn), device=x.device, dtype=torch.bfloat16)
@@ -75,7 +76,7 @@ def time_case(case):
     plan = mod.hesic_plan()
     if gdn:
         plan.set_gdn(torch.ones(Cout, device=DEV), 0.1 * torch.eye(Cout, device=DEV) + 0.01, gdn == 2)
-    xd = to_split(torch.randn(B, Cin, H, W, generator=g).to(DEV))
+    xd = to_split(torch.randn(B, Cin, H, W, generator=g).to(DEV), s, tr)
     Ho, Wo = plan.out_hw(H, W)
     if Cout <= 4:
         yt = torch.zeros((B, Cout, Ho, Wo), device=DEV); yd = C.nchw(yt)
@@ -114,7 +115,7 @@ def run_case(case, timing=False):
         gamma = (torch.rand(Cout, Cout, generator=g) * 0.02 + 0.1 * torch.eye(Cout)).to(DEV)
         plan.set_gdn(beta, gamma, gdn == 2)
     x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
-    xd = to_split(x)
+    xd = to_split(x, s, tr)
     Ho, Wo = plan.out_hw(H, W)
     outs = {}
     planar = Cout <= 4
