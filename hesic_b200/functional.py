@@ -322,3 +322,32 @@ class RansDecoderHandle:
         C.check(_lib.hesic_rans_decoder_decode(self.h, i.ctypes.data, i.size, c.ctypes.data, c.shape[0], c.shape[1],
                                                z.ctypes.data, o.ctypes.data, out.ctypes.data))
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# operators of the DSIC variant (ywz/DSIC/mynet6_plus.py)
+def group_norm(x, groups, weight=None, bias=None, eps=1e-5, relu=False):
+    """nn.GroupNorm(groups, C) (+ the ReLU that follows it everywhere in mynet6_plus.py:224-290)."""
+    x = _f32(x)
+    y = torch.empty_like(x)
+    w = _f32(weight.detach()) if weight is not None else None
+    b = _f32(bias.detach()) if bias is not None else None
+    C.check(_lib.hesic_group_norm(C.ref(C.nchw(x)), C.ref(C.nchw(y)), int(groups), C.ptr(w), C.ptr(b), float(eps), int(relu),
+                                  C.stream()))
+    return y
+
+
+def softmax_channels(x):
+    """nn.functional.softmax(x, dim=-3) (mynet6_plus.py:311)."""
+    x = _f32(x)
+    y = torch.empty_like(x)
+    C.check(_lib.hesic_softmax_channels(C.ref(C.nchw(x)), C.ref(C.nchw(y)), C.stream()))
+    return y
+
+
+def dense_warp(h1, cost):
+    """dense_warp.forward (mynet6_plus.py:316-345): sum_d cost[:, d] * (h1 shifted left by d pixels)."""
+    h1, cost = _f32(h1), _f32(cost)
+    out = torch.empty_like(h1)
+    C.check(_lib.hesic_dense_warp(C.ref(C.nchw(h1)), C.ref(C.nchw(cost)), C.ref(C.nchw(out)), C.stream()))
+    return out

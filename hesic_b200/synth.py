@@ -109,6 +109,12 @@ def synth_state_dict(model, seed=0, latent_gain=4.0, synthesis_gain=0.45, image_
             q[:, 0, 1] = med
             q[:, 0, 2] = med + 10.0
             out[name] = torch.from_numpy(q.astype(np.float32))
+        elif leaf == "weight" and len(shape) == 1:
+            # nn.GroupNorm scale (DSIC, ywz/DSIC/mynet6_plus.py:224-290): around its init value 1
+            out[name] = torch.from_numpy((1.0 + g.standard_normal(shape) * 0.1).astype(np.float32))
+        elif leaf == "weight" and len(shape) == 5:
+            # nn.Conv3d of the DSIC cost volumes: kaiming scale
+            out[name] = torch.from_numpy((g.standard_normal(shape) * math.sqrt(2.0 / _fan_in(name, shape, False))).astype(np.float32))
         elif leaf == "weight" and len(shape) == 4:
             std = math.sqrt(2.0 / _fan_in(name, shape, False))
             w = g.standard_normal(shape) * std

@@ -153,6 +153,17 @@ int hesic_mixture_weights(const float *pooled, const float *w1x1, const float *b
 /* nn.UpsamplingBilinear2d(scale_factor=s) (align_corners=True; newnet1.py:524,564). */
 int hesic_upsample_bilinear(const hesic_tensor *x, const hesic_tensor *y, int scale, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Operators of the DSIC variant (ywz/DSIC/mynet6_plus.py), NCHW fp32.
+ * nn.GroupNorm(groups, C, eps, affine) (+ the nn.ReLU that always follows it, mynet6_plus.py:224-238,262-290):
+ * statistics over (C/groups, H, W) per sample; weight/bias: dev fp32 [C] or NULL. */
+int hesic_group_norm(const hesic_tensor *x, const hesic_tensor *y, int groups, const float *weight, const float *bias,
+                     float eps, int relu, void *stream);
+/* nn.functional.softmax(x, dim=-3): over the disparity channels of a cost volume (mynet6_plus.py:311). */
+int hesic_softmax_channels(const hesic_tensor *x, const hesic_tensor *y, void *stream);
+/* dense_warp.forward (mynet6_plus.py:316-345): out[b,c,y,x] = sum_{d, x+d<W} cost[b,d,y,x] * h1[b,c,y,x+d]. */
+int hesic_dense_warp(const hesic_tensor *h1, const hesic_tensor *cost, const hesic_tensor *out, void *stream);
+
 /* Layout / format conversion with an optional pointwise op: 0 copy, 1 abs (newnet1.py:435),
  * 2 round-half-even (EntropyModel._quantize 'dequantize', entropy_models.py:98-125). */
 enum { HESIC_OP_COPY = 0, HESIC_OP_ABS = 1, HESIC_OP_ROUND = 2 };

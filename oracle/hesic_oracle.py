@@ -420,3 +420,99 @@ def eb_update_pmf(mats, bias, fac, quantiles):
     pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
     tail = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
     return pmf, tail, pmf_length, offset
+
+
+# ----------------------------------------------------------------------------
+# DSIC (ywz/DSIC/mynet6_plus.py) -- BASELINE config 5, SURVEY.md 8a row 15
+def _gn_relu(sd, p, x, groups):
+    """nn.GroupNorm(groups, C) followed by nn.ReLU (mynet6_plus.py:224-238,262-290)."""
+    return F.relu(F.group_norm(x, groups, sd[p + ".weight"], sd[p + ".bias"], 1e-5))
+
+
+# mynet6_plus.py:520-530, 543-553 (the DSIC file's Encoder1/Decoder1 also return the GDN outputs)
+def dsic_encoder1(sd, x, p="encoder1"):
+    g1 = _gdn(sd, p + ".g_a_gdn1", conv(x, *_cw(sd, p + ".g_a_conv1")))
+    g2 = _gdn(sd, p + ".g_a_gdn2", conv(g1, *_cw(sd, p + ".g_a_conv2")))
+    g3 = _gdn(sd, p + ".g_a_gdn3", conv(g2, *_cw(sd, p + ".g_a_conv3")))
+    return conv(g3, *_cw(sd, p + ".g_a_conv4")), g1, g2, g3
+
+
+def dsic_decoder1(sd, y_hat, p="decoder1"):
+    g1 = _gdn(sd, p + ".g_s_gdn1", deconv(y_hat, *_cw(sd, p + ".g_s_conv1")), True)
+    g2 = _gdn(sd, p + ".g_s_gdn2", deconv(g1, *_cw(sd, p + ".g_s_conv2")), True)
+    g3 = _gdn(sd, p + ".g_s_gdn3", deconv(g2, *_cw(sd, p + ".g_s_conv3")), True)
+    return deconv(g3, *_cw(sd, p + ".g_s_conv4")), g1, g2, g3
+
+
+# mynet6_plus.py:216-246
+def dsic_global_context(sd, y1, Fn, Cn, p="_global_context.global_net"):
+    t = y1
+    for i, gn in ((0, 1), (3, 4), (6, 7)):
+        t = _gn_relu(sd, f"{p}.{gn}", conv(t, *_cw(sd, f"{p}.{i}"), stride=1), Fn)
+    t = conv(t, *_cw(sd, f"{p}.9"), stride=1)
+    return torch.reshape(t, (-1, 3, Fn // 3, Cn, t.size(-2), t.size(-1))).split(1, dim=1)
+
+
+# mynet6_plus.py:249-313
+def dsic_cost_volume(sd, p, h1, h2, d, scale, Fn, Cn):
+    F0 = Fn // 3
+    x = torch.cat((h1, h2), dim=1)
+    x = _gn_relu(sd, p + ".model1.1", conv(x, *_cw(sd, p + ".model1.0"), stride=1), 4)
+    h_out = _gn_relu(sd, p + ".model1.4", conv(x, *_cw(sd, p + ".model1.3"), stride=1), 4)
+    d_in = torch.reshape(d, (-1, d.size(-3), d.size(-2), d.size(-1)))
+    d_up = F.interpolate(d_in, scale_factor=scale, mode="bilinear", align_corners=True)   # nn.UpsamplingBilinear2d
+    v = torch.reshape(d_up, (-1, F0, Cn, d_up.size(-2), d_up.size(-1)))
+    for i, gn in ((0, 1), (3, 4)):
+        v = F.conv3d(v, sd[f"{p}.model2.{i}.weight"], sd[f"{p}.model2.{i}.bias"], stride=1, padding=2)
+        v = F.relu(F.group_norm(v, 1, sd[f"{p}.model2.{gn}.weight"], sd[f"{p}.model2.{gn}.bias"], 1e-5))
+    d_out = torch.reshape(v, (-1, F0 * Cn, v.size(-2), v.size(-1)))
+    x = torch.cat((h_out, d_out), dim=1)
+    x = _gn_relu(sd, p + ".model3.1", conv(x, *_cw(sd, p + ".model3.0"), stride=1), 4)
+    x = _gn_relu(sd, p + ".model3.4", conv(x, *_cw(sd, p + ".model3.3"), stride=1), 4)
+    x = conv(x, *_cw(sd, p + ".model3.6"), stride=1)
+    return F.softmax(x, dim=-3)
+
+
+# mynet6_plus.py:316-345
+def dsic_dense_warp(h1, cost):
+    g2 = torch.zeros_like(h1)
+    W = cost.size(-1)
+    for d in range(cost.size(-3)):
+        g2[:, :, :, 0:W - d] += cost[:, d:d + 1, :, 0:W - d] * h1[:, :, :, d:W]
+    return g2
+
+
+# mynet6_plus.py:675-761
+def dsic_forward(sd, x1, x2, K=5, Fn=21, Cn=32, taps=None):
+    T = taps if taps is not None else {}
+    M = sd["encoder1.g_a_conv4.weight"].shape[0]
+    cat = lambda a, b: torch.cat((a, b), dim=-3)
+    cv = lambda i, h1, h2, d, s: dsic_cost_volume(sd, f"_cost_volume{i}", h1, h2, d, s, Fn, Cn)
+    y1, g1_1, g1_2, g1_3 = dsic_encoder1(sd, x1)
+    z1_hat, z1_lik = entropy_bottleneck(encode_hyper(sd, y1, "_h_a1"), *eb_params(sd, "entropy_bottleneck1"))
+    y1_hat, y1_lik = gmm_conditional(y1, *gmm_hyper_y1(sd, z1_hat, "_h_s1", K, M), K)
+    x1_hat, g1_4, g1_5, g1_6 = dsic_decoder1(sd, y1_hat)
+    ctx = dsic_global_context(sd, y1_hat, Fn, Cn)
+
+    a1 = _gdn(sd, "pic2_g_a_gdn1", conv(x2, *_cw(sd, "pic2_g_a_conv1")))
+    c1 = cv(1, g1_1, a1, ctx[0], 8)
+    w1 = dsic_dense_warp(g1_1, c1)
+    a2 = _gdn(sd, "pic2_g_a_gdn2", conv(cat(w1, a1), *_cw(sd, "pic2_g_a_conv2")))
+    w2 = dsic_dense_warp(g1_2, cv(2, g1_2, a2, ctx[1], 4))
+    a3 = _gdn(sd, "pic2_g_a_gdn3", conv(cat(w2, a2), *_cw(sd, "pic2_g_a_conv3")))
+    w3 = dsic_dense_warp(g1_3, cv(3, g1_3, a3, ctx[2], 2))
+    y2 = conv(cat(w3, a3), *_cw(sd, "pic2_g_a_conv4"))
+
+    z2_hat, z2_lik = entropy_bottleneck(encode_hyper(sd, y2, "_h_a2"), *eb_params(sd, "entropy_bottleneck2"))
+    y2_hat, y2_lik = gmm_conditional(y2, *gmm_hyper_y2(sd, z2_hat, y1_hat, "_h_s2", K, M), K)
+
+    s1 = _gdn(sd, "pic2_g_s_gdn1", deconv(y2_hat, *_cw(sd, "pic2_g_s_conv1")), True)
+    w4 = dsic_dense_warp(g1_4, cv(4, g1_4, s1, ctx[2], 2))
+    s2 = _gdn(sd, "pic2_g_s_gdn2", deconv(cat(w4, s1), *_cw(sd, "pic2_g_s_conv2")), True)
+    w5 = dsic_dense_warp(g1_5, cv(5, g1_5, s2, ctx[1], 4))
+    s3 = _gdn(sd, "pic2_g_s_gdn3", deconv(cat(w5, s2), *_cw(sd, "pic2_g_s_conv3")), True)
+    w6 = dsic_dense_warp(g1_6, cv(6, g1_6, s3, ctx[0], 8))
+    x2_hat = deconv(cat(w6, s3), *_cw(sd, "pic2_g_s_conv4"))
+    T.update(y1=y1, y1_hat=y1_hat, g1_1=g1_1, a1=a1, cost1=c1, warp1=w1, y2=y2, y2_hat=y2_hat, ctx0=ctx[0])
+    return {"x1_hat": x1_hat, "x2_hat": x2_hat,
+            "likelihoods": {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}}

@@ -170,7 +170,38 @@ def operators_golden():
     print("operators.npz", len(A), "arrays")
 
 
+def dsic_golden():
+    """DSIC (ywz/DSIC/mynet6_plus.py), BASELINE config 5: whole forward at 64x256 (the reference's dense_warp needs
+    W/8 >= C = 32 disparities) plus cost volumes the reference keeps as module attributes, and scalar metrics
+    of one 256x256 pair."""
+    m = ref_harness.load("mynet6_plus")
+    net = m.DSIC(128, 192, 21, 32, 5).eval()
+    init_tab = sd_table(net.state_dict())
+    sd = synth.synth_state_dict(net, seed=0)
+    net.load_state_dict(sd)
+    x1, x2, _ = synth.stereo_pairs(1, 64, 256, seed=1234)
+    with torch.no_grad():
+        out = net(x1, x2)
+    arrs = {"x1_hat": npf(out["x1_hat"]), "x2_hat": npf(out["x2_hat"]), "cost1": npf(net._cost_volume1.cost),
+            "cost3": npf(net._cost_volume3.cost)}
+    for k, v in out["likelihoods"].items():
+        arrs["lik_" + k] = npf(v)
+    np.savez_compressed(os.path.join(OUT, "dsic.npz"), **arrs)
+    meta = {"module": "mynet6_plus", "B": 1, "H": 64, "W": 256, "metrics": synth.rd_metrics(out, x1, x2),
+            "state_dict_init": init_tab}
+    x1, x2, _ = synth.stereo_pairs(1, 256, 256, seed=1234)
+    with torch.no_grad():
+        out = net(x1, x2)
+    meta["metrics_256"] = synth.rd_metrics(out, x1, x2)
+    meta["sums_256"] = {"x1_hat": float(out["x1_hat"].double().sum()), "x2_hat": float(out["x2_hat"].double().sum())}
+    json.dump(meta, open(os.path.join(OUT, "dsic.json"), "w"), indent=1, sort_keys=True)
+    print("dsic", meta["metrics"], meta["metrics_256"])
+
+
 if __name__ == "__main__":
+    if "--dsic-only" in sys.argv:
+        dsic_golden()
+        sys.exit(0)
     operators_golden()
     model_golden("newnet1", lambda m: m.HSIC(128, 192, 5), "hsic_newnet1", 2, 128, 128)
     model_golden("newnet9", lambda m: m.HSIC(128, 192, 5), "hsic_newnet9", 2, 128, 128, with_yhat=False)
@@ -186,4 +217,5 @@ if __name__ == "__main__":
         o = en(x1, x2, h)
     np.savez_compressed(os.path.join(OUT, "independent_en.npz"), x1_hat=npf(o["x1_hat"]), x2_hat=npf(o["x2_hat"]))
     json.dump({"state_dict_init": tab}, open(os.path.join(OUT, "independent_en.json"), "w"), indent=1, sort_keys=True)
+    dsic_golden()
     print("done")

@@ -73,6 +73,19 @@ def test_independent_en_state_dict():
     assert all(list(sd[k].shape) == gold[k]["shape"] for k in gold)
 
 
+def test_dsic_state_dict_matches_reference():
+    """mynet6_plus.DSIC (BASELINE config 5): same keys, shapes and dtypes as the reference's module."""
+    import mynet6_plus
+    sd = mynet6_plus.DSIC(128, 192, 21, 32, 5).state_dict()
+    gold = load_json("dsic")["state_dict_init"]
+    assert set(sd) == set(gold)
+    for k, g in gold.items():
+        assert list(sd[k].shape) == g["shape"], k
+        assert str(sd[k].dtype).replace("torch.", "") == g["dtype"], k
+    for n in ("DSIC", "DSIC_plus", "Independent_EN", "cost_volume", "dense_warp", "global_context", "GDN", "conv", "deconv"):
+        assert hasattr(mynet6_plus, n), n
+
+
 def test_star_import_surface():
     import newnet1
     for n in ("torch", "nn", "kornia", "math", "os", "np", "time", "RateDistortionLoss", "AverageMeter", "HSIC",

@@ -1,0 +1,112 @@
+"""DSIC (ywz/DSIC/mynet6_plus.py, BASELINE config 5 / SURVEY 8a row 15) on the B200: the three DSIC-only kernels
+and the Conv3d-as-banded-conv2d against the oracle, then the whole forward against the oracle and the fixture the
+unmodified reference produced."""
+import numpy as np
+import pytest
+import torch
+
+from hesic_b200 import compat, synth
+from oracle import hesic_oracle as O
+from tests.helpers import T, assert_close, load_json, load_npz, mismatch_fraction
+
+compat.install()
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.from_numpy((np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32))
+
+
+@pytest.mark.parametrize("shape,groups", [((2, 128, 16, 24), 4), ((1, 672, 4, 16), 21), ((3, 224, 8, 8), 1), ((2, 12, 5, 7), 3)])
+def test_group_norm_relu(shape, groups):
+    from hesic_b200 import functional as F
+    x = _rand(shape, 1, 2.0) + 0.3
+    w, b = 1 + _rand((shape[1],), 2, 0.1), _rand((shape[1],), 3, 0.1)
+    ref = torch.nn.functional.group_norm(x, groups, w, b, 1e-5)
+    assert_close(F.group_norm(x.to(DEV), groups, w.to(DEV), b.to(DEV)), ref, 1e-5, what="group_norm")
+    assert_close(F.group_norm(x.to(DEV), groups, w.to(DEV), b.to(DEV), relu=True), torch.relu(ref), 1e-5, what="group_norm+relu")
+    assert_close(F.group_norm(x.to(DEV), groups), torch.nn.functional.group_norm(x, groups), 1e-5, what="group_norm no affine")
+
+
+def test_softmax_channels_and_dense_warp():
+    from hesic_b200 import functional as F
+    x = _rand((2, 32, 9, 40), 4, 3.0)
+    ref = torch.softmax(x, dim=-3)
+    got = F.softmax_channels(x.to(DEV))
+    assert_close(got, ref, 1e-5, floor=1e-6, what="softmax over channels")
+    assert float((got.sum(1) - 1).abs().max()) < 1e-5
+    for (B, C, H, W, D) in ((2, 128, 8, 64, 32), (1, 5, 3, 40, 32), (1, 33, 2, 100, 7), (1, 4, 2, 16, 32)):
+        h1 = _rand((B, C, H, W), 5)
+        cost = torch.softmax(_rand((B, D, H, W), 6, 2.0), dim=1)
+        if W >= D:
+            ref = O.dsic_dense_warp(h1, cost)
+        else:   # the reference's slicing breaks for W < D (mynet6_plus.py:342); the definition does not
+            ref = torch.zeros_like(h1)
+            for d in range(min(D, W)):
+                ref[..., :W - d] += cost[:, d:d + 1, :, :W - d] * h1[..., d:]
+        assert_close(F.dense_warp(h1.to(DEV), cost.to(DEV)), ref, 1e-5, what=f"dense_warp {B, C, H, W, D}")
+    # one-hot cost = pure shift (size-independent property, full-size row)
+    h1 = _rand((1, 128, 2, 256), 7)
+    cost = torch.zeros(1, 32, 2, 256)
+    cost[:, 5] = 1
+    out = F.dense_warp(h1.to(DEV), cost.to(DEV)).cpu()
+    assert torch.equal(out[..., :251], h1[..., 5:]) and float(out[..., 251:].abs().max()) == 0
+
+
+def test_conv3d_as_banded_conv2d():
+    from hesic_b200.dsic import Conv3dAs2d
+    m = Conv3dAs2d(7, 7, kernel_size=5, stride=1, padding=2)
+    w, b = _rand(tuple(m.weight.shape), 8, (2.0 / 875) ** 0.5), _rand((7,), 9, 0.1)
+    m.load_state_dict({"weight": w, "bias": b})
+    x = _rand((2, 7, 32, 16, 24), 10)
+    ref = torch.nn.functional.conv3d(x, w, b, padding=2)
+    assert_close(m.to(DEV)(x.to(DEV)), ref, 1e-4, what="Conv3d on the tensor-core path")
+
+
+@pytest.fixture(scope="module")
+def dsic():
+    import mynet6_plus
+    net = mynet6_plus.DSIC(128, 192, 21, 32, 5).eval()
+    sd = synth.synth_state_dict(net, seed=0)
+    net.load_state_dict(sd)
+    return net.to(DEV), sd
+
+
+def test_cost_volume_vs_oracle(dsic):
+    """One cost volume (2 convs + GN, upsample x8, 2 Conv3d + GN, 3 convs, softmax) fed the oracle's inputs."""
+    net, sd = dsic
+    x1, x2, _ = synth.stereo_pairs(1, 64, 256, seed=1234)
+    taps = {}
+    with torch.no_grad():
+        O.dsic_forward(sd, x1, x2, taps=taps)
+    got = net._cost_volume1(taps["g1_1"].to(DEV), taps["a1"].to(DEV), taps["ctx0"].to(DEV))
+    assert_close(got, taps["cost1"], 2e-3, floor=float(taps["cost1"].max()) * 0.05, what="cost volume (softmax output)")
+    w = net._warp1(taps["g1_1"].to(DEV), taps["cost1"].to(DEV))
+    assert_close(w, taps["warp1"], 1e-5, what="dense warp on the oracle's cost")
+
+
+def test_dsic_forward_vs_oracle_and_reference_fixture(dsic):
+    from hesic_b200 import _capi as C
+    net, sd = dsic
+    g, meta = load_npz("dsic"), load_json("dsic")
+    x1, x2, _ = synth.stereo_pairs(1, meta["H"], meta["W"], seed=1234)
+    with torch.no_grad():
+        ref = O.dsic_forward(sd, x1, x2)
+    out = net(x1.to(DEV), x2.to(DEV))
+    C.check(C.lib.hesic_tc_status())
+    cpu = {"x1_hat": out["x1_hat"].cpu(), "x2_hat": out["x2_hat"].cpu(),
+           "likelihoods": {k: v.cpu() for k, v in out["likelihoods"].items()}}
+    # symbols may flip at exact x.5 ties (fp32 summation order), so images are compared in the L2 sense
+    for k in ("x1_hat", "x2_hat"):
+        a, b = cpu[k].double(), T(g[k]).double()
+        rel = float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt())
+        assert rel < 5e-3, (k, rel)
+    assert mismatch_fraction(cpu["likelihoods"]["y1"] > 0.5, T(g["lik_y1"]) > 0.5) < 2e-3
+    assert_close(cpu["likelihoods"]["z1"], g["lik_z1"], 1e-3, floor=1e-9)
+    m, r = synth.rd_metrics(cpu, x1, x2), synth.rd_metrics(ref, x1, x2)
+    for k in ("bpp", "bpp1", "bpp2"):
+        assert abs(m[k] - r[k]) <= 5e-3 * r[k], (k, m[k], r[k])
+        assert abs(m[k] - meta["metrics"][k]) <= 5e-3 * meta["metrics"][k], (k, m[k], meta["metrics"][k])
+    for k in ("psnr1", "psnr2"):
+        assert abs(m[k] - r[k]) <= 0.05, (k, m[k], r[k])

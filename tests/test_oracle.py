@@ -155,3 +155,45 @@ def test_full_forward_vs_reference(name):
     m = synth.rd_metrics(out, x1, x2)
     for k, v in meta["metrics"].items():
         assert math.isclose(m[k], v, rel_tol=2e-3, abs_tol=2e-3), (k, m[k], v)
+
+
+def test_dsic_forward_matches_reference_fixture():
+    """Oracle restatement of DSIC.forward (ywz/DSIC/mynet6_plus.py:675-761) vs the unmodified reference at
+    64x256, including two of the cost volumes the reference keeps as module attributes."""
+    import mynet6_plus
+    g, meta = load_npz("dsic"), load_json("dsic")
+    net = mynet6_plus.DSIC(128, 192, 21, 32, 5)
+    sd = synth.synth_state_dict(net, seed=0)
+    x1, x2, _ = synth.stereo_pairs(1, meta["H"], meta["W"], seed=1234)
+    taps = {}
+    with torch.no_grad():
+        out = O.dsic_forward(sd, x1, x2, taps=taps)
+    assert_close(taps["cost1"], g["cost1"], 1e-4, floor=1e-6, what="cost volume 1")
+    assert_close(out["x1_hat"], g["x1_hat"], 1e-5, what="x1_hat")
+    assert_close(out["x2_hat"], g["x2_hat"], 1e-4, what="x2_hat")
+    for k in ("y1", "z1", "z2"):
+        assert_close(out["likelihoods"][k], g["lik_" + k], 1e-4, floor=1e-9, what="likelihood " + k)
+    assert mismatch_fraction(out["likelihoods"]["y2"] > 0.5, T(g["lik_y2"]) > 0.5) < 1e-3
+    m = synth.rd_metrics(out, x1, x2)
+    for k, v in meta["metrics"].items():
+        assert abs(m[k] - v) <= 2e-4 * abs(v), (k, m[k], v)
+
+
+def test_dsic_dense_warp_and_conv3d_identities():
+    """dense_warp with a one-hot cost volume is a pure shift; a Conv3d equals the block-banded 2-D convolution
+    the CUDA path evaluates (hesic_b200/dsic.py: Conv3dAs2d)."""
+    h1 = torch.randn(2, 5, 4, 40)
+    cost = torch.zeros(2, 32, 4, 40)
+    cost[:, 3] = 1.0
+    out = O.dsic_dense_warp(h1, cost)
+    assert torch.equal(out[..., :37], h1[..., 3:]) and float(out[..., 37:].abs().max()) == 0
+    w3, b3 = torch.randn(7, 7, 5, 5, 5) * 0.05, torch.randn(7) * 0.1
+    x = torch.randn(1, 7, 8, 6, 9)
+    ref = torch.nn.functional.conv3d(x, w3, b3, padding=2)
+    D = 8
+    w2 = torch.zeros(7, D, 7, D, 5, 5)
+    for dd in range(D):
+        lo, hi = max(0, dd - 2), min(D, dd + 3)
+        w2[:, dd, :, lo:hi] = w3[:, :, lo - dd + 2:hi - dd + 2]
+    y2 = torch.nn.functional.conv2d(x.reshape(1, 7 * D, 6, 9), w2.reshape(7 * D, 7 * D, 5, 5), b3.repeat_interleave(D), padding=2)
+    assert_close(y2.reshape(ref.shape), ref, 1e-5, what="conv3d as banded conv2d")
