@@ -14,7 +14,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libhesic_b200.so")
 
-FMT_NCHW, FMT_NHWC, FMT_SPLIT, FMT_ROWPAD = 0, 1, 2, 3
+FMT_NCHW, FMT_NHWC, FMT_SPLIT, FMT_ROWPAD, FMT_HILO = 0, 1, 2, 3, 4
 ROWPAD_Y, ROWPAD_X = 4, 8
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
@@ -53,6 +53,11 @@ _sig = {
     "hesic_conv_set_gdn": ([c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p], c_int),
     "hesic_conv_forward": ([c_void_p, _TP, _TP, c_int, c_int, c_void_p], c_int),
     "hesic_conv_forward_cat": ([c_void_p, _TP, _TP, _TP, c_int, c_int, c_void_p], c_int),
+    "hesic_en_conv_create": ([c_int, c_int], c_void_p),
+    "hesic_en_conv_destroy": ([c_void_p], None),
+    "hesic_en_conv_load": ([c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "hesic_en_conv_forward": ([c_void_p, _TP, _TP, c_int, _TP, _TP, c_void_p], c_int),
+    "hesic_en_pack_input": ([_TP, _TP, _TP, c_void_p], c_int),
     "hesic_tc_status": ([], c_int),
     "hesic_gdn": ([_TP, _TP, c_void_p, c_void_p, c_int, c_float, c_void_p], c_int),
     "hesic_warp_perspective": ([_TP, c_void_p, _TP, _TP, c_int, c_void_p], c_int),
@@ -153,6 +158,14 @@ def rowpad(t, C=None, c0=0):
     C = S - c0 if C is None else C
     plane = B * Hp * Wp * S * 2
     return CTensor(t.data_ptr() + 2 * c0, t.data_ptr() + plane + 2 * c0, FMT_ROWPAD, B, C, Hp - ROWPAD_Y, Wp - ROWPAD_X, S)
+
+
+def hilo(t, C=None):
+    """Descriptor for a [B,H,W,2*S] bf16 torch tensor in NHWC_HILO format (per pixel S 'hi' then S 'lo' values):
+    the activation format of the enhancement network (S = 32)."""
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.dim() == 4 and t.shape[-1] % 2 == 0
+    B, H, W, S2 = t.shape
+    return CTensor(t.data_ptr(), None, FMT_HILO, B, S2 // 2 if C is None else C, H, W, S2 // 2)
 
 
 def rowpad_slots(Cin, stride, transposed):

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libhesic_b200.so")
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_small.cu", "elementwise.cu", "dsic_ops.cu", "coder.cpp"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_small.cu", "enhance.cu", "elementwise.cu", "dsic_ops.cu", "coder.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-fvisibility=default", "--expt-relaxed-constexpr"]
 

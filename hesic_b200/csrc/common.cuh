@@ -70,7 +70,7 @@ inline bool same_shape(const hesic_tensor *a, const hesic_tensor *b) {
 
 inline int check_tensor(const hesic_tensor *t, const char *name, bool allow_null_data = false) {
   HESIC_REQUIRE(t != nullptr, "%s: null tensor descriptor", name);
-  HESIC_REQUIRE(t->fmt >= 0 && t->fmt <= 3, "%s: bad format %d", name, t->fmt);
+  HESIC_REQUIRE(t->fmt >= 0 && t->fmt <= 4, "%s: bad format %d", name, t->fmt);
   HESIC_REQUIRE(t->B >= 0 && t->C >= 0 && t->H >= 0 && t->W >= 0, "%s: negative size", name);
   HESIC_REQUIRE(t->Cs == 0 || t->Cs >= t->C, "%s: Cs < C", name);
   if (!allow_null_data && (int64_t)t->B * t->C * t->H * t->W > 0) {
@@ -95,11 +95,14 @@ __device__ __forceinline__ size_t rowpad_off(const TView &t, int b, int y, int x
 __device__ __forceinline__ size_t toff(const TView &t, int b, int c, int y, int x) {
   if (t.fmt == HESIC_FMT_NCHW_F32) return (((size_t)b * t.Cs + c) * t.H + y) * t.W + x;
   if (t.fmt == HESIC_FMT_ROWPAD8_SPLIT) return rowpad_off(t, b, y, x) + c;
+  if (t.fmt == HESIC_FMT_NHWC_HILO) return (((size_t)b * t.H + y) * t.W + x) * 2 * t.Cs + c;   // hi; lo is Cs further
   return (((size_t)b * t.H + y) * t.W + x) * t.Cs + c;
 }
 
 __device__ __forceinline__ float tload(const TView &t, int b, int c, int y, int x) {
   size_t o = toff(t, b, c, y, x);
+  if (t.fmt == HESIC_FMT_NHWC_HILO)
+    return __bfloat162float(((const __nv_bfloat16 *)t.p0)[o]) + __bfloat162float(((const __nv_bfloat16 *)t.p0)[o + t.Cs]);
   if (t.fmt >= HESIC_FMT_NHWC_SPLIT) {
     return __bfloat162float(((const __nv_bfloat16 *)t.p0)[o]) + __bfloat162float(((const __nv_bfloat16 *)t.p1)[o]);
   }
@@ -118,7 +121,8 @@ __device__ __forceinline__ void tstore(const TView &t, int b, int c, int y, int 
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
     ((__nv_bfloat16 *)t.p0)[o] = hi;
-    ((__nv_bfloat16 *)t.p1)[o] = lo;
+    if (t.fmt == HESIC_FMT_NHWC_HILO) ((__nv_bfloat16 *)t.p0)[o + t.Cs] = lo;
+    else ((__nv_bfloat16 *)t.p1)[o] = lo;
   } else {
     ((float *)t.p0)[o] = v;
   }

@@ -37,7 +37,12 @@ enum {
 /* Activation layouts in HBM.  SPLIT is the native inter-layer format of the conv stack:
  * two bf16 planes (hi, lo) with value = float(hi) + float(lo), i.e. a 16-bit-mantissa
  * decomposition of the fp32 value that feeds the bf16x3 tcgen05 path without conversion. */
-enum { HESIC_FMT_NCHW_F32 = 0, HESIC_FMT_NHWC_F32 = 1, HESIC_FMT_NHWC_SPLIT = 2, HESIC_FMT_ROWPAD8_SPLIT = 3 };
+enum { HESIC_FMT_NCHW_F32 = 0, HESIC_FMT_NHWC_F32 = 1, HESIC_FMT_NHWC_SPLIT = 2, HESIC_FMT_ROWPAD8_SPLIT = 3,
+       HESIC_FMT_NHWC_HILO = 4 };
+/* NHWC_HILO is the activation format of the enhancement network (32 channels at full resolution): ONE
+ * bf16 buffer [B][H][W][2*Cs] holding, per pixel, the Cs 'hi' values followed by the Cs 'lo' values
+ * (Cs = 32: 128 bytes per pixel = one 128B-swizzled shared-memory row, so a TMA box of pixels is directly
+ * the K-major A operand [hi | lo] of the bf16x3 contraction).  p1 is unused. */
 /* ROWPAD8_SPLIT is the input format of the full-resolution edge layers (Cin <= 8: the RGB images and
  * the 6-channel concatenations of newnet1.py:643,686): bf16 (hi, lo) planes of
  * [B][H + HESIC_ROWPAD_Y][W + HESIC_ROWPAD_X][8] (Cs = 8 channel slots), image at row/column offset 2, border
@@ -95,6 +100,24 @@ int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor 
  * full-resolution few-channel k5 s1 layers only (else HESIC_E_UNSUPPORTED). */
 int hesic_conv_forward_cat(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y,
                            int act, int path, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Enhancement network layers (Independent_EN, ywz/mywork/newnet1.py:272-311,1278-1300; ResidualBlock,
+ * compressai/layers/layers.py:125-147): conv3x3 (stride 1, padding 1) with Cin <= 32 at full resolution.
+ *   Cout == 32: y is NHWC_HILO;  y = act(conv(x) + bias) [+ res1] [+ res2]   (res*: NHWC_HILO, may be NULL) --
+ *               the LeakyReLU and the identity additions of ResidualBlock / Enhancement_Block in the epilogue;
+ *   Cout <= 4:  y is NCHW fp32;  y = conv(x) + bias [+ res1]   (res1: NCHW fp32 -- Enhancement.forward's
+ *               `self.conv2(out) + identity`, newnet1.py:309-310).
+ * x is NHWC_HILO with Cs == 32 (channel slots >= Cin must hold zeros).  weight: dev fp32 [Cout,Cin,3,3]. */
+typedef struct hesic_en_conv hesic_en_conv;
+hesic_en_conv *hesic_en_conv_create(int Cin, int Cout);
+void hesic_en_conv_destroy(hesic_en_conv *c);
+int hesic_en_conv_load(hesic_en_conv *c, const float *weight, const float *bias, void *stream);
+int hesic_en_conv_forward(hesic_en_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act,
+                          const hesic_tensor *res1, const hesic_tensor *res2, void *stream);
+/* torch.cat((xa, xb), dim=-3) (newnet1.py:302; xb may be NULL) written as NHWC_HILO with 32 channel slots,
+ * zeros above xa->C + xb->C: the input of Enhancement.conv1. */
+int hesic_en_pack_input(const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y, void *stream);
 
 /* Watchdog of the tcgen05 path: every in-kernel barrier wait is time-bounded, so a protocol error
  * cannot hang the GPU.  Returns 0 when no wait has timed out since the last call, else HESIC_E_CUDA

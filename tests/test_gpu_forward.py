@@ -109,3 +109,22 @@ def test_independent_en_vs_reference_fixture():
     out = en.to(DEV)(x1.to(DEV), x2.to(DEV), h.to(DEV))
     assert_close(out["x1_hat"], gold["x1_hat"], 1e-4, what="EN x1")
     assert_close(out["x2_hat"], gold["x2_hat"], 1e-4, what="EN x2")
+
+
+def test_independent_en_full_size_vs_oracle():
+    """512x512 (the BASELINE size), batch 2: the fused enhancement engine against the live oracle."""
+    import newnet1
+    en = newnet1.Independent_EN().eval()
+    sd = synth.synth_state_dict(en, seed=0)
+    en.load_state_dict(sd)
+    x1, x2, h = synth.stereo_pairs(2, 512, 512, seed=77)
+    with torch.no_grad():
+        ref = O.independent_en_forward(sd, x1, x2, h)
+    out = en.to(DEV)(x1.to(DEV), x2.to(DEV), h.to(DEV))
+    from hesic_b200 import _capi as C
+    C.check(C.lib.hesic_tc_status())
+    assert_close(out["x1_hat"], ref["x1_hat"], 1e-4, what="EN x1 512")
+    assert_close(out["x2_hat"], ref["x2_hat"], 1e-4, what="EN x2 512")
+    # pairs are independent
+    one = en(x1[1:].to(DEV), x2[1:].to(DEV), h[1:].to(DEV))
+    assert torch.equal(one["x1_hat"], out["x1_hat"][1:])

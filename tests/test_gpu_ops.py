@@ -362,3 +362,89 @@ def test_operator_modules_match_oracle_submodules():
     assert_close(net.decoder2(yh.to(DEV), x1.to(DEV)), x2h_ref, 1e-4, what="Decoder2")
     y2_ref = O.encoder2(sd, x1, x2)
     assert_close(net.encoder2(x1.to(DEV), x2.to(DEV)), y2_ref, 1e-4, what="Encoder2")
+
+
+def _to_hilo(x):
+    """NCHW fp32 (C <= 32) -> NHWC_HILO bf16 [B,H,W,64] through the library's own converter."""
+    from hesic_b200 import _capi as C
+    B, Cn, H, W = x.shape
+    t = torch.zeros((B, H, W, 64), device=DEV, dtype=torch.bfloat16)
+    xd = x.to(DEV).contiguous()
+    C.check(C.lib.hesic_convert(C.ref(C.nchw(xd)), C.ref(C.hilo(t, Cn)), C.OP_COPY, C.stream()))
+    torch.cuda.synchronize()
+    return t
+
+
+def _from_hilo(t):
+    return (t[..., :32].float() + t[..., 32:].float()).permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("size", [(1, 8, 16), (2, 24, 40), (1, 70, 67), (2, 64, 64)])
+@pytest.mark.parametrize("mode", ["plain", "lrelu", "lrelu_res1", "lrelu_res2"])
+def test_enhancement_conv_parity(size, mode):
+    """conv3x3 32 -> 32 on NHWC_HILO activations with the fused LeakyReLU / identity additions of ResidualBlock and
+    Enhancement_Block (compressai/layers/layers.py:125-147, newnet1.py:272-287), ragged tiles included."""
+    from hesic_b200 import _capi as C
+    from hesic_b200.enhance import EnConvPlan
+    B, H, W = size
+    w = _rand((32, 32, 3, 3), 21, (2.0 / (32 * 9)) ** 0.5)
+    b = _rand((32,), 22, 0.1)
+    x, r1, r2 = _rand((B, 32, H, W), 23), _rand((B, 32, H, W), 24), _rand((B, 32, H, W), 25)
+    xh, r1h, r2h = _to_hilo(x), _to_hilo(r1), _to_hilo(r2)
+    # the oracle sees exactly the values the device tensors hold (hi + lo = 16-bit-mantissa roundings of the inputs)
+    xq, r1q, r2q = _from_hilo(xh).cpu(), _from_hilo(r1h).cpu(), _from_hilo(r2h).cpu()
+    ref = O.conv(xq, w, b, stride=1)
+    if mode != "plain":
+        ref = torch.nn.functional.leaky_relu(ref)
+    if mode in ("lrelu_res1", "lrelu_res2"):
+        ref = ref + r1q
+    if mode == "lrelu_res2":
+        ref = ref + r2q
+    plan = EnConvPlan(32, 32).load(w.to(DEV), b.to(DEV))
+    y = torch.full((B, H, W, 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    plan.run(C.hilo(xh), C.hilo(y), C.ACT_NONE if mode == "plain" else C.ACT_LEAKY,
+             C.hilo(r1h) if mode in ("lrelu_res1", "lrelu_res2") else None, C.hilo(r2h) if mode == "lrelu_res2" else None)
+    C.check(C.lib.hesic_tc_status())
+    assert_close(_from_hilo(y), ref, 1e-4, what=f"enhancement conv {size} {mode}")
+
+
+@pytest.mark.parametrize("size", [(1, 8, 16), (2, 40, 24), (1, 70, 67)])
+def test_enhancement_first_and_last_layer(size):
+    """Enhancement.conv1 on cat(x, x_other_warp) (6 -> 32, newnet1.py:302-304) and conv2 + identity (32 -> 3, :309-310)."""
+    from hesic_b200 import _capi as C
+    from hesic_b200.enhance import EnConvPlan
+    B, H, W = size
+    xa, xb = _rand((B, 3, H, W), 31), _rand((B, 3, H, W), 32)
+    w1, b1 = _rand((32, 6, 3, 3), 33, 0.2), _rand((32,), 34, 0.1)
+    t = torch.full((B, H, W, 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    xa_d, xb_d = xa.to(DEV), xb.to(DEV)
+    C.check(C.lib.hesic_en_pack_input(C.ref(C.nchw(xa_d)), C.ref(C.nchw(xb_d)), C.ref(C.hilo(t)), C.stream()))
+    packed = _from_hilo(t).cpu()
+    assert_close(packed[:, :6], torch.cat((xa, xb), 1), 2e-5, what="en pack")
+    assert float(packed[:, 6:].abs().max()) == 0
+    y = torch.empty((B, H, W, 64), device=DEV, dtype=torch.bfloat16)
+    EnConvPlan(6, 32).load(w1.to(DEV), b1.to(DEV)).run(C.hilo(t), C.hilo(y))
+    assert_close(_from_hilo(y), O.conv(packed[:, :6], w1, b1, stride=1), 1e-4, what="en conv1")
+    w2, b2 = _rand((3, 32, 3, 3), 35, 0.1), _rand((3,), 36, 0.1)
+    feat = _rand((B, 32, H, W), 37)
+    fh = _to_hilo(feat)
+    out = torch.full((B, 3, H, W), float("nan"), device=DEV)
+    ident = xa.to(DEV)
+    EnConvPlan(32, 3).load(w2.to(DEV), b2.to(DEV)).run(C.hilo(fh), C.nchw(out), C.ACT_NONE, C.nchw(ident))
+    C.check(C.lib.hesic_tc_status())
+    assert_close(out, O.conv(_from_hilo(fh).cpu(), w2, b2, stride=1) + xa, 1e-4, what="en conv2 + identity")
+
+
+def test_enhancement_conv_rejects_bad_arguments():
+    from hesic_b200 import _capi as C
+    from hesic_b200.enhance import EnConvPlan
+    with pytest.raises(ValueError):
+        EnConvPlan(64, 32)
+    with pytest.raises(ValueError):
+        EnConvPlan(32, 16)
+    plan = EnConvPlan(32, 32).load(torch.zeros(32, 32, 3, 3, device=DEV))
+    x = torch.zeros((1, 8, 16, 64), device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        plan.run(C.hilo(x), C.hilo(torch.zeros((1, 8, 8, 64), device=DEV, dtype=torch.bfloat16)))
+    with pytest.raises(ValueError):
+        plan.run(C.hilo(x), C.nchw(torch.zeros((1, 32, 8, 16), device=DEV)))
