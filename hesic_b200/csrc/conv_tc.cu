@@ -84,6 +84,7 @@ struct Params {
   int tma_store;           // 1: epilogue stages 128-byte-wide tiles in smem and writes them with TMA
   int w_resident;          // all weight tiles ([tap][kchunk][hi, lo]) are loaded once and stay in smem
   int n_wtiles;            // taps * kchunks (w_resident)
+  int wide_n;              // BN == 128: issue Ah.[Wh; Wl] as one N = 256 MMA
   int stages;
   uint32_t stage_bytes, b_bytes;
   int n_tasks;
@@ -264,19 +265,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             mbar_wait(full_bar(stage), phase, 3);
             tc_fence_after();
-            const uint32_t idesc = instr_desc(min(p.BN, p.CoutPad16 - tk.nt * p.BN));
+            const int nvalid = min(p.BN, p.CoutPad16 - tk.nt * p.BN);
+            const uint32_t idesc = instr_desc(nvalid);
             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
             const uint64_t a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_TILE_BYTES);
             const uint32_t sb = p.w_resident ? w_base + (uint32_t)(2 * (t * p.kchunks + kc)) * p.b_bytes : sa + 2 * A_TILE_BYTES;
             const uint64_t b_hi = smem_desc(sb), b_lo = smem_desc(sb + p.b_bytes);
             const uint32_t d_main = tmem_base + (uint32_t)buf * ACC_STRIDE, d_small = d_main + COL_SMALL;
+            if (p.wide_n && nvalid == 128) {
+              // Full 128-column tile: the (hi, lo) weight tiles are adjacent in shared memory and {main, small} are
+              // adjacent in TMEM, so Ah.[Wh; Wl] is ONE N = 256 MMA -- Ah is read from shared memory once instead of
+              // twice and the issue count drops from 3 to 2 per K = 16 step (the kernel is bound by the tensor
+              // core's shared-memory operand reads: 24 -> 20 KB per step).
+              const uint32_t idesc256 = instr_desc(256);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t o = (uint64_t)(k * 2);   // 32 B per K=16 step, encoded >> 4
-              const uint32_t acc = (first && k == 0) ? 0u : 1u;
-              mma_ss(d_main, a_hi + o, b_hi + o, idesc, acc);
-              mma_ss(d_small, a_hi + o, b_lo + o, idesc, acc);
-              mma_ss(d_small, a_lo + o, b_hi + o, idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t o = (uint64_t)(k * 2);   // 32 B per K=16 step, encoded >> 4
+                mma_ss(d_main, a_hi + o, b_hi + o, idesc256, (first && k == 0) ? 0u : 1u);
+                mma_ss(d_small, a_lo + o, b_hi + o, idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t o = (uint64_t)(k * 2);   // 32 B per K=16 step, encoded >> 4
+                const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                mma_ss(d_main, a_hi + o, b_hi + o, idesc, acc);
+                mma_ss(d_small, a_hi + o, b_lo + o, idesc, acc);
+                mma_ss(d_small, a_lo + o, b_hi + o, idesc, 1u);
+              }
             }
             tc_commit(empty_bar(stage));
             if (last) tc_commit(acc_full(buf));
@@ -820,6 +836,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.n_wtiles = ntaps * p.kchunks;
   p.w_resident = (c->tc_kind == HESIC_TC_ROW2 && p.n_tiles == 1 && p.b_bytes <= (uint32_t)A_TILE_BYTES) ? 1 : 0;
   if (getenv("HESIC_TC_NO_RESIDENT")) p.w_resident = 0;
+  p.wide_n = (!planar && p.BN == 128 && !getenv("HESIC_TC_NARROW")) ? 1 : 0;
   p.stage_bytes = 2u * A_TILE_BYTES + (p.w_resident ? 0u : 2u * p.b_bytes);
   // TMA-store epilogue: channels-last outputs; for the sub-pixel phases of a transposed conv the phase
   // column is folded into the channel dimension of the output map, which needs whole store tiles.

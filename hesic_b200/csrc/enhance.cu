@@ -10,15 +10,19 @@
 //   * one output tile = 16 x 8 pixels (UMMA M = 128).  The producer loads the tile with a one-row halo THREE times,
 //     shifted by dx = -1, 0, +1 pixels (TMA zero fill = the zero padding): 3 x 20 KB instead of 9 tap loads.  Inside
 //     a copy the three dy taps are plain address offsets of one 16-pixel row (2 KB, swizzle-atom aligned).
-//   * the weights of a tap are ONE resident tile  Bt = [Wl | Wh]  (N rows x 128 B); with fp32 parity as in
+//   * the weights of a tap are ONE resident tile of 2N rows x 128 B:  rows [0, N) = [Wh | 0],  rows [N, 2N) =
+//     [Wl | Wh].  One K = 64 MMA chain (4 MMAs of M 128 x N 2N x K 16) per tap then yields, with fp32 parity as in
 //     conv_tc.cu (bf16x3, main + small accumulators):
-//         small += A[0:64] . Bt[0:64]   = Ah.Wl + Al.Wh      (4 MMAs of K = 16)
-//         main  += A[0:32] . Bt[32:64]  = Ah.Wh              (2 MMAs of K = 16)
-//     54 MMAs (M 128 x N 32 x K 16) per tile; all nine tap tiles (36 KB) stay in shared memory.
+//         D[:, 0:N]  (main)  += [Ah | Al] . [Wh | 0]  = Ah.Wh
+//         D[:, N:2N] (small) += [Ah | Al] . [Wl | Wh] = Ah.Wl + Al.Wh
+//     36 MMAs per tile, every A row read from shared memory once per tap (the kernel is bound by the tensor core's
+//     shared-memory operand reads: r01 profile, 53 % of that pipe with separate main / small chains re-reading A);
+//     all nine tap tiles (72 KB) stay in shared memory.
 //   * warp-specialised persistent CTA: warp 0 TMA producer, warp 1 MMA issuer (4 TMEM accumulator buffers),
-//     warps 2-5 epilogue: bias, LeakyReLU, up to two residuals read straight from HBM (prefetched before the
-//     accumulator is ready), hi/lo split, one swizzled staging tile, one TMA store per tile.
-//   * Cout <= 4 (the RGB output layer): same main loop with N = 16 and a planar NCHW fp32 epilogue that adds the
+//     warps 2-5 and 6-9 two epilogue groups taking alternate tiles: bias, LeakyReLU, up to two residuals read
+//     straight from HBM (L2-prefetched one turn ahead, loaded before the accumulator is waited for), hi/lo split,
+//     one swizzled staging tile per group, one TMA store per tile.
+//   * Cout <= 4 (the RGB output layer): same main loop with N = 16 (2N = 32) and a planar NCHW fp32 epilogue that adds the
 //     NCHW identity image.
 #include <cuda.h>
 #include <string.h>
@@ -29,7 +33,7 @@
 
 struct hesic_en_conv {
   int Cin = 0, Cout = 0, N = 0;
-  __nv_bfloat16 *w = nullptr;   // [9][N][64]: row co of tap t = (lo[ci 0..31] | hi[ci 0..31])
+  __nv_bfloat16 *w = nullptr;   // [9][2N][64]: rows [0,N) = (hi[ci 0..31] | 0), rows [N,2N) = (lo[ci] | hi[ci]) of tap t
   float *bias = nullptr;        // [32]
   bool loaded = false;
   CUtensorMap map_w;
@@ -43,13 +47,13 @@ constexpr int TW = 16, TH = 8, HR = TH + 2;
 constexpr int PIX_BYTES = 128;
 constexpr int ROW_BYTES = TW * PIX_BYTES;           // 2 KB: one tile row = two swizzle atoms
 constexpr int SLOT_BYTES = HR * ROW_BYTES;          // 20 KB: one dx-shifted copy of the tile + halo rows
-constexpr int NSLOTS = 8;
-constexpr int W_BYTES = 9 * 32 * 128;               // resident weights (N = 32)
+constexpr int NSLOTS = 6;
+constexpr int W_BYTES = 9 * 64 * 128;               // resident weights (2N = 64 rows per tap)
 constexpr int STG_BYTES = BM * PIX_BYTES;
-constexpr int NT = 192;
+constexpr int NT = 320;                             // TMA warp + MMA warp + 2 x 4 epilogue warps
 constexpr int NACC = 4;
 constexpr uint32_t TMEM_COLS_EN = 256;              // 4 x {main 32, small 32}
-constexpr int SMEM_BYTES = 1024 + W_BYTES + NSLOTS * SLOT_BYTES + STG_BYTES + 512;
+constexpr int SMEM_BYTES = 1024 + W_BYTES + NSLOTS * SLOT_BYTES + 2 * STG_BYTES + 512;
 
 struct EParams {
   int H, W, B, tiles_x, tiles_y, n_tasks;
@@ -62,7 +66,21 @@ struct EParams {
   int y_Cs;
 };
 
-__device__ __forceinline__ void epi_bar128() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar128(int grp) {
+  if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+  else asm volatile("bar.sync 4, 128;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
@@ -76,27 +94,32 @@ __device__ __forceinline__ void add_chunk(float *v, const uint4 &h, const uint4 
 
 __global__ void __launch_bounds__(NT, 1)
 en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_y, const __grid_constant__ EParams p) {
+               const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r1,
+               const __grid_constant__ CUtensorMap map_r2, const __grid_constant__ EParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t w_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t slot_base = w_base + (uint32_t)W_BYTES;
   const uint32_t stg = slot_base + (uint32_t)(NSLOTS * SLOT_BYTES);
-  const uint32_t bar_base = stg + (uint32_t)STG_BYTES;
+  const uint32_t bar_base = stg + 2u * (uint32_t)STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto acc_full = [&](int b) { return bar_base + 128u + 8u * b; };
   auto acc_empty = [&](int b) { return bar_base + 160u + 8u * b; };
   const uint32_t w_full = bar_base + 192u, tmem_slot = bar_base + 200u;
+  auto res_full_bar = [&](int g) { return bar_base + 208u + 8u * g; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t wt_bytes = (uint32_t)p.N * 128u;      // one tap tile
+  const uint32_t wt_bytes = 2u * (uint32_t)p.N * 128u;      // one tap tile (2N rows)
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&map_x); prefetch_map(&map_w);
     if (!p.planar) prefetch_map(&map_y);
+    if (p.res1) prefetch_map(&map_r1);
+    if (p.res2) prefetch_map(&map_r2);
     for (int s = 0; s < NSLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < NACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
     mbar_init(w_full, 1);
+    mbar_init(res_full_bar(0), 1); mbar_init(res_full_bar(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -115,7 +138,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(w_full, 9u * wt_bytes);
-      for (int t = 0; t < 9; ++t) tma_load_2d(&map_w, w_base + (uint32_t)t * wt_bytes, w_full, 0, t * p.N);
+      for (int t = 0; t < 9; ++t) tma_load_2d(&map_w, w_base + (uint32_t)t * wt_bytes, w_full, 0, t * 2 * p.N);
       int slot = 0;
       uint32_t phase = 0;
       for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x) {
@@ -132,7 +155,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = instr_desc(p.N);
+      const uint32_t idesc = instr_desc(2 * p.N), idesc_n = instr_desc(p.N);
       mbar_wait(w_full, 0, 5);
       tc_fence_after();
       int slot = 0, lt = 0;
@@ -141,7 +164,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int buf = lt & (NACC - 1);
         mbar_wait(acc_empty(buf), (((uint32_t)lt >> 2) & 1u) ^ 1u, 2);
         tc_fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)buf * 64u, d_small = d_main + 32u;
+        const uint32_t d = tmem_base + (uint32_t)buf * 64u;   // columns [0, N) main, [N, 2N) small
         for (int c = 0; c < 3; ++c) {
           mbar_wait(full_bar(slot), phase, 3);
           tc_fence_after();
@@ -151,14 +174,12 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const uint64_t a = smem_desc(sa + (uint32_t)dy * ROW_BYTES);
             const uint64_t b = smem_desc(w_base + (uint32_t)(dy * 3 + c) * wt_bytes);
             const uint32_t first = (c == 0 && dy == 0) ? 0u : 1u;
-            // main: Ah . Wh   (A bytes [0, 64), B bytes [64, 128) of every row)
-            mma_ss(d_main, a, b + 4, idesc, first);
-            mma_ss(d_main, a + 2, b + 6, idesc, 1u);
-            // small: [Ah | Al] . [Wl | Wh]
-            mma_ss(d_small, a, b, idesc, first);
-            mma_ss(d_small, a + 2, b + 2, idesc, 1u);
-            mma_ss(d_small, a + 4, b + 4, idesc, 1u);
-            mma_ss(d_small, a + 6, b + 6, idesc, 1u);
+            // K chunks 0,1 (A = Ah): all 2N rows; chunks 2,3 (A = Al): the main rows are zero there -> small rows only
+            mma_ss(d, a, b, idesc, first);
+            mma_ss(d, a + 2, b + 2, idesc, 1u);
+            const uint64_t bs = smem_desc(w_base + (uint32_t)(dy * 3 + c) * wt_bytes + (uint32_t)p.N * 128u);
+            mma_ss(d + (uint32_t)p.N, a + 4, bs + 4, idesc_n, 1u);
+            mma_ss(d + (uint32_t)p.N, a + 6, bs + 6, idesc_n, 1u);
           }
           tc_commit(empty_bar(slot));
           if (++slot == NSLOTS) { slot = 0; phase ^= 1u; }
@@ -167,18 +188,20 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2-5: TMEM lane quadrant = warp % 4) =====================
-    const int quad = warp & 3;
+    // ===================== epilogue (TMEM lane quadrant = warp % 4; group g = tiles lt % 2 == g) =====================
+    const int quad = warp & 3, grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int xi = row & (TW - 1), yi = row >> 4;
-    const bool is_issuer = threadIdx.x == 64;
-    const uint32_t row_off = stg + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    const bool is_issuer = (threadIdx.x & 127) == 64;
+    const uint32_t my_stg = stg + (uint32_t)grp * STG_BYTES;
+    const uint32_t row_off = my_stg + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    const uint32_t res_full = res_full_bar(grp);
+    uint32_t res_phase = 0;
     float bias[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias[j] = j < p.Cout ? __ldg(p.bias + j) : 0.f;
-    int lt = 0;
-    for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x, ++lt) {
+    for (int lt = grp, task = blockIdx.x + grp * gridDim.x; task < p.n_tasks; task += 2 * gridDim.x, lt += 2) {
       const int buf = lt & (NACC - 1);
       const int tb = task / txy, rr = task - tb * txy;
       const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
@@ -196,7 +219,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         tc_fence_after();
         uint32_t r[16], q[16];
         tmem_ld16(acc, r);
-        tmem_ld16(acc + 32u, q);
+        tmem_ld16(acc + 16u, q);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
@@ -210,19 +233,23 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
         continue;
       }
-      // residual rows (128 B each) requested before the accumulator is waited for
-      uint4 r1[8], r2[8];
-      const size_t pix = (((size_t)tb * p.H + oy) * p.W + ox) * 8;   // in uint4 units
-      const bool has1 = p.res1 != nullptr && valid, has2 = p.res2 != nullptr && valid;
-      if (has1) {
-        const uint4 *s = reinterpret_cast<const uint4 *>(p.res1) + pix;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r1[j] = __ldg(s + j);
-      }
-      if (has2) {
-        const uint4 *s = reinterpret_cast<const uint4 *>(p.res2) + pix;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r2[j] = __ldg(s + j);
+      // Residual tiles land in the group's staging buffer by TMA ([128 px][128 B], swizzled like the output tile):
+      // a thread reads its own row, adds, and later writes its output row to the same place.  (Per-thread 128-byte
+      // global loads cost 32 L1 wavefronts per instruction -- r01 profile: +55 / +230 us per layer for one / two
+      // residuals.)  The next tile's residual tiles are prefetched into L2 meanwhile.
+      const bool has1 = p.res1 != nullptr, has2 = p.res2 != nullptr;
+      if (is_issuer) {
+        bulk_wait_read<0>();   // the group's previous output tile has left the staging buffer
+        if (has1) {
+          mbar_expect_tx(res_full, (uint32_t)STG_BYTES);
+          tma_load_4d(&map_r1, my_stg, res_full, 0, tx * TW, ty * TH, tb);
+          const int nt = task + 2 * (int)gridDim.x;
+          if (nt < p.n_tasks) {
+            const int nb = nt / txy, nr = nt - nb * txy;
+            tma_prefetch_4d(&map_r1, 0, (nr % p.tiles_x) * TW, (nr / p.tiles_x) * TH, nb);
+            if (has2) tma_prefetch_4d(&map_r2, 0, (nr % p.tiles_x) * TW, (nr / p.tiles_x) * TH, nb);
+          }
+        }
       }
       mbar_wait(acc_full(buf), ((uint32_t)lt >> 2) & 1u, 7);
       tc_fence_after();
@@ -242,15 +269,31 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
       }
       if (has1) {
+        mbar_wait(res_full, res_phase, 10);
+        res_phase ^= 1u;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) add_chunk(v + 8 * g, r1[g], r1[g + 4]);
-      }
-      if (has2) {
+        for (int g = 0; g < 4; ++g) {
+          const uint4 h = ld_shared_u4(row_off + (((uint32_t)g ^ sw) << 4)), l = ld_shared_u4(row_off + (((uint32_t)(g + 4) ^ sw) << 4));
+          add_chunk(v + 8 * g, h, l);
+        }
+        if (has2) {
+          fence_async_smem();
+          epi_bar128(grp);   // every row of the first residual tile has been read
+          if (is_issuer) {
+            mbar_expect_tx(res_full, (uint32_t)STG_BYTES);
+            tma_load_4d(&map_r2, my_stg, res_full, 0, tx * TW, ty * TH, tb);
+          }
+          mbar_wait(res_full, res_phase, 11);
+          res_phase ^= 1u;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) add_chunk(v + 8 * g, r2[g], r2[g + 4]);
+          for (int g = 0; g < 4; ++g) {
+            const uint4 h = ld_shared_u4(row_off + (((uint32_t)g ^ sw) << 4)), l = ld_shared_u4(row_off + (((uint32_t)(g + 4) ^ sw) << 4));
+            add_chunk(v + 8 * g, h, l);
+          }
+        }
+      } else {
+        epi_bar128(grp);   // staging buffer free (issuer's bulk_wait_read above)
       }
-      if (is_issuer) bulk_wait_read<0>();   // the previous tile has left the staging buffer
-      epi_bar128();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
@@ -262,9 +305,9 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         st_shared_v4(row_off + (((uint32_t)(g + 4) ^ sw) << 4), l0, l1, l2, l3);
       }
       fence_async_smem();
-      epi_bar128();
+      epi_bar128(grp);
       if (is_issuer) {
-        tma_store_4d(&map_y, stg, 0, tx * TW, ty * TH, tb);
+        tma_store_4d(&map_y, my_stg, 0, tx * TW, ty * TH, tb);
         bulk_commit();
       }
     }
@@ -279,7 +322,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   }
 }
 
-// weight [Cout][Cin][3][3] fp32 -> [9][N][64] bf16, row = (lo[0..31] | hi[0..31]), zero padded
+// weight [Cout][Cin][3][3] fp32 -> [9][2N][64] bf16: rows [0,N) = (hi | 0), rows [N,2N) = (lo | hi), zero padded
 __global__ void en_pack_w_kernel(const float *__restrict__ w, int Cin, int Cout, int N, __nv_bfloat16 *__restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * N * 32) return;
@@ -288,9 +331,11 @@ __global__ void en_pack_w_kernel(const float *__restrict__ w, int Cin, int Cout,
   if (ci < Cin && co < Cout) v = w[((size_t)co * Cin + ci) * 9 + t];
   __nv_bfloat16 hi, lo;
   split_bf16(v, hi, lo);
-  __nv_bfloat16 *o = out + ((size_t)t * N + co) * 64;
-  o[ci] = lo;
-  o[32 + ci] = hi;
+  __nv_bfloat16 *m = out + ((size_t)t * 2 * N + co) * 64, *sm = m + (size_t)N * 64;
+  m[ci] = hi;
+  m[32 + ci] = __float2bfloat16_rn(0.f);
+  sm[ci] = lo;
+  sm[32 + ci] = hi;
 }
 
 // cat(xa, xb) NCHW fp32 -> NHWC_HILO (32 slots): thread = pixel, 128 B written per pixel
@@ -359,10 +404,10 @@ extern "C" int hesic_en_conv_load(hesic_en_conv *c, const float *weight, const f
   HESIC_REQUIRE(c && weight, "hesic_en_conv_load: null argument");
   cudaStream_t s = as_stream(stream);
   if (!c->w) {
-    HESIC_CUDA(cudaMalloc(&c->w, (size_t)9 * c->N * 64 * sizeof(__nv_bfloat16)));
+    HESIC_CUDA(cudaMalloc(&c->w, (size_t)9 * 2 * c->N * 64 * sizeof(__nv_bfloat16)));
     HESIC_CUDA(cudaMalloc(&c->bias, 32 * sizeof(float)));
-    const uint64_t dims[2] = {64, (uint64_t)9 * c->N}, strides[1] = {128};
-    const uint32_t box[2] = {64, (uint32_t)c->N};
+    const uint64_t dims[2] = {64, (uint64_t)9 * 2 * c->N}, strides[1] = {128};
+    const uint32_t box[2] = {64, (uint32_t)(2 * c->N)};
     int r = tc::make_tensor_map(&c->map_w, c->w, 2, dims, strides, box);
     if (r != HESIC_OK) return r;
   }
@@ -442,8 +487,12 @@ extern "C" int hesic_en_conv_forward(hesic_en_conv *c, const hesic_tensor *x, co
   if ((r = tc::make_tensor_map(&mx, x->p0, 4, dims, strides, box_in)) != HESIC_OK) return r;
   if (planar) my = mx;
   else if ((r = tc::make_tensor_map(&my, y->p0, 4, dims, strides, box_out)) != HESIC_OK) return r;
+  CUtensorMap mr1 = mx, mr2 = mx;
+  if (!planar && res1 && (r = tc::make_tensor_map(&mr1, res1->p0, 4, dims, strides, box_out)) != HESIC_OK) return r;
+  if (!planar && res2 && (r = tc::make_tensor_map(&mr2, res2->p0, 4, dims, strides, box_out)) != HESIC_OK) return r;
+  if (!planar && !res1 && res2) { mr1 = mr2; p.res1 = p.res2; p.res2 = nullptr; }
   const int grid = std::min(p.n_tasks, num_sms);
-  en_conv_kernel<<<grid, NT, SMEM_BYTES, as_stream(stream)>>>(mx, c->map_w, my, p);
+  en_conv_kernel<<<grid, NT, SMEM_BYTES, as_stream(stream)>>>(mx, c->map_w, my, mr1, mr2, p);
   HESIC_LAUNCHED("en_conv_kernel");
   return HESIC_OK;
 }
