@@ -403,6 +403,46 @@ def independent_en_forward(sd, x1_hat, x2_hat, h, align_corners=True):
 
 
 # ----------------------------------------------------------------------------
+# Homography front-end (ywz/mywork/model.py:53-111; test3real.py:171-181) -- SURVEY 8f rank 3
+def homography_net_forward(sd, a, b):
+    """Net.forward: four Blocks (conv3x3, ReLU, conv3x3, ReLU, [MaxPool 2x2]) then Flatten, FC 1024, ReLU, FC 8
+    (Dropout is the identity in eval mode) -> delta [B,4,2]."""
+    x = torch.cat((a, b), dim=1)
+    for i in range(4):
+        x = F.relu(F.conv2d(x, *_cw(sd, f"cnn.{i}.layers.0"), padding=1))
+        x = F.relu(F.conv2d(x, *_cw(sd, f"cnn.{i}.layers.2"), padding=1))
+        if i < 3:
+            x = F.max_pool2d(x, 2, 2)
+    x = x.reshape(x.shape[0], -1)
+    x = F.relu(F.linear(x, sd["fc.2.weight"], sd["fc.2.bias"]))
+    return F.linear(x, sd["fc.5.weight"], sd["fc.5.bias"]).view(-1, 4, 2)
+
+
+def get_perspective_transform(src, dst):
+    """kornia.get_perspective_transform (un-vendored; call sites test3real.py:179, model.py:26,108): the homography
+    mapping four points src[B,4,2] onto dst[B,4,2], by the direct linear transform with h33 = 1, in float64."""
+    x, y = src[..., 0].double(), src[..., 1].double()
+    u, v = dst[..., 0].double(), dst[..., 1].double()
+    z, o = torch.zeros_like(x), torch.ones_like(x)
+    A = torch.cat([torch.stack([x, y, o, z, z, z, -x * u, -y * u], -1), torch.stack([z, z, z, x, y, o, -x * v, -y * v], -1)], 1)
+    rhs = torch.cat([u, v], 1).unsqueeze(-1)
+    sol = torch.linalg.solve(A, rhs).squeeze(-1)
+    H = torch.cat([sol, torch.ones(src.shape[0], 1, dtype=sol.dtype)], 1).reshape(-1, 3, 3)
+    return H.to(src.dtype)
+
+
+def h_adjust(orishapea, orishapeb, resizeshapea, resizeshapeb, h):
+    """test3real.py:56-66 (the caller's in-place rescale of H from the 256-pixel frame to the image frame)."""
+    a, b = orishapea / resizeshapea, orishapeb / resizeshapeb
+    h = h.clone()
+    h[:, 0, :] = a * h[:, 0, :]
+    h[:, :, 0] = (1.0 / a) * h[:, :, 0]
+    h[:, 1, :] = b * h[:, 1, :]
+    h[:, :, 1] = (1.0 / b) * h[:, :, 1]
+    return h
+
+
+# ----------------------------------------------------------------------------
 # EntropyBottleneck.update() tables (entropy_models.py:302-343) -- float part; the
 # pmf -> integer CDF step is oracle/coder_oracle.c (ops.cpp:24-81)
 def eb_update_pmf(mats, bias, fac, quantiles):

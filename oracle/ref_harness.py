@@ -82,7 +82,7 @@ def install():
 
 
 def load(module_name):
-    """Import a reference model file (newnet1, newnet1_joint, newnet9, mynet6_plus) and return the module."""
+    """Import a reference model file (newnet1, newnet1_joint, newnet9, mynet6_plus, model) and return the module."""
     install()
     import importlib.util
 
@@ -91,6 +91,7 @@ def load(module_name):
         "newnet1_joint": os.path.join(REF, "ywz/mywork/newnet1_joint.py"),
         "newnet9": os.path.join(REF, "ywz/mywork/.trash/newnet9.py"),
         "mynet6_plus": os.path.join(REF, "ywz/DSIC/mynet6_plus.py"),
+        "model": os.path.join(REF, "ywz/mywork/model.py"),
     }
     spec = importlib.util.spec_from_file_location("_ref_" + module_name, paths[module_name])
     mod = importlib.util.module_from_spec(spec)

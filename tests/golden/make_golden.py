@@ -198,7 +198,25 @@ def dsic_golden():
     print("dsic", meta["metrics"], meta["metrics_256"])
 
 
+def homography_golden():
+    """ywz/mywork/model.py Net (the front-end that produces h_matrix) on two 128x128 gray patches."""
+    m = ref_harness.load("model")
+    net = m.Net(patch_size=128).eval()
+    tab = sd_table(net.state_dict())
+    net.load_state_dict(synth.synth_state_dict(net, seed=0))
+    x1, x2, _ = synth.stereo_pairs(2, 128, 128, seed=55)
+    a, b = x1.mean(1, keepdim=True), x2.mean(1, keepdim=True)
+    with torch.no_grad():
+        delta = net(a, b)
+    np.savez_compressed(os.path.join(OUT, "homography_net.npz"), delta=npf(delta))
+    json.dump({"state_dict_init": tab}, open(os.path.join(OUT, "homography_net.json"), "w"), indent=1, sort_keys=True)
+    print("homography", delta.abs().mean().item())
+
+
 if __name__ == "__main__":
+    if "--homography-only" in sys.argv:
+        homography_golden()
+        sys.exit(0)
     if "--dsic-only" in sys.argv:
         dsic_golden()
         sys.exit(0)
@@ -218,4 +236,5 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(OUT, "independent_en.npz"), x1_hat=npf(o["x1_hat"]), x2_hat=npf(o["x2_hat"]))
     json.dump({"state_dict_init": tab}, open(os.path.join(OUT, "independent_en.json"), "w"), indent=1, sort_keys=True)
     dsic_golden()
+    homography_golden()
     print("done")

@@ -101,6 +101,13 @@ def test_star_import_surface():
     assert set(layer_names) == {"GDN", "GDN1", "AttentionBlock", "MaskedConv2d", "ResidualBlock", "ResidualBlockUpsample",
                                 "ResidualBlockWithStride", "conv3x3", "subpel_conv3x3"}
     from compressai.models import CompressionModel  # noqa: F401
+    # the homography front-end the drivers import next to the codec (test3real.py:42)
+    import model
+    assert model.__file__.startswith(compat.SITE)
+    for n in ("Net", "photometric_loss", "Block", "Flatten", "save_pic", "kornia", "torch", "nn", "F"):
+        assert hasattr(model, n), n
+    import kornia
+    assert callable(kornia.warp_perspective) and callable(kornia.get_perspective_transform)
 
 
 def test_host_coder_known_answers():

@@ -128,3 +128,90 @@ def test_independent_en_full_size_vs_oracle():
     # pairs are independent
     one = en(x1[1:].to(DEV), x2[1:].to(DEV), h[1:].to(DEV))
     assert torch.equal(one["x1_hat"], out["x1_hat"][1:])
+
+
+def test_homography_net_vs_reference_fixture():
+    """The front-end that produces h_matrix (ywz/mywork/model.py Net), operator level on the
+    hesic_b200 conv kernels, against the reference's stored delta."""
+    import model
+    net = model.Net(patch_size=128).eval()
+    net.load_state_dict(synth.synth_state_dict(net, seed=0))
+    x1, x2, _ = synth.stereo_pairs(2, 128, 128, seed=55)
+    a, b = x1.mean(1, keepdim=True).to(DEV), x2.mean(1, keepdim=True).to(DEV)
+    delta = net.to(DEV)(a, b)
+    assert delta.shape == (2, 4, 2)
+    assert_close(delta, load_npz("homography_net")["delta"], 1e-4, what="homography delta")
+
+
+def test_driver_flow_test3real():
+    """The body of test_epoch in ywz/mywork/test3real.py:143-224 on synthetic tensors, written as the driver
+    writes it (star-import of newnet9, HomographyModel around model.Net, kornia.get_perspective_transform,
+    torch.inverse, the in-place h_adjust, model -> model2 -> criterion), against the oracle doing the same."""
+    import kornia
+    import newnet9
+    from model import Net
+
+    class HomographyModel(torch.nn.Module):          # test3real.py:46-51
+        def __init__(self):
+            super().__init__()
+            self.model = Net(patch_size=128)
+
+        def forward(self, a, b):
+            return self.model(a, b)
+
+    modelhomo = HomographyModel().eval()
+    sd_h = synth.synth_state_dict(modelhomo, seed=0)
+    for k in sd_h:                                   # small corner offsets: a near-identity homography
+        if k.endswith("fc.5.weight") or k.endswith("fc.5.bias"):
+            sd_h[k] = sd_h[k] * 0.01
+    modelhomo.load_state_dict(sd_h)
+    net = newnet9.HSIC(N=128, M=192, K=5).eval()
+    sd = synth.synth_state_dict(net, seed=0)
+    net.load_state_dict(sd)
+    en = newnet9.Independent_EN().eval()
+    sd_en = synth.synth_state_dict(en, seed=0)
+    en.load_state_dict(sd_en)
+    d1, d2, _ = synth.stereo_pairs(2, 256, 256, seed=31)
+    homo1 = torch.nn.functional.interpolate(d1.mean(1, keepdim=True), size=(128, 128), mode="bilinear", align_corners=False)
+    homo2 = torch.nn.functional.interpolate(d2.mean(1, keepdim=True), size=(128, 128), mode="bilinear", align_corners=False)
+    corners = torch.tensor([[[64., 64.], [191., 64.], [191., 191.], [64., 191.]]]).repeat(2, 1, 1)
+
+    # oracle (CPU), same sequence
+    with torch.no_grad():
+        c0 = corners - corners[:, 0].view(-1, 1, 2)
+        dlt = O.homography_net_forward({k[len("model."):]: v for k, v in sd_h.items()}, homo1, homo2)
+        h_ref = O.h_adjust(256, 256, 256, 256, torch.inverse(O.get_perspective_transform(c0, c0 + dlt)))
+        ref = O.hsic_forward(sd, d1, d2, h_ref, twice_left=False)
+        ref2 = O.independent_en_forward(sd_en, ref["x1_hat"], ref["x2_hat"], h_ref)
+
+    # the driver's code, on the device
+    modelhomo, net, en = modelhomo.to(DEV), net.to(DEV), en.to(DEV)
+    d1d, d2d = d1.to(DEV), d2.to(DEV)
+    homo_corners = corners.to(DEV)
+    homo_corners = homo_corners - homo_corners[:, 0].view(-1, 1, 2)
+    delta_hat = modelhomo(homo1.to(DEV), homo2.to(DEV))
+    h = kornia.get_perspective_transform(homo_corners, homo_corners + delta_hat)
+    h_matrix = torch.inverse(h)
+    a, b = d1d.shape[-2] / 256, d1d.shape[-1] / 256   # h_adjust, test3real.py:56-66
+    h_matrix[:, 0, :] = a * h_matrix[:, 0, :]
+    h_matrix[:, :, 0] = (1. / a) * h_matrix[:, :, 0]
+    h_matrix[:, 1, :] = b * h_matrix[:, 1, :]
+    h_matrix[:, :, 1] = (1. / b) * h_matrix[:, :, 1]
+    out_net = net(d1d, d2d, h_matrix)
+    out_net2 = en(out_net["x1_hat"], out_net["x2_hat"], h_matrix)
+    float(net.aux_loss())
+    assert_close(h_matrix, h_ref, 1e-3, what="h_matrix")
+    out_net2["likelihoods"] = out_net["likelihoods"]
+    m = _check_against(out_net2, {"x1_hat": ref2["x1_hat"], "x2_hat": ref2["x2_hat"]}, d1, d2, what="driver flow")
+    m_ref = synth.rd_metrics({"x1_hat": ref2["x1_hat"], "x2_hat": ref2["x2_hat"], "likelihoods": ref["likelihoods"]}, d1, d2)
+    for k in ("bpp", "psnr1", "psnr2"):
+        assert math.isclose(m[k], m_ref[k], rel_tol=2e-3, abs_tol=2e-3), (k, m[k], m_ref[k])
+    # the driver's criterion (test3real.py:90-124; MS-SSIM left out: pytorch_msssim is not installed here)
+    mse = torch.nn.MSELoss()
+    num_pixels = d1d.size(0) * d1d.size(2) * d1d.size(3)
+    bpp_loss = sum((torch.log(lk).sum() / (-math.log(2) * num_pixels)) for lk in out_net["likelihoods"].values())
+    psnr1 = 10 * math.log10(1 / float(mse(out_net2["x1_hat"], d1d)))
+    assert math.isclose(float(bpp_loss), m["bpp"], rel_tol=1e-4) and math.isclose(psnr1, m["psnr1"], rel_tol=1e-4)
+    meter = newnet9.AverageMeter()
+    meter.update(bpp_loss)
+    assert math.isclose(float(meter.avg), m["bpp"], rel_tol=1e-4)

@@ -197,3 +197,33 @@ def test_dsic_dense_warp_and_conv3d_identities():
         w2[:, dd, :, lo:hi] = w3[:, :, lo - dd + 2:hi - dd + 2]
     y2 = torch.nn.functional.conv2d(x.reshape(1, 7 * D, 6, 9), w2.reshape(7 * D, 7 * D, 5, 5), b3.repeat_interleave(D), padding=2)
     assert_close(y2.reshape(ref.shape), ref, 1e-5, what="conv3d as banded conv2d")
+
+
+def test_homography_net_oracle_vs_reference_fixture():
+    """ywz/mywork/model.py Net: oracle restatement against the delta the unmodified reference produced."""
+    from hesic_b200 import compat
+    compat.install()
+    import model
+    net = model.Net(patch_size=128).eval()
+    gold_sd = load_json("homography_net")["state_dict_init"]
+    sd0 = net.state_dict()
+    assert set(sd0) == set(gold_sd) and all(list(sd0[k].shape) == gold_sd[k]["shape"] for k in gold_sd)
+    sd = synth.synth_state_dict(net, seed=0)
+    x1, x2, _ = synth.stereo_pairs(2, 128, 128, seed=55)
+    with torch.no_grad():
+        delta = O.homography_net_forward(sd, x1.mean(1, keepdim=True), x2.mean(1, keepdim=True))
+    assert_close(delta, load_npz("homography_net")["delta"], 1e-4, what="homography delta")
+
+
+def test_perspective_transform_maps_the_corners():
+    """get_perspective_transform (kornia, un-vendored: parity unpinned) -- checked by its defining property:
+    H maps each source corner onto its destination corner; h_adjust is the caller's frame rescale."""
+    g = torch.Generator().manual_seed(5)
+    src = torch.tensor([[[0., 0.], [127., 0.], [127., 127.], [0., 127.]]]).repeat(3, 1, 1)
+    dst = src + (torch.rand(3, 4, 2, generator=g) - 0.5) * 16
+    H = O.get_perspective_transform(src, dst).double()
+    p = torch.cat([src.double(), torch.ones(3, 4, 1, dtype=torch.float64)], -1) @ H.transpose(1, 2)
+    assert torch.allclose(p[..., :2] / p[..., 2:], dst.double(), atol=1e-3)
+    Hs = O.h_adjust(512, 512, 256, 256, H.float())
+    q = torch.cat([2 * src.double(), torch.ones(3, 4, 1, dtype=torch.float64)], -1) @ Hs.double().transpose(1, 2)
+    assert torch.allclose(q[..., :2] / q[..., 2:], 2 * dst.double(), atol=5e-3)
