@@ -35,37 +35,46 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe): one long-lived
+    `nvidia-smi -lms 50` process, its lines collected by this thread."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                c = [x.strip() for x in line.strip().split(",")]
+                if len(c) >= 7:
+                    self.rows.append(c)
+        except Exception:
+            pass
 
-    def stop(self):
-        self._stop_evt.set()
+    def mark(self):
+        """Number of samples so far (to select the ones taken inside a timed region)."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=3)
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        rows = self.rows[first:last] or self.rows
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        pw = sorted(float(r[2]) for r in rows if r[2].replace(".", "").isdigit())
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": float(rows[0][1]) if rows else None, "power_w": pw[len(pw) // 2] if pw else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
 
 
 def cpu_port_forward(model_kind, n_pairs, iters, warmup):
@@ -183,7 +192,9 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)
     C.lib.hesic_launch_count(1)
+    mark0 = sampler.mark() if sampler else 0
     ms = timed(lambda i: step(*sets[i % 2]), args.steps)
     launches = C.lib.hesic_launch_count(0)
     m_dev = metrics(partial.cpu(), B * world)
@@ -203,7 +214,7 @@ def run_ours(args):
 
     e2e_all(2)
     ms_e2e = timed(e2e_all, args.steps, whole=True)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(mark0) if sampler else None
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
     if rank != 0:
