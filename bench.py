@@ -126,6 +126,10 @@ def run_ours(args):
     from hesic_b200 import sharding, synth
     hesic_b200.install()
 
+    # libraries (NCCL prints its version banner) write to fd 1: park stdout on stderr until the result line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -291,9 +295,11 @@ def run_ours(args):
                          "sample": f"{args.cpu_iters} forwards of 1 synthetic 512x512 pair with the oracle (torch CPU fp32 port of "
                                    f"the reference's HSIC.forward), {cpu_sec:.2f} s each"},
     }
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)     # the JSON line is the only thing this process writes to stdout
+    print(json.dumps(line), flush=True)
 
 
 def main():
