@@ -7,6 +7,8 @@
 // form, with bias + activation (+ GDN as a 1x1 contraction over x^2) fused.
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "conv.h"
 
 namespace hesic {
@@ -411,6 +413,13 @@ extern "C" int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float 
   return HESIC_OK;
 }
 
+extern "C" int hesic_conv_enable_gdn(hesic_conv *c, int enable) {
+  HESIC_REQUIRE(c, "hesic_conv_enable_gdn: null conv");
+  HESIC_REQUIRE(!enable || c->gdn_beta, "hesic_conv_enable_gdn: no GDN has been packed for this layer");
+  c->has_gdn = enable != 0;
+  return HESIC_OK;
+}
+
 static int conv_forward_any(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *xb, const hesic_tensor *y, int act,
                             int path, void *stream) {
   HESIC_REQUIRE(c && c->loaded, "hesic_conv_forward: weights not loaded");
@@ -440,6 +449,10 @@ static int conv_forward_any(hesic_conv *c, const hesic_tensor *x, const hesic_te
     return HESIC_E_UNSUPPORTED;
   }
   if (path == HESIC_PATH_TCGEN05 || (path == HESIC_PATH_AUTO && tc_ok)) return conv_forward_tc(c, x, y, act, s);
+  static const bool trace = getenv("HESIC_TRACE_SIMT") != nullptr;   // which layers miss the tensor-core path
+  if (trace)
+    fprintf(stderr, "[hesic] CUDA-core conv: %d->%d k%dx%d s%d tr%d  in fmt%d %dx%dx%d  out fmt%d %dx%d path=%d\n", c->Cin, c->Cout,
+            c->kh, c->kw, c->stride, c->transposed, x->fmt, x->B, x->H, x->W, y->fmt, y->H, y->W, path);
   return conv_forward_simt(c, x, y, act, s);
 }
 

@@ -2,8 +2,9 @@
 (BASELINE config 5), on the hesic_b200 kernels.
 
 Same class tree, constructor arguments, ``forward`` signatures and ``state_dict`` keys as the reference
-file.  This first version runs at operator level: every convolution is a tcgen05 launch through
-``functional.conv2d`` (NCHW in/out), GroupNorm+ReLU, the disparity softmax and ``dense_warp`` are the kernels
+file.  ``DSIC.forward`` runs on the fused engine of hesic_b200/dsic_engine.py; the modules below are also callable
+on their own at operator level (every convolution a tcgen05 launch through ``functional.conv2d``, NCHW in/out).
+GroupNorm+ReLU, the disparity softmax and ``dense_warp`` are the kernels
 of csrc/dsic_ops.cu, and the two ``nn.Conv3d`` layers of each cost volume run as ONE 2-D convolution over
 the (F0 x C) = 224 stacked channels with a block-banded weight (a 5-tap correlation along the disparity
 axis is a banded channel-mixing matrix), i.e. on the same tensor-core path as every other layer.
@@ -175,7 +176,21 @@ class DSIC(CompressionModel):
         self._h_s1 = gmm_hyper_y1(N=N, M=M, K=K)
         self._h_s2 = gmm_hyper_y2(N=N, M=M, K=K)
 
+    @property
+    def hesic_engine(self):
+        if self.__dict__.get("_engine") is None:
+            from .dsic_engine import DsicEngine
+            self.__dict__["_engine"] = DsicEngine(self)
+        return self.__dict__["_engine"]
+
     def forward(self, x1, x2):
+        """mynet6_plus.py:675-761, eval mode, on the fused engine (hesic_b200/dsic_engine.py); the operator-level
+        composition of the same kernels remains available as ``forward_operator_level`` (parity cross-check)."""
+        if self.training:
+            raise NotImplementedError("hesic_b200: DSIC.forward is the inference path; call .eval() first")
+        return self.hesic_engine.forward(x1, x2)
+
+    def forward_operator_level(self, x1, x2):
         if self.training:
             raise NotImplementedError("hesic_b200: DSIC.forward is the inference path; call .eval() first")
         C.require_cuda(x1, x2)

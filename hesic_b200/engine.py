@@ -61,6 +61,18 @@ class HesicEngine:
         self.align_corners = align_corners
         self.path = path
         self.log2_sums = None
+        # The view-2 analysis (warp of x1, pre_conv, encoder2, h_a2, bottleneck 2) does not depend on view 1 until
+        # the conditioning buffer is assembled: it is enqueued on a side stream so that its HBM-bound kernels fill
+        # the gaps of view 1's tensor-core kernels (and vice versa).  HESIC_ONE_STREAM=1 disables the fork.
+        self._side = {}
+        import os
+        self.two_streams = not os.environ.get("HESIC_ONE_STREAM")
+
+    def _side_stream(self, dev):
+        s = self._side.get(dev)
+        if s is None:
+            s = self._side[dev] = torch.cuda.Stream(device=dev)
+        return s
 
     # ---- helpers -------------------------------------------------------------------------
     def _plan(self, conv_mod, gdn_mod=None):
@@ -190,6 +202,40 @@ class HesicEngine:
         a = lambda i: acc[i:i + 1]
         joint = self.variant == "joint"
 
+        # ---- fork: view-2 analysis on the side stream ------------------------------------------
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev) if self.two_streams else main
+        if side is not main:
+            side.wait_stream(main)
+        x1_warp = _nchw(B, 3, H, W, dev)
+        cat_out = _nchw(B, 6, H, W, dev)   # cat(after_gdn(..), x1_hat_warp)  newnet1.py:686
+        with torch.cuda.stream(side):
+            # ---- view 2 analysis -------------------------------------------------------------
+            self._warp(C.nchw(x1), h, C.nchw(x1_warp))
+            enc2 = m.encoder2
+            # pre_gdn(pre_conv(cat(x1_warp, x2)))  (newnet1.py:643-644): fp32 stencil over the two sources, written
+            # straight into the ROWPAD8 input planes of g_a_conv1
+            if self.path == C.PATH_AUTO:
+                _, pre_d, _, _ = self._run(enc2.pre_conv, C.nchw(x1_warp), B, H, W, "rowpad", gdn=enc2.pre_gdn,
+                                           dst=(self._rowpad_buf("pre", B, H, W), 0), xb_desc=C.nchw(x2))
+            else:
+                cat_in = _nchw(B, 6, H, W, dev)
+                self._convert(C.nchw(x1_warp), C.nchw(cat_in, 3, 0))
+                self._convert(C.nchw(x2), C.nchw(cat_in, 3, 3))
+                cin_d = C.nchw(cat_in) if self.path == C.PATH_SIMT else self._rowpad("cat_in", C.nchw(cat_in), B, 6, H, W)
+                _, pre_nchw_d, _, _ = self._run(enc2.pre_conv, cin_d, B, H, W, "nchw", gdn=enc2.pre_gdn)
+                pre_d = self._rowpad("pre", pre_nchw_d, B, 3, H, W)
+            y2, y2_d, Hy2, Wy2 = self._analysis(enc2, pre_d, B, H, W)
+            z2_pre = None
+            if not joint:
+                y2_abs = _split(B, Hy2, Wy2, M, dev)
+                self._convert(y2_d, C.split(y2_abs), C.OP_ABS)
+                z2, z2_d, Hz, Wz = self._seq3(m._h_a2.encode_hyper, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_NONE),
+                                              C.split(y2_abs), B, Hy2, Wy2, "nhwc")
+                z2_pre = self._bottleneck(m.entropy_bottleneck2, z2, z2_d, B, Hz, Wz, a(3))
+        joined = torch.cuda.Event()
+        joined.record(side)
+
         # ---- view 1 --------------------------------------------------------------------
         y1, y1_d, Hy, Wy = self._analysis(m.encoder1, self._rowpad("x1", C.nchw(x1), B, 3, H, W), B, H, W)
         if joint:
@@ -207,24 +253,6 @@ class HesicEngine:
             y1_hat, y1_lik, y1h_split_d = self._gmm(m.gaussian1, y1_d, s_d, m_d, w1, B, Hy, Wy, M, K, a(0))
         x1_hat, _, _, _ = self._synthesis(m.decoder1, y1h_split_d, B, Hy, Wy)
 
-        # ---- view 2 analysis -------------------------------------------------------------
-        x1_warp = _nchw(B, 3, H, W, dev)
-        cat_out = _nchw(B, 6, H, W, dev)   # cat(after_gdn(..), x1_hat_warp)  newnet1.py:686
-        self._warp(C.nchw(x1), h, C.nchw(x1_warp))
-        enc2 = m.encoder2
-        # pre_gdn(pre_conv(cat(x1_warp, x2)))  (newnet1.py:643-644): fp32 stencil over the two sources, written
-        # straight into the ROWPAD8 input planes of g_a_conv1
-        if self.path == C.PATH_AUTO:
-            _, pre_d, _, _ = self._run(enc2.pre_conv, C.nchw(x1_warp), B, H, W, "rowpad", gdn=enc2.pre_gdn,
-                                       dst=(self._rowpad_buf("pre", B, H, W), 0), xb_desc=C.nchw(x2))
-        else:
-            cat_in = _nchw(B, 6, H, W, dev)
-            self._convert(C.nchw(x1_warp), C.nchw(cat_in, 3, 0))
-            self._convert(C.nchw(x2), C.nchw(cat_in, 3, 3))
-            cin_d = C.nchw(cat_in) if self.path == C.PATH_SIMT else self._rowpad("cat_in", C.nchw(cat_in), B, 6, H, W)
-            _, pre_nchw_d, _, _ = self._run(enc2.pre_conv, cin_d, B, H, W, "nchw", gdn=enc2.pre_gdn)
-            pre_d = self._rowpad("pre", pre_nchw_d, B, 3, H, W)
-        y2, y2_d, _, _ = self._analysis(enc2, pre_d, B, H, W)
         x1hw_d = C.nchw(cat_out, 3, 3)
         x1hw_rp = None
         if self.variant != "newnet9":                  # "twiceLeft": the warped reconstruction is re-encoded
@@ -246,15 +274,13 @@ class HesicEngine:
             yw, yw_d, _, _ = self._analysis(m.encoder1, x1hw_rp, B, H, W)   # "twiceLeft"
             self._convert(yw_d, cond_slice, C.OP_ROUND)
 
-        # ---- view 2 entropy model ---------------------------------------------------------
+        # ---- join; view 2 entropy model ------------------------------------------------------
+        if side is not main:
+            main.wait_event(joined)
         if joint:
             y2_hat, y2_lik, y2h_split_d = self._joint_entropy(2, y2, y2_d, cond_buf, B, Hy, Wy, a(3), a(1))
         else:
-            y2_abs = _split(B, Hy, Wy, M, dev)
-            self._convert(y2_d, C.split(y2_abs), C.OP_ABS)
-            z2, z2_d, Hz, Wz = self._seq3(m._h_a2.encode_hyper, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_NONE),
-                                          C.split(y2_abs), B, Hy, Wy, "nhwc")
-            z2_hat, z2h_d, z2_lik = self._bottleneck(m.entropy_bottleneck2, z2, z2_d, B, Hz, Wz, a(3))
+            z2_hat, z2h_d, z2_lik = z2_pre
             C.check(_lib.hesic_upsample_bilinear(C.ref(z2h_d), C.ref(C.split(cond_buf, m.N, 0)), 4, C.stream()))
             hs = m._h_s2
             cd = C.split(cond_buf)

@@ -33,6 +33,7 @@ class ConvPlan:
             raise ValueError(C.last_error())
         self._key = None
         self._gdn_key = None
+        self._gdn_on = False
 
     def __del__(self):
         try:
@@ -58,16 +59,21 @@ class ConvPlan:
         return self
 
     def set_gdn(self, beta, gamma, inverse, beta_min=1e-6):
+        """Attach (beta, gamma given) or detach (beta None) the fused GDN.  The packed operands are kept across a
+        detach, so a layer shared by a fused engine and stand-alone operator calls toggles without re-packing."""
         if beta is None:
-            C.check(_lib.hesic_conv_set_gdn(self.h, None, None, 0, 0.0, C.stream()))
-            self._gdn_key = None
+            if self._gdn_on:
+                C.check(_lib.hesic_conv_enable_gdn(self.h, 0))
+                self._gdn_on = False
             return self
         key = self._ver(beta, gamma) + (inverse,)
-        if key == self._gdn_key:
-            return self
-        C.check(_lib.hesic_conv_set_gdn(self.h, C.ptr(_f32(beta.detach())), C.ptr(_f32(gamma.detach())), int(inverse),
-                                        float(beta_min), C.stream()))
-        self._gdn_key = key
+        if key != self._gdn_key:
+            C.check(_lib.hesic_conv_set_gdn(self.h, C.ptr(_f32(beta.detach())), C.ptr(_f32(gamma.detach())), int(inverse),
+                                            float(beta_min), C.stream()))
+            self._gdn_key = key
+        elif not self._gdn_on:
+            C.check(_lib.hesic_conv_enable_gdn(self.h, 1))
+        self._gdn_on = True
         return self
 
     def out_hw(self, H, W):

@@ -30,7 +30,9 @@ class _PlanMixin:
             raise NotImplementedError("hesic_b200 conv: only zero padding")
 
     def hesic_plan(self):
-        """Lazily created ConvPlan with the current weights packed (re-packed when they change)."""
+        """Lazily created ConvPlan with the current weights packed (re-packed when they change) and NO fused GDN:
+        an engine that fuses the GDN that follows re-attaches it (ConvPlan.set_gdn) after fetching the plan, so a
+        stand-alone call of this layer after an engine run is again a plain convolution."""
         if self._hesic_plan is None:
             self._geometry_ok()
             tr = isinstance(self, nn.ConvTranspose2d)
@@ -39,6 +41,7 @@ class _PlanMixin:
                                           _one(self.output_padding, "output_padding") if tr else 0)
         mask = getattr(self, "mask", None)
         self._hesic_plan.load(self.weight, self.bias, mask)
+        self._hesic_plan.set_gdn(None, None, False)
         return self._hesic_plan
 
     def _apply(self, fn, *a, **k):

@@ -92,6 +92,9 @@ int hesic_conv_load(hesic_conv *c, const float *weight, const float *bias, const
  * on the device.  Pass NULLs to detach. */
 int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float *gamma, int inverse, float beta_min,
                        void *stream);
+/* Detach (0) / re-attach (1) the GDN packed by the last hesic_conv_set_gdn without re-packing it: the same layer
+ * object serves the fused engine (GDN in the epilogue) and stand-alone operator calls (plain convolution). */
+int hesic_conv_enable_gdn(hesic_conv *c, int enable);
 int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, int path,
                        void *stream);
 /* Same layer applied to torch.cat((xa, xb), dim=1) without materialising the concatenation
@@ -177,14 +180,19 @@ int hesic_mixture_weights(const float *pooled, const float *w1x1, const float *b
 int hesic_upsample_bilinear(const hesic_tensor *x, const hesic_tensor *y, int scale, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Operators of the DSIC variant (ywz/DSIC/mynet6_plus.py), NCHW fp32.
+ * Operators of the DSIC variant (ywz/DSIC/mynet6_plus.py).  Each takes the reference's NCHW fp32 tensors, or -- for
+ * the fused DSIC engine, which keeps activations channels-last between tensor-core convolutions -- the
+ * channels-last forms named below (channel slices of wider buffers allowed, Cs > C).
  * nn.GroupNorm(groups, C, eps, affine) (+ the nn.ReLU that always follows it, mynet6_plus.py:224-238,262-290):
- * statistics over (C/groups, H, W) per sample; weight/bias: dev fp32 [C] or NULL. */
+ * statistics over (C/groups, H, W) per sample; weight/bias: dev fp32 [C] or NULL.
+ * Formats: NCHW fp32 -> NCHW fp32, or NHWC fp32 -> NHWC_SPLIT / NHWC fp32 (channels per group a multiple of 4). */
 int hesic_group_norm(const hesic_tensor *x, const hesic_tensor *y, int groups, const float *weight, const float *bias,
                      float eps, int relu, void *stream);
-/* nn.functional.softmax(x, dim=-3): over the disparity channels of a cost volume (mynet6_plus.py:311). */
+/* nn.functional.softmax(x, dim=-3): over the disparity channels of a cost volume (mynet6_plus.py:311).
+ * NCHW fp32, or NHWC fp32 with C <= 64. */
 int hesic_softmax_channels(const hesic_tensor *x, const hesic_tensor *y, void *stream);
-/* dense_warp.forward (mynet6_plus.py:316-345): out[b,c,y,x] = sum_{d, x+d<W} cost[b,d,y,x] * h1[b,c,y,x+d]. */
+/* dense_warp.forward (mynet6_plus.py:316-345): out[b,c,y,x] = sum_{d, x+d<W} cost[b,d,y,x] * h1[b,c,y,x+d].
+ * All NCHW fp32, or h1 / out NHWC_SPLIT with an NHWC fp32 cost. */
 int hesic_dense_warp(const hesic_tensor *h1, const hesic_tensor *cost, const hesic_tensor *out, void *stream);
 
 /* Layout / format conversion with an optional pointwise op: 0 copy, 1 abs (newnet1.py:435),

@@ -110,3 +110,85 @@ def test_dsic_forward_vs_oracle_and_reference_fixture(dsic):
         assert abs(m[k] - meta["metrics"][k]) <= 5e-3 * meta["metrics"][k], (k, m[k], meta["metrics"][k])
     for k in ("psnr1", "psnr2"):
         assert abs(m[k] - r[k]) <= 0.05, (k, m[k], r[k])
+
+
+def _to_split(x, Cs=None, c0=0):
+    """NCHW fp32 -> channel slice [c0, c0+C) of a [2,B,H,W,Cs] SPLIT buffer (rest NaN-free zeros)."""
+    from hesic_b200 import _capi as C
+    B, Cn, H, W = x.shape
+    Cs = Cn if Cs is None else Cs
+    t = torch.zeros((2, B, H, W, Cs), device=DEV, dtype=torch.bfloat16)
+    xd = x.to(DEV).contiguous()
+    C.check(C.lib.hesic_convert(C.ref(C.nchw(xd)), C.ref(C.split(t, Cn, c0)), C.OP_COPY, C.stream()))
+    torch.cuda.synchronize()
+    return t
+
+
+def _from_split(t, Cn=None, c0=0):
+    v = t[0].float() + t[1].float()
+    Cn = v.shape[-1] - c0 if Cn is None else Cn
+    return v[..., c0:c0 + Cn].permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("shape,groups", [((2, 128, 16, 24), 4), ((1, 672, 4, 16), 21), ((3, 224, 8, 8), 1), ((2, 32, 5, 7), 2)])
+def test_group_norm_channels_last(shape, groups):
+    """The fused engine's GroupNorm: NHWC fp32 in (the conv output), SPLIT channel slice out (the next conv's input)."""
+    from hesic_b200 import _capi as C
+    B, Cn, H, W = shape
+    x = _rand(shape, 1, 2.0) + 0.3
+    w, b = 1 + _rand((Cn,), 2, 0.1), _rand((Cn,), 3, 0.1)
+    ref = torch.relu(torch.nn.functional.group_norm(x, groups, w, b, 1e-5))
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wd, bd = w.to(DEV), b.to(DEV)
+    out = torch.zeros((2, B, H, W, Cn + 40), device=DEV, dtype=torch.bfloat16)
+    C.check(C.lib.hesic_group_norm(C.ref(C.nhwc(xn)), C.ref(C.split(out, Cn, 8)), groups, C.ptr(wd), C.ptr(bd), 1e-5, 1, C.stream()))
+    assert_close(_from_split(out, Cn, 8), ref, 2e-5, what="group_norm NHWC -> SPLIT slice")
+    assert float(out[..., :8].float().abs().max()) == 0 and float(out[..., Cn + 8:].float().abs().max()) == 0
+    on = torch.empty((B, H, W, Cn), device=DEV)
+    C.check(C.lib.hesic_group_norm(C.ref(C.nhwc(xn)), C.ref(C.nhwc(on)), groups, None, None, 1e-5, 0, C.stream()))
+    assert_close(on.permute(0, 3, 1, 2), torch.nn.functional.group_norm(x, groups), 1e-5, what="group_norm NHWC no affine")
+
+
+def test_softmax_and_dense_warp_channels_last():
+    from hesic_b200 import _capi as C
+    x = _rand((2, 32, 9, 40), 4, 3.0)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    yn = torch.empty_like(xn)
+    C.check(C.lib.hesic_softmax_channels(C.ref(C.nhwc(xn)), C.ref(C.nhwc(yn)), C.stream()))
+    assert_close(yn.permute(0, 3, 1, 2), torch.softmax(x, dim=-3), 1e-5, floor=1e-6, what="softmax NHWC")
+    for (B, Cn, H, W, D) in ((2, 128, 8, 64, 32), (1, 128, 3, 100, 32), (1, 8, 2, 40, 7)):
+        h1 = _rand((B, Cn, H, W), 5)
+        cost = torch.softmax(_rand((B, D, H, W), 6, 2.0), dim=1)
+        buf = _to_split(h1, 3 * Cn, 2 * Cn)                      # [w | a | g] level buffer of the engine
+        hq = _from_split(buf, Cn, 2 * Cn).cpu()
+        ref = O.dsic_dense_warp(hq, cost)
+        cn = cost.permute(0, 2, 3, 1).contiguous().to(DEV)
+        C.check(C.lib.hesic_dense_warp(C.ref(C.split(buf, Cn, 2 * Cn)), C.ref(C.nhwc(cn)), C.ref(C.split(buf, Cn, 0)), C.stream()))
+        assert_close(_from_split(buf, Cn, 0), ref, 2e-5, what=f"dense_warp channels-last {B, Cn, H, W, D}")
+        assert torch.equal(_from_split(buf, Cn, 2 * Cn).cpu(), hq) and float(buf[..., Cn:2 * Cn].float().abs().max()) == 0
+
+
+def test_dsic_engine_and_operator_level_second_size(dsic):
+    """A second size and batch 2: the fused engine and the operator-level composition of the same kernels both match
+    the oracle (they differ from each other only through x.5 rounding ties of the latents)."""
+    net, sd = dsic
+    x1, x2, _ = synth.stereo_pairs(2, 128, 320, seed=21)   # W / 8 >= 32 disparities (the reference breaks below)
+    with torch.no_grad():
+        ref = O.dsic_forward(sd, x1, x2)
+    a = net(x1.to(DEV), x2.to(DEV))
+    b = net.forward_operator_level(x1.to(DEV), x2.to(DEV))
+    from hesic_b200 import _capi as C
+    C.check(C.lib.hesic_tc_status())
+    r = synth.rd_metrics(ref, x1, x2)
+    for name, out in (("engine", a), ("operator level", b)):
+        cpu = {"x1_hat": out["x1_hat"].cpu(), "x2_hat": out["x2_hat"].cpu(),
+               "likelihoods": {k: v.cpu() for k, v in out["likelihoods"].items()}}
+        for k in ("x1_hat", "x2_hat"):
+            rel = float((cpu[k].double() - ref[k].double()).pow(2).sum().sqrt() / ref[k].double().pow(2).sum().sqrt())
+            assert rel < 2e-2, (name, k, rel)
+        assert_close(cpu["likelihoods"]["z1"], ref["likelihoods"]["z1"], 1e-3, floor=1e-9, what=name + " z1 likelihood")
+        m = synth.rd_metrics(cpu, x1, x2)
+        for k in ("bpp", "bpp1", "bpp2"):
+            assert abs(m[k] - r[k]) <= 5e-3 * r[k], (name, k, m[k], r[k])
+        for k in ("psnr1", "psnr2"):
+            assert abs(m[k] - r[k]) <= 0.1, (name, k, m[k], r[k])

@@ -215,3 +215,18 @@ def test_driver_flow_test3real():
     meter = newnet9.AverageMeter()
     meter.update(bpp_loss)
     assert math.isclose(float(meter.avg), m["bpp"], rel_tol=1e-4)
+
+
+def test_operator_call_after_engine_run_is_a_plain_conv():
+    """The engine fuses GDN into the preceding conv's plan; a stand-alone call of that layer afterwards (the
+    compressai operator surface) must again be the plain convolution, and the engine must still fuse on the next run."""
+    net, sd = _model("newnet1")
+    x1, x2, h = synth.stereo_pairs(1, 128, 128, seed=3)
+    a = net(x1.to(DEV), x2.to(DEV), h.to(DEV))
+    y = net.encoder1.g_a_conv1(x1.to(DEV))
+    assert_close(y, O.conv(x1, sd["encoder1.g_a_conv1.weight"], sd["encoder1.g_a_conv1.bias"]), 1e-4, what="stand-alone conv")
+    g = net.encoder1.g_a_gdn1(y)
+    assert_close(g, O.gdn(O.conv(x1, sd["encoder1.g_a_conv1.weight"], sd["encoder1.g_a_conv1.bias"]),
+                          sd["encoder1.g_a_gdn1.beta"], sd["encoder1.g_a_gdn1.gamma"]), 1e-4, what="stand-alone GDN")
+    b = net(x1.to(DEV), x2.to(DEV), h.to(DEV))
+    assert torch.equal(a["x1_hat"], b["x1_hat"]) and torch.equal(a["likelihoods"]["y2"], b["likelihoods"]["y2"])

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""DSIC forward timing (BASELINE config 5: batch 8 x 512x512 on one B200), operator-level path.
+"""DSIC forward timing (BASELINE config 5: batch 8 x 512x512 on one B200), fused engine (hesic_b200/dsic_engine.py).
 
     python tools/dsic_time.py [B] [H] [W] [reps]"""
 import os
