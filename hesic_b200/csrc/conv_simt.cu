@@ -9,6 +9,8 @@
 
 #include <stdlib.h>
 
+#include <vector>
+
 #include "conv.h"
 
 namespace hesic {
@@ -364,6 +366,18 @@ extern "C" int hesic_conv_load(hesic_conv *c, const float *weight, const float *
     size_t tc_elems = std::max(taps * c->Cin, (size_t)c->tc_taps * c->tc_k) * c->CoutPad;
     HESIC_CUDA(cudaMalloc(&c->w_hi, tc_elems * sizeof(__nv_bfloat16)));
     HESIC_CUDA(cudaMalloc(&c->w_lo, tc_elems * sizeof(__nv_bfloat16)));
+  }
+  c->live_taps = ~0ull;
+  if (mask && taps <= 64) {
+    // once per load: which taps does the mask keep?  (host copy + sync; weights are loaded once per model)
+    const size_t n = (size_t)c->Cout * c->Cin * taps;
+    std::vector<float> hm(n);
+    HESIC_CUDA(cudaMemcpyAsync(hm.data(), mask, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HESIC_CUDA(cudaStreamSynchronize(s));
+    uint64_t live = 0;
+    for (size_t i = 0; i < n; ++i)
+      if (hm[i] != 0.f) live |= 1ull << (i % taps);
+    c->live_taps = live ? live : ~0ull;   // an all-zero mask keeps every (zero-weight) tap
   }
   size_t total = taps * c->Cin * c->CoutPad;
   int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);

@@ -656,6 +656,7 @@ static int build_taps(const hesic_conv *c, Params &p) {
   } else if (!c->transposed) {
     for (int ky = 0; ky < c->kh; ++ky)
       for (int kx = 0; kx < c->kw; ++kx) {
+        if (c->kh * c->kw <= 64 && !((c->live_taps >> (ky * c->kw + kx)) & 1ull)) continue;   // masked-out tap (MaskedConv2d)
         const int oy = ky - c->pad, ox = kx - c->pad;
         if (c->stride == 1) add_tap(p, n, oy, ox, 0, 0, ky * c->kw + kx);
         else {

@@ -448,3 +448,26 @@ def test_enhancement_conv_rejects_bad_arguments():
         plan.run(C.hilo(x), C.hilo(torch.zeros((1, 8, 8, 64), device=DEV, dtype=torch.bfloat16)))
     with pytest.raises(ValueError):
         plan.run(C.hilo(x), C.nchw(torch.zeros((1, 32, 8, 16), device=DEV)))
+
+
+@pytest.mark.parametrize("mask_type", ["A", "B"])
+@pytest.mark.parametrize("path", ["auto", "simt"])
+def test_masked_conv2d(mask_type, path):
+    """MaskedConv2d (compressai/layers/layers.py:21-45; HESIC+ context_prediction, newnet1_joint.py:635-639): the
+    tensor-core path skips the taps the mask removes (12 / 13 live taps of 25), the CUDA-core path multiplies by it."""
+    from hesic_b200 import _capi as C
+    from hesic_b200 import functional as F
+    from compressai.layers import MaskedConv2d
+    m = MaskedConv2d(192, 384, kernel_size=5, padding=2, stride=1, mask_type=mask_type)
+    w, b = _rand(tuple(m.weight.shape), 41, (2.0 / (192 * 25)) ** 0.5), _rand((384,), 42, 0.1)
+    m.load_state_dict({"weight": w, "bias": b, "mask": m.mask.clone()})
+    x = _rand((2, 192, 16, 24), 43)
+    ref = torch.nn.functional.conv2d(x, w * m.mask, b, padding=2)
+    m = m.to(DEV)
+    if path == "auto":
+        y = m(x.to(DEV))
+    else:
+        m.weight.data *= m.mask
+        y = F.conv2d(x.to(DEV), m.hesic_plan(), path=C.PATH_SIMT)
+    assert_close(y, ref, 1e-4, what=f"MaskedConv2d type {mask_type} ({path})")
+    assert int(m.mask[0, 0].sum()) == (12 if mask_type == "A" else 13)
