@@ -45,8 +45,9 @@ __device__ __forceinline__ void block_add_double(double v, double *acc) {
 //  * The blend itself is fp32 in grid_sample's order.  Optional second output in ROWPAD format: the warped
 //    image is the input of the next 3->128 tensor-core layer (newnet1.py:753-754), which saves a repack pass.
 constexpr int WARP_STAGE_FLOATS = 6144;   // 24 KB: e.g. 3 channels x 40 x 51 source pixels
-constexpr int WARP_TILE = 32, WARP_ROWS = 4;   // block = 32 x 32 destination pixels, 4 rows per thread
+constexpr int WARP_TILE = 32;   // block = 32 x (8 * WARP_ROWS) destination pixels, WARP_ROWS rows per thread
 
+template <int WARP_ROWS>
 __global__ void __launch_bounds__(256, 3) warp_kernel(const TView src, const float *__restrict__ Mx, const TView dst,
                                                   const TView dst2, int align_corners) {
   __shared__ double T[9], S[12];
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(256, 3) warp_kernel(const TView src, const flo
   const unsigned bias = 4u;   // x0, y0 >= -2 for finite pixels
 #pragma unroll
   for (int k = 0; k < WARP_ROWS; ++k) {
-    const int y = blockIdx.y * WARP_TILE + threadIdx.y + 8 * k;
+    const int y = blockIdx.y * (8 * WARP_ROWS) + threadIdx.y + 8 * k;
     const double gy = fma((double)y, S[10], -1.0);
     double u = fma(gx, S[0], fma(gy, S[1], S[2]));
     double v = fma(gx, S[3], fma(gy, S[4], S[5]));
@@ -155,9 +156,42 @@ __global__ void __launch_bounds__(256, 3) warp_kernel(const TView src, const flo
   const int nc = src.C, plane = wh * ww;
   const bool nchw_out = dst.fmt == HESIC_FMT_NCHW_F32;
   const size_t dplane = (size_t)dst.H * dst.W;
+  if (staged && nc == 3 && nchw_out) {
+    // Fast path of the forward pass (RGB, window staged): branch-free taps.  A tap outside the image gets weight 0
+    // and its address clamped into the staged window (finite data), which leaves grid_sample's result and its
+    // nw + ne + sw + se summation order unchanged.
+#pragma unroll
+    for (int k = 0; k < WARP_ROWS; ++k) {
+      const int y = blockIdx.y * (8 * WARP_ROWS) + threadIdx.y + 8 * k;
+      if (y >= dst.H) break;
+      const int x1 = x0[k] + 1, y1 = y0[k] + 1;
+      const bool vx0 = fin[k] && x0[k] >= 0 && x0[k] < src.W, vx1 = fin[k] && x1 >= 0 && x1 < src.W;
+      const bool vy0 = y0[k] >= 0 && y0[k] < src.H, vy1 = y1 >= 0 && y1 < src.H;
+      const float bx0 = vx0 ? 1.f - ax[k] : 0.f, bx1 = vx1 ? ax[k] : 0.f;
+      const float by0 = vy0 ? 1.f - ay[k] : 0.f, by1 = vy1 ? ay[k] : 0.f;
+      // weights exactly as grid_sample forms them: (1-ax)(1-ay), ax(1-ay), (1-ax)ay, ax*ay -- or 0
+      const float wnw = bx0 * by0, wne = bx1 * by0, wsw = bx0 * by1, wse = bx1 * by1;
+      const int cx0 = min(max(x0[k] - wx0, 0), ww - 1), cx1 = min(max(x1 - wx0, 0), ww - 1);
+      const int r0 = min(max(y0[k] - wy0, 0), wh - 1) * ww, r1 = min(max(y1 - wy0, 0), wh - 1) * ww;
+      float out[3];
+      float *dp = (float *)dst.p0 + ((size_t)b * dst.Cs * dst.H + y) * dst.W + x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float *t = stage + c * plane;
+        float o = t[r0 + cx0] * wnw;
+        o += t[r0 + cx1] * wne;
+        o += t[r1 + cx0] * wsw;
+        o += t[r1 + cx1] * wse;
+        out[c] = o;
+        dp[c * dplane] = o;
+      }
+      if (dst2.p0) store_rowpad_pixel(dst2, b, y, x, out);
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < WARP_ROWS; ++k) {
-    const int y = blockIdx.y * WARP_TILE + threadIdx.y + 8 * k;
+    const int y = blockIdx.y * (8 * WARP_ROWS) + threadIdx.y + 8 * k;
     if (y >= dst.H) break;
     const int x1 = x0[k] + 1, y1 = y0[k] + 1;
     const float wnw = (1.f - ax[k]) * (1.f - ay[k]), wne = ax[k] * (1.f - ay[k]);
@@ -603,8 +637,12 @@ extern "C" int hesic_warp_perspective(const hesic_tensor *src, const float *M, c
   HESIC_REQUIRE(src->p0 != dst->p0, "warp: in-place is not supported");
   if (numel(dst) == 0) return HESIC_OK;
   HESIC_REQUIRE(src->H < 60000 && src->W < 60000, "warp: source image too large");
-  dim3 blk(32, 8), grid((dst->W + WARP_TILE - 1) / WARP_TILE, (dst->H + WARP_TILE - 1) / WARP_TILE, dst->B);
-  warp_kernel<<<grid, blk, 0, as_stream(stream)>>>(view(src), M, view(dst), d2, align_corners);
+  static const int rows = getenv("HESIC_WARP_ROWS") ? atoi(getenv("HESIC_WARP_ROWS")) : 4;
+  const int ty = 8 * (rows == 1 ? 1 : (rows == 2 ? 2 : 4));
+  dim3 blk(32, 8), grid((dst->W + WARP_TILE - 1) / WARP_TILE, (dst->H + ty - 1) / ty, dst->B);
+  if (rows == 1) warp_kernel<1><<<grid, blk, 0, as_stream(stream)>>>(view(src), M, view(dst), d2, align_corners);
+  else if (rows == 2) warp_kernel<2><<<grid, blk, 0, as_stream(stream)>>>(view(src), M, view(dst), d2, align_corners);
+  else warp_kernel<4><<<grid, blk, 0, as_stream(stream)>>>(view(src), M, view(dst), d2, align_corners);
   HESIC_LAUNCHED("warp_kernel");
   return HESIC_OK;
 }
