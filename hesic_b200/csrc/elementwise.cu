@@ -464,8 +464,24 @@ __global__ void __launch_bounds__(256) spatial_max_nhwc_kernel(const TView x, fl
   const int c = blockIdx.x * 32 + cl;
   float m = -INFINITY;
   const int P = x.H * x.W;
-  if (c < x.C)
-    for (int p = pl; p < P; p += 8) m = fmaxf(m, tload(x, b, c, p / x.W, p % x.W));
+  if (c < x.C) {
+    if (x.fmt == HESIC_FMT_NHWC_F32) {
+      // four independent running maxima per thread: the loads of a thread are in flight together
+      const float *base = (const float *)x.p0 + (size_t)b * P * x.Cs + c;
+      float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      int p = pl;
+      for (; p + 24 < P; p += 32) {
+        m = fmaxf(m, __ldg(base + (size_t)p * x.Cs));
+        m1 = fmaxf(m1, __ldg(base + (size_t)(p + 8) * x.Cs));
+        m2 = fmaxf(m2, __ldg(base + (size_t)(p + 16) * x.Cs));
+        m3 = fmaxf(m3, __ldg(base + (size_t)(p + 24) * x.Cs));
+      }
+      for (; p < P; p += 8) m = fmaxf(m, __ldg(base + (size_t)p * x.Cs));
+      m = fmaxf(fmaxf(m, m1), fmaxf(m2, m3));
+    } else {
+      for (int p = pl; p < P; p += 8) m = fmaxf(m, tload(x, b, c, p / x.W, p % x.W));
+    }
+  }
   red[pl][cl] = m;
   __syncthreads();
   if (pl == 0 && c < x.C) {
@@ -547,6 +563,29 @@ __global__ void __launch_bounds__(256) convert_kernel(const TView x, const TView
   tstore(y, b, c, yy, xx, v);
 }
 
+// NHWC fp32 -> SPLIT planes (channel slices allowed), four channels per thread: the y -> |y| / round(y) hand-offs
+// between the analysis stack and the hyper path (newnet1.py:435,755)
+__global__ void __launch_bounds__(256) convert_nhwc_split_kernel(const TView x, const TView y, int op, size_t n4) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int C4 = x.C >> 2;
+  const int cq = (int)(i % C4);
+  const size_t pix = i / C4;
+  const float4 v = __ldg(reinterpret_cast<const float4 *>((const float *)x.p0 + pix * x.Cs + 4 * cq));
+  float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (op == HESIC_OP_ABS) o[k] = fabsf(o[k]);
+    else if (op == HESIC_OP_ROUND) o[k] = rintf(o[k]);
+  }
+  __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) split_bf16(o[k], hi[k], lo[k]);
+  const size_t off = pix * y.Cs + 4 * cq;
+  *reinterpret_cast<uint2 *>((__nv_bfloat16 *)y.p0 + off) = *reinterpret_cast<const uint2 *>(hi);
+  *reinterpret_cast<uint2 *>((__nv_bfloat16 *)y.p1 + off) = *reinterpret_cast<const uint2 *>(lo);
+}
+
 // NCHW fp32 (C <= 8) -> ROWPAD split planes: thread = pixel, one 16- or 8-byte store per plane (all channel
 // slots, zeros above C), reads coalesced per source plane.
 __global__ void __launch_bounds__(256) rowpad_kernel(const TView x, const TView y, int op, size_t npix) {
@@ -598,6 +637,18 @@ __global__ void __launch_bounds__(256) indexes_scale_kernel(const TView sc, cons
   int idx = nt - 1;
   for (int j = 0; j < nt - 1; ++j) idx -= (s <= tab[j]) ? 1 : 0;
   out[i] = idx;
+}
+
+// both tensors dense fp32 in the same layout: 128-bit loads, fp32 squares folded into fp64 four at a time
+__global__ void __launch_bounds__(256) sse_dense_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, double *acc,
+                                                       size_t n4) {
+  double s = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 u = __ldg(a + i), v = __ldg(b + i);
+    const float dx = u.x - v.x, dy = u.y - v.y, dz = u.z - v.z, dw = u.w - v.w;
+    s += ((double)dx * (double)dx + (double)dy * (double)dy) + ((double)dz * (double)dz + (double)dw * (double)dw);
+  }
+  block_add_double(s, acc);
 }
 
 __global__ void __launch_bounds__(256) sse_kernel(const TView a, const TView b_, double *acc, size_t n) {
@@ -795,6 +846,12 @@ extern "C" int hesic_convert(const hesic_tensor *x, const hesic_tensor *y, int o
     HESIC_LAUNCHED("rowpad_kernel");
     return HESIC_OK;
   }
+  if (x->fmt == HESIC_FMT_NHWC_F32 && y->fmt == HESIC_FMT_NHWC_SPLIT && (x->C & 3) == 0 && ((x->Cs > 0 ? x->Cs : x->C) & 3) == 0 &&
+      ((y->Cs > 0 ? y->Cs : y->C) & 3) == 0 && ((uintptr_t)x->p0 & 15) == 0 && (((uintptr_t)y->p0 | (uintptr_t)y->p1) & 7) == 0) {
+    convert_nhwc_split_kernel<<<nblk(n / 4), 256, 0, as_stream(stream)>>>(view(x), view(y), op, n / 4);
+    HESIC_LAUNCHED("convert_nhwc_split_kernel");
+    return HESIC_OK;
+  }
   convert_kernel<<<nblk(n), 256, 0, as_stream(stream)>>>(view(x), view(y), op, n);
   HESIC_LAUNCHED("convert_kernel");
   return HESIC_OK;
@@ -847,6 +904,14 @@ extern "C" int hesic_sum_squared_error(const hesic_tensor *a, const hesic_tensor
   size_t n = numel(a);
   if (n == 0) return HESIC_OK;
   unsigned blocks = nblk(n) < 148 * 8 ? nblk(n) : 148 * 8;
+  const bool dense = a->fmt == b->fmt && (a->fmt == HESIC_FMT_NCHW_F32 || a->fmt == HESIC_FMT_NHWC_F32) &&
+                     (a->Cs == 0 || a->Cs == a->C) && (b->Cs == 0 || b->Cs == b->C) && (n & 3) == 0 &&
+                     (((uintptr_t)a->p0 | (uintptr_t)b->p0) & 15u) == 0;
+  if (dense) {
+    sse_dense_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const float4 *)a->p0, (const float4 *)b->p0, acc, n / 4);
+    HESIC_LAUNCHED("sse_dense_kernel");
+    return HESIC_OK;
+  }
   sse_kernel<<<blocks, 256, 0, as_stream(stream)>>>(view(a), view(b), acc, n);
   HESIC_LAUNCHED("sse_kernel");
   return HESIC_OK;

@@ -471,3 +471,25 @@ def test_masked_conv2d(mask_type, path):
         y = F.conv2d(x.to(DEV), m.hesic_plan(), path=C.PATH_SIMT)
     assert_close(y, ref, 1e-4, what=f"MaskedConv2d type {mask_type} ({path})")
     assert int(m.mask[0, 0].sum()) == (12 if mask_type == "A" else 13)
+
+
+def test_sum_squared_error_and_channels_last_max():
+    """RateDistortionLoss's MSE partial sum (test3real.py:99-111) in fp64, dense (128-bit loads) and strided forms;
+    spatial_pool2d on the channels-last layout the engine uses."""
+    from hesic_b200 import _capi as C
+    from hesic_b200 import functional as F
+    a, b = _rand((3, 3, 40, 52), 51), _rand((3, 3, 40, 52), 52)
+    ref = float(((a.double() - b.double()) ** 2).sum())
+    acc = torch.zeros(2, device=DEV, dtype=torch.float64)
+    F.sum_squared_error(a.to(DEV), b.to(DEV), acc[0:1])
+    wide = torch.zeros((3, 5, 40, 52), device=DEV)
+    wide[:, 1:4] = a.to(DEV)
+    bd = b.to(DEV)
+    C.check(C.lib.hesic_sum_squared_error(C.ref(C.nchw(wide, 3, 1)), C.ref(C.nchw(bd)), C.ptr(acc[1:2]), C.stream()))
+    got = acc.cpu()
+    assert abs(float(got[0]) - ref) <= 1e-9 * ref and abs(float(got[1]) - ref) <= 1e-9 * ref
+    x = _rand((2, 960, 9, 13), 53)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.empty((2, 960), device=DEV)
+    C.check(C.lib.hesic_spatial_max(C.ref(C.nhwc(xn)), C.ptr(out), C.stream()))
+    assert torch.equal(out.cpu(), x.amax(dim=(2, 3)))
