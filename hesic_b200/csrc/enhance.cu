@@ -11,13 +11,15 @@
 //     shifted by dx = -1, 0, +1 pixels (TMA zero fill = the zero padding): 3 x 20 KB instead of 9 tap loads.  Inside
 //     a copy the three dy taps are plain address offsets of one 16-pixel row (2 KB, swizzle-atom aligned).
 //   * the weights of a tap are ONE resident tile of 2N rows x 128 B:  rows [0, N) = [Wh | 0],  rows [N, 2N) =
-//     [Wl | Wh].  One K = 64 MMA chain (4 MMAs of M 128 x N 2N x K 16) per tap then yields, with fp32 parity as in
-//     conv_tc.cu (bf16x3, main + small accumulators):
+//     [Wl | Wh].  One K = 64 MMA chain per tap then yields, with fp32 parity as in conv_tc.cu (bf16x3, main + small
+//     accumulators in adjacent TMEM columns):
 //         D[:, 0:N]  (main)  += [Ah | Al] . [Wh | 0]  = Ah.Wh
 //         D[:, N:2N] (small) += [Ah | Al] . [Wl | Wh] = Ah.Wl + Al.Wh
-//     36 MMAs per tile, every A row read from shared memory once per tap (the kernel is bound by the tensor core's
-//     shared-memory operand reads: r01 profile, 53 % of that pipe with separate main / small chains re-reading A);
-//     all nine tap tiles (72 KB) stay in shared memory.
+//     (K chunks 0,1 = the Ah half: two M128 x N(2N) x K16 MMAs; chunks 2,3 = the Al half, where the main rows are zero:
+//     two N-wide MMAs on the small rows only.)  36 MMAs per tile, every A row read from shared memory once per tap --
+//     the kernel is bound by shared-memory bandwidth (r01 profile: tensor-core operand reads alone are 53 % of it;
+//     a first version with separate main / small chains re-read A 1.5x and was 30 % slower); all nine tap tiles
+//     (72 KB) stay in shared memory.
 //   * warp-specialised persistent CTA: warp 0 TMA producer, warp 1 MMA issuer (4 TMEM accumulator buffers),
 //     warps 2-5 and 6-9 two epilogue groups taking alternate tiles: bias, LeakyReLU, up to two residuals read
 //     straight from HBM (L2-prefetched one turn ahead, loaded before the accumulator is waited for), hi/lo split,

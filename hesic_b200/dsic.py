@@ -263,7 +263,11 @@ class Independent_EN(nn.Module):
         self.EH2 = Enhancement()
 
     def forward(self, x1_hat, x2_hat):
-        return {"x1_hat": self.EH1(x1_hat), "x2_hat": self.EH2(x2_hat)}
+        """mynet6_plus.py Independent_EN on the fused enhancement kernels (hesic_b200/enhance.py)."""
+        if self.__dict__.get("_engine") is None:
+            from .enhance import EnhanceEngine
+            self.__dict__["_engine"] = EnhanceEngine(self)
+        return self.__dict__["_engine"].forward_mono(x1_hat, x2_hat)
 
 
 class DSIC_plus(nn.Module):

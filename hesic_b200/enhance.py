@@ -75,11 +75,13 @@ class EnhanceEngine:
         return t
 
     def _enhancement(self, eh, x, x_other_warp, out):
-        """Enhancement.forward (newnet1.py:296-311) for one view; x / x_other_warp / out: NCHW fp32."""
+        """Enhancement.forward (newnet1.py:296-311) for one view; x / x_other_warp / out: NCHW fp32.  x_other_warp
+        None: the DSIC variant without a cross-view input (mynet6_plus.py:57-78)."""
         B, _, H, W = x.shape
         dev = x.device
         a, b, c, t = (C.hilo(self._buf(n, B, H, W, dev)) for n in "abct")
-        C.check(_lib.hesic_en_pack_input(C.ref(C.nchw(x)), C.ref(C.nchw(x_other_warp)), C.ref(t), C.stream()))
+        C.check(_lib.hesic_en_pack_input(C.ref(C.nchw(x)), C.ref(C.nchw(x_other_warp)) if x_other_warp is not None else None,
+                                         C.ref(t), C.stream()))
         en_plan(eh.conv1).run(t, a)
         for eb in (eh.EB1, eh.EB2, eh.EB3):
             # Enhancement_Block (newnet1.py:272-287): RB3(RB2(RB1(a))) + a, ResidualBlock = lrelu(conv2(lrelu(conv1(x)))) + x
@@ -92,6 +94,15 @@ class EnhanceEngine:
             a, b = b, a
         en_plan(eh.conv2).run(a, C.nchw(out), C.ACT_NONE, res1=C.nchw(x))
         return out
+
+    def forward_mono(self, x1_hat, x2_hat):
+        """mynet6_plus.Independent_EN.forward: each view enhanced on its own."""
+        C.require_cuda(x1_hat, x2_hat)
+        x1_hat, x2_hat = F._f32(x1_hat), F._f32(x2_hat)
+        if x1_hat.dim() != 4 or x1_hat.shape[1] != 3 or x2_hat.shape != x1_hat.shape:
+            raise ValueError("Independent_EN: x1_hat and x2_hat must be [B,3,H,W] tensors of the same shape")
+        return {"x1_hat": self._enhancement(self.m.EH1, x1_hat, None, torch.empty_like(x1_hat)),
+                "x2_hat": self._enhancement(self.m.EH2, x2_hat, None, torch.empty_like(x2_hat))}
 
     def forward(self, x1_hat, x2_hat, h_matrix):
         C.require_cuda(x1_hat, x2_hat, h_matrix)

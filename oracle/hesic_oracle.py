@@ -394,6 +394,16 @@ def enhancement(sd, p, x, other_warp):
     return out + x
 
 
+def dsic_independent_en_forward(sd, x1_hat, x2_hat):
+    """ywz/DSIC/mynet6_plus.py:57-100: the DSIC enhancement has no cross-view input (conv1 is 3 -> 32 on x alone)."""
+    def one(p, x):
+        out = F.conv2d(x, *_cw(sd, p + ".conv1"), padding=1)
+        for eb in ("EB1", "EB2", "EB3"):
+            out = _enh_block(sd, f"{p}.{eb}", out)
+        return F.conv2d(out, *_cw(sd, p + ".conv2"), padding=1) + x
+    return {"x1_hat": one("EH1", x1_hat), "x2_hat": one("EH2", x2_hat)}
+
+
 def independent_en_forward(sd, x1_hat, x2_hat, h, align_corners=True):
     size = (x1_hat.shape[-2], x1_hat.shape[-1])
     x1_hat_warp = warp_perspective(x1_hat, h, size, align_corners)

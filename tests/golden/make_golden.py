@@ -198,6 +198,18 @@ def dsic_golden():
     print("dsic", meta["metrics"], meta["metrics_256"])
 
 
+def dsic_en_golden():
+    """mynet6_plus.Independent_EN (the enhancement stage of DSIC_plus, mynet6_plus.py:57-100,1352-1370) at 64x64."""
+    m = ref_harness.load("mynet6_plus")
+    en = m.Independent_EN().eval()
+    en.load_state_dict(synth.synth_state_dict(en, seed=0))
+    x1, x2, _ = synth.stereo_pairs(1, 64, 64, seed=98)
+    with torch.no_grad():
+        o = en(x1, x2)
+    np.savez_compressed(os.path.join(OUT, "dsic_independent_en.npz"), x1_hat=npf(o["x1_hat"]), x2_hat=npf(o["x2_hat"]))
+    print("dsic en", float(o["x1_hat"].abs().mean()))
+
+
 def homography_golden():
     """ywz/mywork/model.py Net (the front-end that produces h_matrix) on two 128x128 gray patches."""
     m = ref_harness.load("model")
@@ -214,6 +226,9 @@ def homography_golden():
 
 
 if __name__ == "__main__":
+    if "--dsic-en-only" in sys.argv:
+        dsic_en_golden()
+        sys.exit(0)
     if "--homography-only" in sys.argv:
         homography_golden()
         sys.exit(0)
@@ -237,4 +252,5 @@ if __name__ == "__main__":
     json.dump({"state_dict_init": tab}, open(os.path.join(OUT, "independent_en.json"), "w"), indent=1, sort_keys=True)
     dsic_golden()
     homography_golden()
+    dsic_en_golden()
     print("done")

@@ -192,3 +192,15 @@ def test_dsic_engine_and_operator_level_second_size(dsic):
             assert abs(m[k] - r[k]) <= 5e-3 * r[k], (name, k, m[k], r[k])
         for k in ("psnr1", "psnr2"):
             assert abs(m[k] - r[k]) <= 0.1, (name, k, m[k], r[k])
+
+
+def test_dsic_plus_enhancement_vs_reference_fixture():
+    """mynet6_plus.Independent_EN (second stage of DSIC_plus) on the fused enhancement kernels."""
+    import mynet6_plus
+    en = mynet6_plus.Independent_EN().eval()
+    en.load_state_dict(synth.synth_state_dict(en, seed=0))
+    x1, x2, _ = synth.stereo_pairs(1, 64, 64, seed=98)
+    out = en.to(DEV)(x1.to(DEV), x2.to(DEV))
+    g = load_npz("dsic_independent_en")
+    assert_close(out["x1_hat"], g["x1_hat"], 1e-4, what="DSIC EN x1")
+    assert_close(out["x2_hat"], g["x2_hat"], 1e-4, what="DSIC EN x2")

@@ -227,3 +227,17 @@ def test_perspective_transform_maps_the_corners():
     Hs = O.h_adjust(512, 512, 256, 256, H.float())
     q = torch.cat([2 * src.double(), torch.ones(3, 4, 1, dtype=torch.float64)], -1) @ Hs.double().transpose(1, 2)
     assert torch.allclose(q[..., :2] / q[..., 2:], 2 * dst.double(), atol=5e-3)
+
+
+def test_dsic_independent_en_oracle_vs_reference_fixture():
+    from hesic_b200 import compat
+    compat.install()
+    import mynet6_plus
+    en = mynet6_plus.Independent_EN().eval()
+    sd = synth.synth_state_dict(en, seed=0)
+    x1, x2, _ = synth.stereo_pairs(1, 64, 64, seed=98)
+    with torch.no_grad():
+        o = O.dsic_independent_en_forward(sd, x1, x2)
+    g = load_npz("dsic_independent_en")
+    assert_close(o["x1_hat"], g["x1_hat"], 1e-5, what="DSIC EN x1")
+    assert_close(o["x2_hat"], g["x2_hat"], 1e-5, what="DSIC EN x2")
