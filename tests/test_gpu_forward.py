@@ -230,3 +230,26 @@ def test_operator_call_after_engine_run_is_a_plain_conv():
                           sd["encoder1.g_a_gdn1.beta"], sd["encoder1.g_a_gdn1.gamma"]), 1e-4, what="stand-alone GDN")
     b = net(x1.to(DEV), x2.to(DEV), h.to(DEV))
     assert torch.equal(a["x1_hat"], b["x1_hat"]) and torch.equal(a["likelihoods"]["y2"], b["likelihoods"]["y2"])
+
+
+def test_forward_kitti_size_vs_oracle():
+    """A KITTI-sized, non-square pair (320 x 1216, ywz/mywork/test3real.py:6): nothing in the path hard-codes 512 x 512.
+    HSIC then Independent_EN, as the driver chains them, against the oracle."""
+    import newnet1
+    net, sd = _model("newnet1")
+    x1, x2, h = synth.stereo_pairs(1, 320, 1216, seed=11)
+    with torch.no_grad():
+        ref = O.hsic_forward(sd, x1, x2, h)
+    out = net(x1.to(DEV), x2.to(DEV), h.to(DEV))
+    m = _check_against(out, ref, x1, x2, what="kitti size")
+    r = synth.rd_metrics(ref, x1, x2)
+    for k in ("bpp", "psnr1", "psnr2"):
+        assert math.isclose(m[k], r[k], rel_tol=2e-3, abs_tol=2e-3), (k, m[k], r[k])
+    en = newnet1.Independent_EN().eval()
+    sd_en = synth.synth_state_dict(en, seed=0)
+    en.load_state_dict(sd_en)
+    with torch.no_grad():
+        ref2 = O.independent_en_forward(sd_en, out["x1_hat"].cpu(), out["x2_hat"].cpu(), h)
+    out2 = en.to(DEV)(out["x1_hat"], out["x2_hat"], h.to(DEV))
+    assert_close(out2["x1_hat"], ref2["x1_hat"], 1e-4, what="EN x1 kitti size")
+    assert_close(out2["x2_hat"], ref2["x2_hat"], 1e-4, what="EN x2 kitti size")
