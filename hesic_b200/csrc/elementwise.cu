@@ -552,6 +552,51 @@ __global__ void __launch_bounds__(256) upsample_kernel(const TView x, const TVie
   tstore(y, b, c, oy, ox, v);
 }
 
+// nn.UpsamplingBilinear2d on channels-last data, four channels per thread: NHWC fp32 or SPLIT in (channel slices
+// allowed), SPLIT or NHWC fp32 out.  Same arithmetic as upsample_kernel (at::native upsample_bilinear2d, align_corners).
+__device__ __forceinline__ float4 ld4_cl(const TView &t, size_t pix, int c) {
+  const size_t o = pix * t.Cs + c;
+  if (t.fmt == HESIC_FMT_NHWC_F32) return __ldg(reinterpret_cast<const float4 *>((const float *)t.p0 + o));
+  const uint2 h = __ldg(reinterpret_cast<const uint2 *>((const __nv_bfloat16 *)t.p0 + o));
+  const uint2 l = __ldg(reinterpret_cast<const uint2 *>((const __nv_bfloat16 *)t.p1 + o));
+  return make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16),
+                     __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
+                     __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16),
+                     __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(256) upsample_cl_kernel(const TView x, const TView y, size_t n4) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int C4 = y.C >> 2;
+  const int cq = (int)(i % C4);
+  size_t r = i / C4;
+  const int ox = (int)(r % y.W); r /= y.W;
+  const int oy = (int)(r % y.H);
+  const int b = (int)(r / y.H);
+  const float sh = y.H > 1 ? (float)(x.H - 1) / (float)(y.H - 1) : 0.f;
+  const float sw = y.W > 1 ? (float)(x.W - 1) / (float)(y.W - 1) : 0.f;
+  const float fy = sh * oy, fx = sw * ox;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int yp = y0 < x.H - 1 ? 1 : 0, xp = x0 < x.W - 1 ? 1 : 0;
+  const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const size_t row0 = ((size_t)b * x.H + y0) * x.W, row1 = ((size_t)b * x.H + y0 + yp) * x.W;
+  const float4 a = ld4_cl(x, row0 + x0, 4 * cq), bq = ld4_cl(x, row0 + x0 + xp, 4 * cq);
+  const float4 c = ld4_cl(x, row1 + x0, 4 * cq), d = ld4_cl(x, row1 + x0 + xp, 4 * cq);
+  const float o[4] = {hy * (hx * a.x + lx * bq.x) + ly * (hx * c.x + lx * d.x), hy * (hx * a.y + lx * bq.y) + ly * (hx * c.y + lx * d.y),
+                      hy * (hx * a.z + lx * bq.z) + ly * (hx * c.z + lx * d.z), hy * (hx * a.w + lx * bq.w) + ly * (hx * c.w + lx * d.w)};
+  const size_t off = (((size_t)b * y.H + oy) * y.W + ox) * y.Cs + 4 * cq;
+  if (y.fmt == HESIC_FMT_NHWC_SPLIT) {
+    __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split_bf16(o[k], hi[k], lo[k]);
+    *reinterpret_cast<uint2 *>((__nv_bfloat16 *)y.p0 + off) = *reinterpret_cast<const uint2 *>(hi);
+    *reinterpret_cast<uint2 *>((__nv_bfloat16 *)y.p1 + off) = *reinterpret_cast<const uint2 *>(lo);
+  } else {
+    *reinterpret_cast<float4 *>((float *)y.p0 + off) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256) convert_kernel(const TView x, const TView y, int op, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -825,6 +870,20 @@ extern "C" int hesic_upsample_bilinear(const hesic_tensor *x, const hesic_tensor
                 "upsample: output shape mismatch");
   size_t n = numel(y);
   if (n == 0) return HESIC_OK;
+  {
+    const int xCs = x->Cs > 0 ? x->Cs : x->C, yCs = y->Cs > 0 ? y->Cs : y->C;
+    const bool xin = x->fmt == HESIC_FMT_NHWC_F32 || x->fmt == HESIC_FMT_NHWC_SPLIT;
+    const bool yout = y->fmt == HESIC_FMT_NHWC_F32 || y->fmt == HESIC_FMT_NHWC_SPLIT;
+    const uintptr_t xa = x->fmt == HESIC_FMT_NHWC_F32 ? 15 : 7, ya = y->fmt == HESIC_FMT_NHWC_F32 ? 15 : 7;
+    const bool al = ((uintptr_t)x->p0 & xa) == 0 && ((uintptr_t)y->p0 & ya) == 0 &&
+                    (x->fmt != HESIC_FMT_NHWC_SPLIT || ((uintptr_t)x->p1 & 7) == 0) &&
+                    (y->fmt != HESIC_FMT_NHWC_SPLIT || ((uintptr_t)y->p1 & 7) == 0);
+    if (xin && yout && al && (x->C & 3) == 0 && (xCs & 3) == 0 && (yCs & 3) == 0) {
+      upsample_cl_kernel<<<nblk(n / 4), 256, 0, as_stream(stream)>>>(view(x), view(y), n / 4);
+      HESIC_LAUNCHED("upsample_cl_kernel");
+      return HESIC_OK;
+    }
+  }
   upsample_kernel<<<nblk(n), 256, 0, as_stream(stream)>>>(view(x), view(y), n);
   HESIC_LAUNCHED("upsample_kernel");
   return HESIC_OK;

@@ -204,3 +204,24 @@ def test_dsic_plus_enhancement_vs_reference_fixture():
     g = load_npz("dsic_independent_en")
     assert_close(out["x1_hat"], g["x1_hat"], 1e-4, what="DSIC EN x1")
     assert_close(out["x2_hat"], g["x2_hat"], 1e-4, what="DSIC EN x2")
+
+
+@pytest.mark.parametrize("scale", [2, 4, 8])
+def test_upsample_channels_last(scale):
+    """nn.UpsamplingBilinear2d (align_corners=True) in the engines' layouts: an NHWC fp32 channel slice (a context volume
+    of the global-context tensor, mynet6_plus.py:269) or SPLIT planes (z_hat, newnet1.py:564) into a SPLIT slice."""
+    from hesic_b200 import _capi as C
+    x = _rand((2, 224, 4, 6), 61)
+    ref = torch.nn.functional.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=True)
+    wide = torch.zeros((2, 4, 6, 672), device=DEV)
+    wide[..., 224:448] = x.permute(0, 2, 3, 1).to(DEV)
+    out = torch.zeros((2, 2, 4 * scale, 6 * scale, 224 + 16), device=DEV, dtype=torch.bfloat16)
+    C.check(C.lib.hesic_upsample_bilinear(C.ref(C.nhwc(wide, 224, 224)), C.ref(C.split(out, 224, 8)), scale, C.stream()))
+    assert_close(_from_split(out, 224, 8), ref, 2e-5, what="upsample NHWC slice -> SPLIT slice")
+    assert float(out[..., :8].float().abs().max()) == 0 and float(out[..., 232:].float().abs().max()) == 0
+    xs = _to_split(x)
+    xq = _from_split(xs).cpu()
+    out2 = torch.zeros((2, 2, 4 * scale, 6 * scale, 224), device=DEV, dtype=torch.bfloat16)
+    C.check(C.lib.hesic_upsample_bilinear(C.ref(C.split(xs)), C.ref(C.split(out2)), scale, C.stream()))
+    assert_close(_from_split(out2), torch.nn.functional.interpolate(xq, scale_factor=scale, mode="bilinear", align_corners=True), 2e-5,
+                 what="upsample SPLIT -> SPLIT")
