@@ -85,6 +85,7 @@ struct Params {
   int w_resident;          // all weight tiles ([tap][kchunk][hi, lo]) are loaded once and stay in smem
   int n_wtiles;            // taps * kchunks (w_resident)
   int wide_n;              // BN == 128: issue Ah.[Wh; Wl] as one N = 256 MMA
+  int stg_sets;            // 1 or 2 staging tile pairs for the TMA-store epilogue (2: a pair does not wait for the previous pair's store)
   int stages;
   uint32_t stage_bytes, b_bytes;
   int n_tasks;
@@ -168,7 +169,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t smem_base = w_base + (p.w_resident ? (uint32_t)p.n_wtiles * 2u * p.b_bytes : 0u);
   const uint32_t b_off = p.w_resident ? 0u : 2u * A_TILE_BYTES;             // B operand inside a stage
   const uint32_t stg_base = smem_base + (uint32_t)p.stages * p.stage_bytes;   // epilogue store staging (tma_store)
-  const uint32_t bar_base = stg_base + (p.tma_store ? (uint32_t)STAGING_BYTES : 0u);
+  const uint32_t bar_base = stg_base + (p.tma_store ? (uint32_t)(STAGING_BYTES * p.stg_sets) : 0u);
   // barrier map (8 B each)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
@@ -338,7 +339,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int txy = p.tiles_x * p.tiles_y;
     const int nchunks = p.BN / 32, npairs = (nchunks + 1) / 2;
     const bool is_issuer = threadIdx.x == 64;
-    const uint32_t row_off = stg_base + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    const uint32_t row_off0 = stg_base + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    uint32_t pair_ctr = 0;   // store pairs issued so far (selects the staging set)
     // activation as max(v, slope * v): slope 1 = none, 0 = ReLU, 0.01 = LeakyReLU
     const float act_slope = p.act == HESIC_ACT_RELU ? 0.f : (p.act == HESIC_ACT_LEAKY_RELU ? 0.01f : 1.f);
     int lt = 0;
@@ -365,7 +367,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (valid && active) store_chunk(p, v, pix, nb);
           return;
         }
-        if (is_issuer) bulk_wait_read<0>();     // the previous pair's tiles have been read by TMA
+        // staging set of this pair; with two sets only the pair before the previous one must have left shared memory
+        const uint32_t stg_set = stg_base + (p.stg_sets == 2 ? (pair_ctr & 1u) * (uint32_t)STAGING_BYTES : 0u);
+        const uint32_t row_off = row_off0 + (stg_set - stg_base);
+        ++pair_ctr;
+        if (is_issuer) {
+          if (p.stg_sets == 2) bulk_wait_read<1>();
+          else bulk_wait_read<0>();
+        }
         epi_bar();
         if (p.out_fmt == HESIC_FMT_NHWC_F32) {
           // one [128 px][32 ch fp32] tile per group
@@ -379,9 +388,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           epi_bar();
           if (is_issuer) {
             const int nb0 = n0 + 2 * i * 32;
-            tma_store_5d(&map_y0, stg_base, c_fold + nb0, mx, ry, my, mb);
+            tma_store_5d(&map_y0, stg_set, c_fold + nb0, mx, ry, my, mb);
             if (2 * i + 1 < nchunks && nb0 + 32 < p.Cout)
-              tma_store_5d(&map_y0, stg_base + A_TILE_BYTES, c_fold + nb0 + 32, mx, ry, my, mb);
+              tma_store_5d(&map_y0, stg_set + A_TILE_BYTES, c_fold + nb0 + 32, mx, ry, my, mb);
             bulk_commit();
           }
         } else {
@@ -403,8 +412,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           epi_bar();
           if (is_issuer) {
             const int c0 = c_fold + n0 + 2 * i * 32;
-            tma_store_5d(&map_y0, stg_base, c0, mx, ry, my, mb);
-            tma_store_5d(&map_y1, stg_base + A_TILE_BYTES, c0, mx, ry, my, mb);
+            tma_store_5d(&map_y0, stg_set, c0, mx, ry, my, mb);
+            tma_store_5d(&map_y1, stg_set + A_TILE_BYTES, c0, mx, ry, my, mb);
             bulk_commit();
           }
         }
@@ -846,8 +855,17 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.tma_store = (!planar && (yCs * esz) % 16 == 0 &&
                  (p.os == 1 || (p.os == 2 && c->Cout % store_ch == 0 && !((y->H | y->W) & 1)))) ? 1 : 0;
   if (getenv("HESIC_TC_DIRECT_STORE")) p.tma_store = 0;
-  const int fixed = 1024 + BAR_BYTES + CHAN_BYTES + (p.tma_store ? STAGING_BYTES : 0) +
-                    (p.w_resident ? p.n_wtiles * 2 * (int)p.b_bytes : 0);
+  int fixed = 1024 + BAR_BYTES + CHAN_BYTES + (p.tma_store ? STAGING_BYTES : 0) +
+              (p.w_resident ? p.n_wtiles * 2 * (int)p.b_bytes : 0);
+  p.stg_sets = 1;
+  if (p.tma_store && !getenv("HESIC_TC_ONE_STAGING")) {
+    // a second staging set where the operand pipeline keeps its depth: short-K layers are epilogue-bound and every store
+    // pair otherwise waits for the previous pair to leave shared memory (r01 profile of the first analysis layer: 11 %)
+    const int st2 = (SMEM_LIMIT - fixed - STAGING_BYTES) / (int)p.stage_bytes;
+    static const int force = getenv("HESIC_TC_TWO_STAGING") ? atoi(getenv("HESIC_TC_TWO_STAGING")) : 0;   // experiment knob
+    const bool want = st2 >= 3 || (p.w_resident && st2 >= 2) || (force == 1 && st2 >= 2 && p.n_phases > 1) || (force == 2 && st2 >= 2);
+    if (want) { p.stg_sets = 2; fixed += STAGING_BYTES; }
+  }
   p.stages = std::min(8, (SMEM_LIMIT - fixed) / (int)p.stage_bytes);
   if (p.stages < 2) { set_error("conv tcgen05: tile does not fit shared memory"); return HESIC_E_UNSUPPORTED; }
   p.n_tasks = p.tiles_x * p.tiles_y * p.tiles_b * p.n_phases * p.n_tiles;
