@@ -76,6 +76,14 @@ _sig = {
     "hesic_build_indexes_channel": ([c_int, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "hesic_build_indexes_scale": ([_TP, c_void_p, c_int, c_float, c_void_p, c_void_p], c_int),
     "hesic_sum_squared_error": ([_TP, _TP, c_void_p, c_void_p], c_int),
+    "hesic_gmm_cdf_tables": ([_TP, _TP, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p], c_int),
+    "hesic_range_encoder_create": ([], c_void_p),
+    "hesic_range_encoder_destroy": ([c_void_p], None),
+    "hesic_range_encoder_push": ([c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int], c_int),
+    "hesic_range_encoder_finish": ([c_void_p, c_void_p, c_int64], c_int64),
+    "hesic_range_decoder_create": ([c_void_p, c_int64], c_void_p),
+    "hesic_range_decoder_destroy": ([c_void_p], None),
+    "hesic_range_decoder_decode": ([c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p], c_int),
     "hesic_pmf_to_quantized_cdf": ([_FP, c_int, c_int, POINTER(c_uint32)], c_int),
     "hesic_rans_encoder_create": ([], c_void_p),
     "hesic_rans_encoder_destroy": ([c_void_p], None),

@@ -256,3 +256,111 @@ extern "C" int hesic_rans_decoder_decode(hesic_rans_decoder *d, const int32_t *i
   }
   return HESIC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Range coder for the file codec of the stereo models (HSIC.compress / decompress, newnet1.py:823-1273; SURVEY.md
+// 8f rank 2).  The reference calls the un-vendored, un-pinned PyPI `range_coder` there
+// (RangeEncoder(path).encode([symbol], cdf) once per latent element, newnet1.py:983-1040), so the byte stream of
+// that package cannot be pinned; this is a self-contained carry-less range coder (64-bit low, 48-bit minimum
+// range, byte renormalisation) with the same calling pattern: one symbol per call against an arbitrary integer
+// cumulative-frequency row whose total need not be a power of two (the reference's rows sum to 65536 only
+// approximately, newnet1.py:974-977).
+namespace {
+constexpr uint64_t kTop = 1ull << 56, kBot = 1ull << 48;
+}
+
+struct hesic_range_encoder {
+  uint64_t low = 0, range = ~0ull;
+  std::vector<uint8_t> out;
+  void put(uint32_t cum, uint32_t freq, uint32_t total) {
+    range /= total;
+    low += cum * range;
+    range *= freq;
+    while ((low ^ (low + range)) < kTop || (range < kBot && ((range = (0 - low) & (kBot - 1)), true))) {
+      out.push_back(static_cast<uint8_t>(low >> 56));
+      low <<= 8;
+      range <<= 8;
+    }
+  }
+};
+
+struct hesic_range_decoder {
+  uint64_t low = 0, range = ~0ull, code = 0;
+  std::vector<uint8_t> in;
+  size_t pos = 0;
+  uint8_t next() { return pos < in.size() ? in[pos++] : 0; }
+};
+
+extern "C" hesic_range_encoder *hesic_range_encoder_create(void) { return new hesic_range_encoder(); }
+extern "C" void hesic_range_encoder_destroy(hesic_range_encoder *e) { delete e; }
+
+extern "C" int hesic_range_encoder_push(hesic_range_encoder *e, const int32_t *symbols, int64_t n, const int32_t *cdfs,
+                                        int cdf_pitch, int cdf_len) {
+  if (!e || n < 0 || (n > 0 && (!symbols || !cdfs)) || cdf_len < 2 || cdf_pitch < cdf_len) {
+    set_error("range_encoder_push: invalid argument");
+    return HESIC_E_INVALID;
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t *row = cdfs + (size_t)i * cdf_pitch;
+    const int32_t s = symbols[i];
+    if (s < 0 || s >= cdf_len - 1 || row[s + 1] <= row[s] || row[0] != 0 || row[cdf_len - 1] <= 0) {
+      set_error("range_encoder_push: symbol %d of element %lld has no probability mass (row length %d)", (int)s, (long long)i,
+                cdf_len);
+      return HESIC_E_INVALID;
+    }
+    e->put((uint32_t)row[s], (uint32_t)(row[s + 1] - row[s]), (uint32_t)row[cdf_len - 1]);
+  }
+  return HESIC_OK;
+}
+
+extern "C" int64_t hesic_range_encoder_finish(hesic_range_encoder *e, uint8_t *out, int64_t out_cap) {
+  if (!e) { set_error("range_encoder_finish: null encoder"); return HESIC_E_INVALID; }
+  const int64_t need = (int64_t)e->out.size() + 8;
+  if (!out || out_cap < need) return need;
+  std::copy(e->out.begin(), e->out.end(), out);
+  uint64_t low = e->low;
+  for (int i = 0; i < 8; ++i) { out[e->out.size() + i] = static_cast<uint8_t>(low >> 56); low <<= 8; }
+  e->out.clear();
+  e->low = 0;
+  e->range = ~0ull;
+  return need;
+}
+
+extern "C" hesic_range_decoder *hesic_range_decoder_create(const uint8_t *stream, int64_t nbytes) {
+  if (nbytes < 0 || (nbytes > 0 && !stream)) { set_error("range_decoder_create: invalid stream"); return nullptr; }
+  hesic_range_decoder *d = new hesic_range_decoder();
+  d->in.assign(stream, stream + nbytes);
+  for (int i = 0; i < 8; ++i) d->code = (d->code << 8) | d->next();
+  return d;
+}
+extern "C" void hesic_range_decoder_destroy(hesic_range_decoder *d) { delete d; }
+
+extern "C" int hesic_range_decoder_decode(hesic_range_decoder *d, int64_t n, const int32_t *cdfs, int cdf_pitch, int cdf_len,
+                                          int32_t *out_symbols) {
+  if (!d || n < 0 || (n > 0 && (!cdfs || !out_symbols)) || cdf_len < 2 || cdf_pitch < cdf_len) {
+    set_error("range_decoder_decode: invalid argument");
+    return HESIC_E_INVALID;
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t *row = cdfs + (size_t)i * cdf_pitch;
+    const uint32_t total = (uint32_t)row[cdf_len - 1];
+    if (row[0] != 0 || row[cdf_len - 1] <= 0) { set_error("range_decoder_decode: malformed cumulative row"); return HESIC_E_INVALID; }
+    d->range /= total;
+    uint64_t v = (d->code - d->low) / d->range;
+    if (v >= total) v = total - 1;                 // corrupt stream: stay inside the table
+    // last index with row[idx] <= v
+    const int32_t *hi = std::upper_bound(row, row + cdf_len, (int32_t)v);
+    int s = (int)(hi - row) - 1;
+    if (s > cdf_len - 2) s = cdf_len - 2;
+    while (s > 0 && row[s + 1] <= row[s]) --s;     // never land on an empty interval
+    out_symbols[i] = s;
+    d->low += (uint64_t)(uint32_t)row[s] * d->range;
+    d->range *= (uint32_t)(row[s + 1] - row[s]);
+    while ((d->low ^ (d->low + d->range)) < kTop || (d->range < kBot && ((d->range = (0 - d->low) & (kBot - 1)), true))) {
+      d->code = (d->code << 8) | d->next();
+      d->low <<= 8;
+      d->range <<= 8;
+    }
+  }
+  return HESIC_OK;
+}

@@ -684,6 +684,73 @@ __global__ void __launch_bounds__(256) indexes_scale_kernel(const TView sc, cons
   out[i] = idx;
 }
 
+// ---------------------------------------------------------------------------------------------
+// File codec (HSIC.compress / decompress, newnet1.py:934-978): per latent element the integer cumulative-frequency
+// row of its K-component mixture.  Thread = element; the arithmetic follows the reference's op sequence in fp32
+// (torch elementwise ops for the pmf, then numpy: clip, pairwise-summed normalisation, round half even, running sum).
+constexpr int CDF_MAX_S = 129;   // 2 * minmax + 1 <= 129
+
+// numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src: pairwise_sum) for a contiguous fp32 vector
+__device__ float np_pairwise_sum(const float *a, int n) {
+  if (n < 8) {
+    float res = 0.f;
+    for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+  }
+  if (n <= 128) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __fadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+}
+
+__global__ void __launch_bounds__(128) gmm_cdf_kernel(const TView scales, const TView means, const float *__restrict__ weights,
+                                                     int K, int M, const int32_t *__restrict__ channels, int n_channels,
+                                                     int minmax, float scale_bound, int32_t *__restrict__ out) {
+  const int HW = scales.H * scales.W;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_channels * HW) return;
+  const int ci = e / HW, pos = e - ci * HW;
+  const int c = channels[ci], yy = pos / scales.W, xx = pos - yy * scales.W;
+  const int S = 2 * minmax + 1;
+  float pmf[CDF_MAX_S];
+  for (int k = 0; k < K; ++k) {
+    const int ck = k * M + c;
+    const float mu = __fadd_rn(tload(means, 0, ck, yy, xx), (float)minmax);      // means + minmax  (newnet1.py:950)
+    const float sc = fmaxf(tload(scales, 0, ck, yy, xx), scale_bound);           // lower_bound_scale
+    const float w = weights[ck];
+    for (int sidx = 0; sidx < S; ++sidx) {
+      const float v = fabsf(__fsub_rn((float)sidx, mu));
+      const float up = std_cumulative(__fdiv_rn(__fsub_rn(0.5f, v), sc));
+      const float lo = std_cumulative(__fdiv_rn(__fsub_rn(-0.5f, v), sc));
+      const float term = __fmul_rn(__fsub_rn(up, lo), w);
+      pmf[sidx] = k == 0 ? term : __fadd_rn(pmf[sidx], term);
+    }
+  }
+  for (int sidx = 0; sidx < S; ++sidx) pmf[sidx] = fminf(fmaxf(pmf[sidx], 1.0f / 65536.0f), 1.0f);   // np.clip
+  const float tot = np_pairwise_sum(pmf, S);
+  int32_t *row = out + (size_t)e * (S + 1);
+  float acc = 0.f;
+  row[0] = 0;
+  for (int sidx = 0; sidx < S; ++sidx) {
+    const float q = rintf(__fmul_rn(__fdiv_rn(pmf[sidx], tot), 65536.0f));       // np.round(pmf / sum * 65536)
+    acc = __fadd_rn(acc, q);                                                     // np.add.accumulate (fp32)
+    row[sidx + 1] = (int32_t)acc;
+  }
+}
+
 // both tensors dense fp32 in the same layout: 128-bit loads, fp32 squares folded into fp64 four at a time
 __global__ void __launch_bounds__(256) sse_dense_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, double *acc,
                                                        size_t n4) {
@@ -952,6 +1019,26 @@ extern "C" int hesic_build_indexes_scale(const hesic_tensor *scales, const float
   indexes_scale_kernel<<<nblk(n), 256, n_table * sizeof(float), as_stream(stream)>>>(view(scales), table, n_table,
                                                                                     scale_bound, out, n);
   HESIC_LAUNCHED("indexes_scale_kernel");
+  return HESIC_OK;
+}
+
+extern "C" int hesic_gmm_cdf_tables(const hesic_tensor *scales, const hesic_tensor *means, const float *weights, int K, int M,
+                                    const int32_t *channels, int n_channels, int minmax, float scale_bound,
+                                    int32_t *out_cdf, void *stream) {
+  int r;
+  if ((r = check_tensor(scales, "cdf tables scales")) != HESIC_OK) return r;
+  if ((r = check_tensor(means, "cdf tables means")) != HESIC_OK) return r;
+  HESIC_REQUIRE(weights && out_cdf && (channels || n_channels == 0), "cdf tables: null argument");
+  HESIC_REQUIRE(K >= 1 && M >= 1 && scales->C == K * M && means->C == K * M, "cdf tables: scales/means need K*M channels");
+  HESIC_REQUIRE(scales->B == 1 && means->B == 1 && means->H == scales->H && means->W == scales->W,
+                "cdf tables: one image at a time (as the reference's codec), scales and means of the same size");
+  HESIC_REQUIRE(minmax >= 1 && 2 * minmax + 1 <= CDF_MAX_S, "cdf tables: minmax must be in [1, %d]", (CDF_MAX_S - 1) / 2);
+  HESIC_REQUIRE(n_channels >= 0 && n_channels <= M, "cdf tables: bad channel count");
+  const int n = n_channels * scales->H * scales->W;
+  if (n == 0) return HESIC_OK;
+  gmm_cdf_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(view(scales), view(means), weights, K, M, channels, n_channels,
+                                                                 minmax, scale_bound, out_cdf);
+  HESIC_LAUNCHED("gmm_cdf_kernel");
   return HESIC_OK;
 }
 

@@ -357,3 +357,72 @@ def dense_warp(h1, cost):
     out = torch.empty_like(h1)
     C.check(_lib.hesic_dense_warp(C.ref(C.nchw(h1)), C.ref(C.nchw(cost)), C.ref(C.nchw(out)), C.stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# file codec of the stereo models (newnet1.py:823-1273)
+def gmm_cdf_tables(scales, means, weights, K, channels, minmax, scale_bound=0.11):
+    """Per-element cumulative-frequency rows of the K-component mixture (newnet1.py:934-978) for the given channels of a
+    [1, K*M, H, W] parameter set: int32 [len(channels)*H*W, 2*minmax+2] on the device, rows in (channel, h, w) order."""
+    scales, means = _f32(scales), _f32(means)
+    w = _f32(weights).reshape(-1)
+    M = scales.shape[1] // K
+    if scales.shape[0] != 1 or w.numel() != K * M:
+        raise ValueError("gmm_cdf_tables: one image at a time, weights with K*M entries")
+    ch = torch.as_tensor(np.asarray(channels, dtype=np.int32).reshape(-1), device=scales.device)
+    n = int(ch.numel()) * scales.shape[2] * scales.shape[3]
+    out = torch.empty((n, 2 * int(minmax) + 2), device=scales.device, dtype=torch.int32)
+    C.check(_lib.hesic_gmm_cdf_tables(C.ref(C.nchw(scales)), C.ref(C.nchw(means)), C.ptr(w), int(K), int(M), C.ptr(ch),
+                                      int(ch.numel()), int(minmax), float(scale_bound), C.ptr(out), C.stream()))
+    return out
+
+
+class RangeEncoderHandle:
+    """Host range coder (csrc/coder.cpp): one symbol per cumulative-frequency row."""
+
+    def __init__(self):
+        self.h = _lib.hesic_range_encoder_create()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.hesic_range_encoder_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def push(self, symbols, cdfs):
+        s, c = _i32(symbols).reshape(-1), _i32(cdfs)
+        if c.ndim != 2 or c.shape[0] != s.size:
+            raise ValueError("range coder: one cumulative row per symbol")
+        C.check(_lib.hesic_range_encoder_push(self.h, s.ctypes.data, s.size, c.ctypes.data, c.shape[1], c.shape[1]))
+
+    def finish(self):
+        n = _lib.hesic_range_encoder_finish(self.h, None, 0)
+        if n < 0:
+            C.check(int(n))
+        buf = np.empty(n, dtype=np.uint8)
+        assert _lib.hesic_range_encoder_finish(self.h, buf.ctypes.data, n) == n
+        return buf.tobytes()
+
+
+class RangeDecoderHandle:
+    def __init__(self, data):
+        self._buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        self.h = _lib.hesic_range_decoder_create(self._buf.ctypes.data if self._buf.size else None, self._buf.size)
+        if not self.h:
+            raise ValueError(C.last_error())
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.hesic_range_decoder_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def decode(self, cdfs):
+        c = _i32(cdfs)
+        out = np.empty(c.shape[0], dtype=np.int32)
+        C.check(_lib.hesic_range_decoder_decode(self.h, c.shape[0], c.ctypes.data, c.shape[1], c.shape[1], out.ctypes.data))
+        return out

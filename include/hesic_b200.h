@@ -244,6 +244,34 @@ int hesic_rans_decoder_decode(hesic_rans_decoder *d, const int32_t *indexes, int
                               int n_cdfs, int cdf_pitch, const int32_t *cdf_sizes, const int32_t *offsets,
                               int32_t *out_symbols);
 
+/* ---------------------------------------------------------------------------------------------
+ * File codec of the stereo models (HSIC.compress / decompress, ywz/mywork/newnet1.py:823-1273).
+ * Device side: per latent element, the 16-bit cumulative-frequency row the reference builds on the host in a Python
+ * double loop (newnet1.py:934-978): pmf[s] = sum_k w_k (Phi((.5-|s-(mu_k+minmax)|)/sigma_k) - Phi((-.5-|..|)/sigma_k)),
+ * s = 0..2*minmax, sigma_k = max(sigma_k, bound); clip to [1/65536, 1]; pmf / sum(pmf) * 65536 (fp32, numpy's pairwise
+ * summation order); round half even; cumulative sum.  scales / means: [1, K*M, H, W] (any layout), weights: dev fp32
+ * [K*M]; channels: dev int32 [n_channels] (the non-zero channels, newnet1.py:882-886).  out_cdf: dev int32
+ * [n_channels*H*W, 2*minmax+2], rows in the coding order (channel, h, w). */
+int hesic_gmm_cdf_tables(const hesic_tensor *scales, const hesic_tensor *means, const float *weights, int K, int M,
+                         const int32_t *channels, int n_channels, int minmax, float scale_bound, int32_t *out_cdf,
+                         void *stream);
+/* Host range coder with the calling pattern of the un-vendored PyPI `range_coder` the reference uses there (one
+ * symbol per cumulative row, totals need not be powers of two).  Its byte stream is this library's own (carry-less
+ * range coder, 64-bit low, byte renormalisation): the reference's package is neither vendored nor pinned.
+ * cdfs: host int32 [n, cdf_pitch], row i = cumulative frequencies (cdf_len entries, first 0) of element i. */
+typedef struct hesic_range_encoder hesic_range_encoder;
+hesic_range_encoder *hesic_range_encoder_create(void);
+void hesic_range_encoder_destroy(hesic_range_encoder *e);
+int hesic_range_encoder_push(hesic_range_encoder *e, const int32_t *symbols, int64_t n, const int32_t *cdfs, int cdf_pitch,
+                             int cdf_len);
+/* returns the stream length; writes it (and resets the encoder) if out_cap is large enough */
+int64_t hesic_range_encoder_finish(hesic_range_encoder *e, uint8_t *out, int64_t out_cap);
+typedef struct hesic_range_decoder hesic_range_decoder;
+hesic_range_decoder *hesic_range_decoder_create(const uint8_t *stream, int64_t nbytes);
+void hesic_range_decoder_destroy(hesic_range_decoder *d);
+int hesic_range_decoder_decode(hesic_range_decoder *d, int64_t n, const int32_t *cdfs, int cdf_pitch, int cdf_len,
+                               int32_t *out_symbols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -413,6 +413,40 @@ def independent_en_forward(sd, x1_hat, x2_hat, h, align_corners=True):
 
 
 # ----------------------------------------------------------------------------
+# File codec of the stereo models (newnet1.py:934-978 / 1135-1180) -- SURVEY 8f rank 2.  The reference evaluates the
+# pmf with torch ops (on 'cuda:0', hard-coded) and the integer table with numpy on the host; this follows the same
+# op sequence on the CPU.  `range_coder` itself is un-vendored and un-pinned: parity of the byte stream is unpinned.
+def codec_cdf_tables(scales, means, weights, K, channels, minmax, scale_bound=0.11):
+    """-> int array [len(channels)*H*W, 2*minmax+2]: per latent element the cumulative-frequency row the reference passes
+    to RangeEncoder.encode / RangeDecoder.decode, rows in the coding order (channel, h, w)."""
+    import numpy as np
+    M = scales.shape[1] // K
+    H, W = scales.shape[-2:]
+    S = 2 * minmax + 1
+    samples = torch.arange(0, S, dtype=torch.float32).reshape(S, 1, 1).expand(S, H, W)
+    w_all = weights.reshape(-1)
+    rows = []
+    for ch in channels:
+        idx = [int(ch) + k * M for k in range(K)]
+        sigma, mu = scales[0, idx], means[0, idx] + minmax
+        pmf = None
+        for k in range(K):
+            values = torch.abs(samples - mu[k])
+            sc = torch.max(sigma[k], torch.tensor([scale_bound]))
+            upper = std_cumulative((0.5 - values) / sc)
+            lower = std_cumulative((-0.5 - values) / sc)
+            term = (upper - lower) * w_all[idx[k]]
+            pmf = term if pmf is None else pmf + term
+        pmf = pmf.numpy()
+        for h in range(H):
+            for w in range(W):
+                p = np.clip(pmf[:, h, w], 1.0 / 65536, 1.0)
+                p = np.round(p / np.sum(p) * 65536)
+                rows.append([0] + [int(v) for v in np.add.accumulate(p)])
+    return np.asarray(rows, dtype=np.int64).reshape(-1, S + 1)
+
+
+# ----------------------------------------------------------------------------
 # Homography front-end (ywz/mywork/model.py:53-111; test3real.py:171-181) -- SURVEY 8f rank 3
 def homography_net_forward(sd, a, b):
     """Net.forward: four Blocks (conv3x3, ReLU, conv3x3, ReLU, [MaxPool 2x2]) then Flatten, FC 1024, ReLU, FC 8
