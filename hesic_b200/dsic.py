@@ -190,44 +190,106 @@ class DSIC(CompressionModel):
             raise NotImplementedError("hesic_b200: DSIC.forward is the inference path; call .eval() first")
         return self.hesic_engine.forward(x1, x2)
 
+    def _analysis_oplevel(self, x1, x2):
+        """Everything up to the quantised latents (mynet6_plus.py:675-723 / 799-845), module by module.  z is passed
+        through ``code_z`` (forward: the bottleneck's likelihood path; codec: compress + decompress)."""
+        cat = lambda a, b: torch.cat((a, b), dim=-3)
+        y1, g1_1, g1_2, g1_3 = self.encoder1(x1)
+        z1 = self._h_a1(y1)
+        return y1, (g1_1, g1_2, g1_3), z1, cat
+
+    def _view2_analysis_oplevel(self, x2, g1, ctx, cat):
+        a1 = self.pic2_g_a_gdn1(self.pic2_g_a_conv1(x2))
+        w1 = self._warp1(g1[0], self._cost_volume1(g1[0], a1, ctx[0]))
+        a2 = self.pic2_g_a_gdn2(self.pic2_g_a_conv2(cat(w1, a1)))
+        w2 = self._warp2(g1[1], self._cost_volume2(g1[1], a2, ctx[1]))
+        a3 = self.pic2_g_a_gdn3(self.pic2_g_a_conv3(cat(w2, a2)))
+        w3 = self._warp3(g1[2], self._cost_volume3(g1[2], a3, ctx[2]))
+        return self.pic2_g_a_conv4(cat(w3, a3))
+
+    def _view2_synthesis_oplevel(self, y2_hat, g1_dec, ctx, cat):
+        g1_4, g1_5, g1_6 = g1_dec
+        s1 = self.pic2_g_s_gdn1(self.pic2_g_s_conv1(y2_hat))
+        w4 = self._warp4(g1_4, self._cost_volume4(g1_4, s1, ctx[2]))
+        s2 = self.pic2_g_s_gdn2(self.pic2_g_s_conv2(cat(w4, s1)))
+        w5 = self._warp5(g1_5, self._cost_volume5(g1_5, s2, ctx[1]))
+        s3 = self.pic2_g_s_gdn3(self.pic2_g_s_conv3(cat(w5, s2)))
+        w6 = self._warp6(g1_6, self._cost_volume6(g1_6, s3, ctx[0]))
+        return self.pic2_g_s_conv4(cat(w6, s3))
+
     def forward_operator_level(self, x1, x2):
         if self.training:
             raise NotImplementedError("hesic_b200: DSIC.forward is the inference path; call .eval() first")
         C.require_cuda(x1, x2)
-        cat = lambda a, b: torch.cat((a, b), dim=-3)
         with torch.no_grad():
-            y1, g1_1, g1_2, g1_3 = self.encoder1(x1)
-            z1_hat, z1_lik = self.entropy_bottleneck1(self._h_a1(y1))
+            y1, g1, z1, cat = self._analysis_oplevel(x1, x2)
+            z1_hat, z1_lik = self.entropy_bottleneck1(z1)
             y1_hat, y1_lik = self.gaussian1(y1, *self._h_s1(z1_hat))
             x1_hat, g1_4, g1_5, g1_6 = self.decoder1(y1_hat)
             ctx = self._global_context(y1_hat)
-
-            a1 = self.pic2_g_a_gdn1(self.pic2_g_a_conv1(x2))
-            w1 = self._warp1(g1_1, self._cost_volume1(g1_1, a1, ctx[0]))
-            a2 = self.pic2_g_a_gdn2(self.pic2_g_a_conv2(cat(w1, a1)))
-            w2 = self._warp2(g1_2, self._cost_volume2(g1_2, a2, ctx[1]))
-            a3 = self.pic2_g_a_gdn3(self.pic2_g_a_conv3(cat(w2, a2)))
-            w3 = self._warp3(g1_3, self._cost_volume3(g1_3, a3, ctx[2]))
-            y2 = self.pic2_g_a_conv4(cat(w3, a3))
-
+            y2 = self._view2_analysis_oplevel(x2, g1, ctx, cat)
             z2_hat, z2_lik = self.entropy_bottleneck2(self._h_a2(y2))
             y2_hat, y2_lik = self.gaussian2(y2, *self._h_s2(z2_hat, y1_hat))
-
-            s1 = self.pic2_g_s_gdn1(self.pic2_g_s_conv1(y2_hat))
-            w4 = self._warp4(g1_4, self._cost_volume4(g1_4, s1, ctx[2]))
-            s2 = self.pic2_g_s_gdn2(self.pic2_g_s_conv2(cat(w4, s1)))
-            w5 = self._warp5(g1_5, self._cost_volume5(g1_5, s2, ctx[1]))
-            s3 = self.pic2_g_s_gdn3(self.pic2_g_s_conv3(cat(w5, s2)))
-            w6 = self._warp6(g1_6, self._cost_volume6(g1_6, s3, ctx[0]))
-            x2_hat = self.pic2_g_s_conv4(cat(w6, s3))
+            x2_hat = self._view2_synthesis_oplevel(y2_hat, (g1_4, g1_5, g1_6), ctx, cat)
         return {"x1_hat": x1_hat, "x2_hat": x2_hat,
                 "likelihoods": {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}}
 
-    def compress(self, *args, **kwargs):
-        raise NotImplementedError("hesic_b200: DSIC.compress/decompress depend on the un-vendored `range_coder` "
-                                  "package (SURVEY.md 8f); the forward path is implemented")
+    def _quantize(self, inputs, mode, means=None):
+        return self.gaussian1._quantize(inputs, mode, means)
 
-    decompress = compress
+    def compress(self, x1, x2, output_name, output_path=""):
+        """mynet6_plus.py:799-1126: same ``.npz`` / ``.bin`` layout and table arithmetic as HSIC.compress (SURVEY.md 8f rank 4);
+        the .bin stream is this library's own range coder (``range_coder`` is un-vendored: parity unpinned)."""
+        import os
+        from .stereo import codec_write
+        if self.training:
+            raise NotImplementedError("hesic_b200: compress() is an inference path; call .eval() first")
+        C.require_cuda(x1, x2)
+        if x1.shape[0] != 1:
+            raise ValueError("DSIC.compress codes one stereo pair per call, as the reference does")
+        with torch.no_grad():
+            y1, g1, z1, cat = self._analysis_oplevel(x1, x2)
+            z1s = self.entropy_bottleneck1.compress(z1)
+            z1_hat = self.entropy_bottleneck1.decompress(z1s, z1.size()[-2:])
+            gmm1 = self._h_s1(z1_hat)
+            y1_hat = self._quantize(y1, "dequantize", means=None)
+            ctx = self._global_context(y1_hat)
+            y2 = self._view2_analysis_oplevel(x2, g1, ctx, cat)
+            z2 = self._h_a2(y2)
+            z2s = self.entropy_bottleneck2.compress(z2)
+            z2_hat = self.entropy_bottleneck2.decompress(z2s, z2.size()[-2:])
+            gmm2 = self._h_s2(z2_hat, y1_hat)
+            y2_hat = self._quantize(y2, "dequantize", means=None)
+            out1, out2, delta = codec_write(self, x1.shape[2:], [(y1_hat, gmm1, z1s), (y2_hat, gmm2, z2s)], output_name, output_path)
+        num_pixels = x1.shape[2] * x1.shape[3] * 2
+        return {"bpp_real": (os.path.getsize(out1) + os.path.getsize(out2)) * 8 / num_pixels, "enctime": delta,
+                "y1_hat": y1_hat, "y2_hat": y2_hat, "z1_hat": z1_hat, "z2_hat": z2_hat}
+
+    def decompress(self, device, output_name, output_path=""):
+        """mynet6_plus.py:1129-1350."""
+        import time
+        from .stereo import codec_code_view, codec_read
+        if self.training:
+            raise NotImplementedError("hesic_b200: decompress() is an inference path; call .eval() first")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("hesic_b200: DSIC.decompress needs the model on a CUDA device (no CPU fallback)")
+        with torch.no_grad():
+            size, heads, dec = codec_read(self, output_name, output_path)
+            y_shape = [v // 16 for v in size]
+            z_shape = [v // 4 for v in y_shape]
+            start = time.time()
+            z1_hat = self.entropy_bottleneck1.decompress([heads[0][0]], z_shape)
+            z2_hat = self.entropy_bottleneck2.decompress([heads[1][0]], z_shape)
+            y1_hat = torch.zeros((1, self.M, *y_shape), device=dev)
+            y2_hat = torch.zeros((1, self.M, *y_shape), device=dev)
+            codec_code_view(self, dec, y1_hat, self._h_s1(z1_hat), heads[0][1], heads[0][2], decode=True)
+            x1_hat, g1_4, g1_5, g1_6 = self.decoder1(y1_hat)
+            codec_code_view(self, dec, y2_hat, self._h_s2(z2_hat, y1_hat), heads[1][1], heads[1][2], decode=True)
+            ctx = self._global_context(y1_hat)
+            x2_hat = self._view2_synthesis_oplevel(y2_hat, (g1_4, g1_5, g1_6), ctx, lambda a, b: torch.cat((a, b), dim=-3))
+        return {"x1_hat": x1_hat, "x2_hat": x2_hat, "y1_hat": y1_hat, "y2_hat": y2_hat, "z1_hat": z1_hat, "z2_hat": z2_hat,
+                "dectime": time.time() - start}
 
 
 class Enhancement_Block(nn.Module):

@@ -256,6 +256,67 @@ class Decoder2(nn.Module):
         return self.after_conv(torch.cat((x, x1_hat_warp), dim=-3))
 
 
+# ---------------------------------------------------------------------------------------------
+# file-codec helpers shared by HSIC and DSIC (newnet1.py:870-1066,1069-1273; mynet6_plus.py:799-1350)
+def codec_code_view(model, coder, y_hat, gmm, minmax, channels, decode):
+    """Range-code (or decode into) the non-zero channels of one view: the per-element cumulative rows come from the
+    device (hesic_gmm_cdf_tables), the coder runs on the host (newnet1.py:934-985 / 1135-1181)."""
+    if len(channels) == 0:
+        return
+    sigma, means, weights = gmm
+    tables = F.gmm_cdf_tables(sigma, means, weights, model.K, channels, minmax, model.gaussian1._scale_bound_value())
+    tables = tables.cpu().numpy()
+    Hy, Wy = y_hat.shape[-2:]
+    ch = torch.as_tensor(np.asarray(channels, dtype=np.int64), device=y_hat.device)
+    if decode:
+        sym = torch.from_numpy(coder.decode(tables).astype(np.float32) - minmax).reshape(len(channels), Hy, Wy)
+        y_hat[0, ch] = sym.to(y_hat.device)
+    else:
+        coder.push((y_hat[0, ch] + minmax).to(torch.int32).reshape(-1).cpu().numpy(), tables)
+
+
+def codec_write(model, shape_hw, views, output_name, output_path):
+    """views = [(y_hat, gmm, z_strings)] * 2 -> ``<name>.npz`` (header, newnet1.py:877-906) and ``<name>.bin`` (range-coded
+    y1 then y2); returns (path1, path2, seconds spent entropy coding)."""
+    import time
+    out1 = os.path.join(output_path, str(output_name) + ".npz")
+    out2 = os.path.join(output_path, str(output_name) + ".bin")
+    heads = []
+    with open(out1, "wb") as f:
+        f.write(np.array(shape_hw, dtype=np.uint16).tobytes())
+        for y_hat, _, zs in views:
+            yi = y_hat[0].to(torch.int64)
+            flag = (yi.abs().sum(dim=(1, 2)) > 0).cpu().numpy().astype(np.uint8)
+            minmax = int(max(int(yi.max().abs()), int(yi.min().abs()), 1))
+            if len(zs[0]) > 65535 or minmax > 64:
+                raise ValueError("compress: z string or symbol range exceeds the reference's uint16 / table header")
+            f.write(np.array([len(zs[0]), minmax], dtype=np.uint16).tobytes())
+            f.write(np.packbits(flag).tobytes())
+            f.write(zs[0])
+            heads.append((np.flatnonzero(flag), minmax))
+    start = time.time()
+    enc = F.RangeEncoderHandle()
+    for (y_hat, gmm, _), (channels, minmax) in zip(views, heads):
+        codec_code_view(model, enc, y_hat, gmm, minmax, channels, decode=False)
+    with open(out2, "wb") as f:
+        f.write(enc.finish())
+    return out1, out2, time.time() - start
+
+
+def codec_read(model, output_name, output_path):
+    """-> image size (H, W), [(z string, minmax, non-zero channels)] * 2, range decoder over ``<name>.bin``."""
+    with open(os.path.join(output_path, str(output_name) + ".npz"), "rb") as f:
+        x_shape = np.frombuffer(f.read(4), dtype=np.uint16)
+        heads = []
+        for _ in range(2):
+            length, minmax = (int(v) for v in np.frombuffer(f.read(4), dtype=np.uint16))
+            flag = np.unpackbits(np.frombuffer(f.read(model.M // 8), dtype=np.uint8))
+            heads.append((f.read(length), minmax, np.flatnonzero(flag)))
+    with open(os.path.join(output_path, str(output_name) + ".bin"), "rb") as f:
+        dec = F.RangeDecoderHandle(f.read())
+    return (int(x_shape[0]), int(x_shape[1])), heads, dec
+
+
 class _HSICBase(CompressionModel):
     _variant = "newnet1"
 
@@ -329,85 +390,38 @@ class _HSICBase(CompressionModel):
         x1_warp_aftercodec = F.warp_perspective(x1_hat, h_matrix, size)
         return self.gaussian1._quantize(self.encoder1(x1_warp_aftercodec)[0], "dequantize")
 
-    def _code_view(self, coder, y_hat, gmm, minmax, channels, decode):
-        """Range-code (or decode into) the non-zero channels of one view: the per-element cumulative rows come from
-        the device (hesic_gmm_cdf_tables), the coder runs on the host (newnet1.py:934-985 / 1135-1181)."""
-        if len(channels) == 0:
-            return
-        sigma, means, weights = gmm
-        tables = F.gmm_cdf_tables(sigma, means, weights, self.K, channels, minmax, self.gaussian1._scale_bound_value())
-        tables = tables.cpu().numpy()
-        Hy, Wy = y_hat.shape[-2:]
-        if decode:
-            sym = torch.from_numpy(coder.decode(tables).astype(np.float32) - minmax).reshape(len(channels), Hy, Wy)
-            y_hat[0, torch.as_tensor(np.asarray(channels, dtype=np.int64), device=y_hat.device)] = sym.to(y_hat.device)
-        else:
-            sel = y_hat[0, torch.as_tensor(np.asarray(channels, dtype=np.int64), device=y_hat.device)]
-            coder.push((sel + minmax).to(torch.int32).reshape(-1).cpu().numpy(), tables)
-
     def compress(self, x1, x2, h_matrix, output_name, output_path="", device="cpu"):
         """newnet1.py:823-1066: writes ``<name>.npz`` (sizes, z strings, non-zero-channel flags, symbol range) and
         ``<name>.bin`` (range-coded y1 then y2).  File layout as in the reference; the .bin byte stream is this
         library's own range coder (the reference's ``range_coder`` package is un-vendored and un-pinned)."""
-        import time
         if self._variant == "joint":
             raise NotImplementedError("hesic_b200: the autoregressive codec of HESIC+ (newnet1_joint.py:793-1321) is not built")
         (y1_hat, gmm1, z1_hat, z1s), (y2_hat, gmm2, z2_hat, z2s), _ = self._codec_front(x1, x2, h_matrix)
-        out1 = os.path.join(output_path, str(output_name) + ".npz")
-        out2 = os.path.join(output_path, str(output_name) + ".bin")
-        views = []
-        with open(out1, "wb") as f:
-            f.write(np.array(x1.shape[2:], dtype=np.uint16).tobytes())
-            for y_hat, zs in ((y1_hat, z1s), (y2_hat, z2s)):
-                yi = y_hat[0].to(torch.int64)
-                flag = (yi.abs().sum(dim=(1, 2)) > 0).cpu().numpy().astype(np.uint8)
-                minmax = int(max(int(yi.max().abs()), int(yi.min().abs()), 1))
-                if len(zs[0]) > 65535 or minmax > 64:
-                    raise ValueError("HSIC.compress: z string or symbol range exceeds the reference's uint16 / table header")
-                f.write(np.array([len(zs[0]), minmax], dtype=np.uint16).tobytes())
-                f.write(np.packbits(flag).tobytes())
-                f.write(zs[0])
-                views.append((np.flatnonzero(flag), minmax))
-        start = time.time()
-        enc = F.RangeEncoderHandle()
-        for (y_hat, gmm), (channels, minmax) in zip(((y1_hat, gmm1), (y2_hat, gmm2)), views):
-            self._code_view(enc, y_hat, gmm, minmax, channels, decode=False)
-        with open(out2, "wb") as f:
-            f.write(enc.finish())
-        delta = time.time() - start
+        out1, out2, delta = codec_write(self, x1.shape[2:], [(y1_hat, gmm1, z1s), (y2_hat, gmm2, z2s)], output_name, output_path)
         num_pixels = x1.shape[2] * x1.shape[3] * 2
         return {"bpp_real": (os.path.getsize(out1) + os.path.getsize(out2)) * 8 / num_pixels, "enctime": delta,
                 "bpp_side": os.path.getsize(out1) * 8 / num_pixels,
                 "y1_hat": y1_hat, "y2_hat": y2_hat, "z1_hat": z1_hat, "z2_hat": z2_hat}
 
     def decompress(self, x1, x2, h_matrix, output_name, output_path="", device="cpu"):
-        """newnet1.py:1069-1273 (x1 / x2 are only consulted for the image size and device, as in the reference)."""
+        """newnet1.py:1069-1273 (x1 / x2 are only consulted for the device, as in the reference)."""
         import time
         if self._variant == "joint":
             raise NotImplementedError("hesic_b200: the autoregressive codec of HESIC+ (newnet1_joint.py:793-1321) is not built")
         C.require_cuda(x1, h_matrix)
         dev = x1.device
-        with open(os.path.join(output_path, str(output_name) + ".npz"), "rb") as f:
-            x_shape = np.frombuffer(f.read(4), dtype=np.uint16)
-            heads = []
-            for _ in range(2):
-                length, minmax = (int(v) for v in np.frombuffer(f.read(4), dtype=np.uint16))
-                flag = np.unpackbits(np.frombuffer(f.read(self.M // 8), dtype=np.uint8))
-                heads.append((f.read(length), minmax, np.flatnonzero(flag)))
-        with open(os.path.join(output_path, str(output_name) + ".bin"), "rb") as f:
-            dec = F.RangeDecoderHandle(f.read())
-        y_shape = [int(v) // 16 for v in x_shape]
+        size, heads, dec = codec_read(self, output_name, output_path)
+        y_shape = [v // 16 for v in size]
         z_shape = [v // 4 for v in y_shape]
-        size = (int(x_shape[0]), int(x_shape[1]))
         start = time.time()
         z1_hat = self.entropy_bottleneck1.decompress([heads[0][0]], z_shape)
         z2_hat = self.entropy_bottleneck2.decompress([heads[1][0]], z_shape)
         y1_hat = torch.zeros((1, self.M, *y_shape), device=dev)
         y2_hat = torch.zeros((1, self.M, *y_shape), device=dev)
-        self._code_view(dec, y1_hat, self._h_s1(z1_hat), heads[0][1], heads[0][2], decode=True)
+        codec_code_view(self, dec, y1_hat, self._h_s1(z1_hat), heads[0][1], heads[0][2], decode=True)
         x1_hat = self.decoder1(y1_hat)[0]
         gmm2 = self._h_s2(z2_hat, self._codec_condition(x1_hat, y1_hat, h_matrix, size))
-        self._code_view(dec, y2_hat, gmm2, heads[1][1], heads[1][2], decode=True)
+        codec_code_view(self, dec, y2_hat, gmm2, heads[1][1], heads[1][2], decode=True)
         x1_hat_warp = F.warp_perspective(x1_hat, h_matrix, size)
         x2_hat = self.decoder2(y2_hat, x1_hat_warp)
         return {"x1_hat": x1_hat, "x2_hat": x2_hat, "y1_hat": y1_hat, "y2_hat": y2_hat, "z1_hat": z1_hat, "z2_hat": z2_hat,

@@ -80,3 +80,24 @@ def test_compress_argument_errors(tmp_path):
         net.compress(x, x, torch.eye(3, device=DEV).repeat(2, 1, 1), "p", output_path=str(tmp_path))
     with pytest.raises(NotImplementedError):
         newnet1_joint.HSIC(128, 192, 5).eval().to(DEV).compress(x[:1], x[:1], torch.eye(3, device=DEV)[None], "p", output_path=str(tmp_path))
+
+
+def test_dsic_compress_decompress_round_trip(tmp_path):
+    """mynet6_plus.DSIC.compress / decompress (mynet6_plus.py:799-1350): same file layout and tables."""
+    import mynet6_plus
+    net = mynet6_plus.DSIC(128, 192, 21, 32, 5).eval()
+    net.load_state_dict(synth.synth_state_dict(net, seed=0))
+    net = net.to(DEV)
+    net.entropy_bottleneck1.update(force=True)
+    net.entropy_bottleneck2.update(force=True)
+    x1, x2, _ = (t.to(DEV) for t in synth.stereo_pairs(1, 64, 256, seed=1234))
+    fwd = net(x1, x2)
+    enc = net.compress(x1, x2, "pair0", output_path=str(tmp_path))
+    dec = net.decompress("cuda:0", "pair0", output_path=str(tmp_path))
+    for k in ("y1_hat", "y2_hat", "z1_hat", "z2_hat"):
+        assert torch.equal(dec[k], enc[k]), k
+    for k in ("x1_hat", "x2_hat"):
+        rel = float((dec[k] - fwd[k]).double().pow(2).sum().sqrt() / fwd[k].double().pow(2).sum().sqrt())
+        assert rel < 2e-2, (k, rel)
+    est = sum(float(torch.log2(v.double()).sum()) for v in fwd["likelihoods"].values()) / (-2 * 64 * 256)
+    assert 0.7 * est <= enc["bpp_real"] <= 1.02 * est, (enc["bpp_real"], est)
