@@ -862,9 +862,8 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     // a second staging set where the operand pipeline keeps its depth: short-K layers are epilogue-bound and every store
     // pair otherwise waits for the previous pair to leave shared memory (r01 profile of the first analysis layer: 11 %)
     const int st2 = (SMEM_LIMIT - fixed - STAGING_BYTES) / (int)p.stage_bytes;
-    static const int force = getenv("HESIC_TC_TWO_STAGING") ? atoi(getenv("HESIC_TC_TWO_STAGING")) : 0;   // experiment knob
-    const bool want = st2 >= 3 || (p.w_resident && st2 >= 2) || (force == 1 && st2 >= 2 && p.n_phases > 1) || (force == 2 && st2 >= 2);
-    if (want) { p.stg_sets = 2; fixed += STAGING_BYTES; }
+    // (measured: giving up the third pipeline stage for it slows the K-heavy layers by 5-20 %)
+    if (st2 >= 3 || (p.w_resident && st2 >= 2)) { p.stg_sets = 2; fixed += STAGING_BYTES; }
   }
   p.stages = std::min(8, (SMEM_LIMIT - fixed) / (int)p.stage_bytes);
   if (p.stages < 2) { set_error("conv tcgen05: tile does not fit shared memory"); return HESIC_E_UNSUPPORTED; }
