@@ -395,7 +395,7 @@ class _HSICBase(CompressionModel):
         ``<name>.bin`` (range-coded y1 then y2).  File layout as in the reference; the .bin byte stream is this
         library's own range coder (the reference's ``range_coder`` package is un-vendored and un-pinned)."""
         if self._variant == "joint":
-            raise NotImplementedError("hesic_b200: the autoregressive codec of HESIC+ (newnet1_joint.py:793-1321) is not built")
+            return self._compress_joint(x1, x2, h_matrix, output_name, output_path)
         (y1_hat, gmm1, z1_hat, z1s), (y2_hat, gmm2, z2_hat, z2s), _ = self._codec_front(x1, x2, h_matrix)
         out1, out2, delta = codec_write(self, x1.shape[2:], [(y1_hat, gmm1, z1s), (y2_hat, gmm2, z2s)], output_name, output_path)
         num_pixels = x1.shape[2] * x1.shape[3] * 2
@@ -407,7 +407,7 @@ class _HSICBase(CompressionModel):
         """newnet1.py:1069-1273 (x1 / x2 are only consulted for the device, as in the reference)."""
         import time
         if self._variant == "joint":
-            raise NotImplementedError("hesic_b200: the autoregressive codec of HESIC+ (newnet1_joint.py:793-1321) is not built")
+            return self._decompress_joint(x1, h_matrix, output_name, output_path)
         C.require_cuda(x1, h_matrix)
         dev = x1.device
         size, heads, dec = codec_read(self, output_name, output_path)
@@ -423,6 +423,124 @@ class _HSICBase(CompressionModel):
         gmm2 = self._h_s2(z2_hat, self._codec_condition(x1_hat, y1_hat, h_matrix, size))
         codec_code_view(self, dec, y2_hat, gmm2, heads[1][1], heads[1][2], decode=True)
         x1_hat_warp = F.warp_perspective(x1_hat, h_matrix, size)
+        x2_hat = self.decoder2(y2_hat, x1_hat_warp)
+        return {"x1_hat": x1_hat, "x2_hat": x2_hat, "y1_hat": y1_hat, "y2_hat": y2_hat, "z1_hat": z1_hat, "z2_hat": z2_hat,
+                "dectime": time.time() - start}
+
+
+    # ---- HESIC+ file codec: autoregressive over the latent positions (newnet1_joint.py:793-1321) ---------------------
+    def _joint_position_params(self, view, y_pad, params, extra, h, w):
+        """Gaussian parameters of all channels at latent position (h, w) from what is already known there: the causal
+        5x5 neighbourhood of y_hat through the masked context model, the hyper-decoder output and (view 2) the warped
+        left latent (newnet1_joint.py:899-906 / 988-995).  The encoder and the decoder both call exactly this routine, so
+        they derive identical tables."""
+        ctxp = getattr(self, f"context_prediction{view}")
+        ep = getattr(self, f"entropy_parameters{view}")
+        ctx = ctxp(y_pad[:, :, h:h + 5, w:w + 5].contiguous())[:, :, 2:3, 2:3]
+        parts = [params[:, :, h:h + 1, w:w + 1], ctx]
+        if extra is not None:
+            parts.append(extra[:, :, h:h + 1, w:w + 1])
+        scales, means = ep(torch.cat(parts, dim=1).contiguous()).chunk(2, 1)
+        return scales.contiguous(), means.contiguous()
+
+    def _joint_code_view(self, view, coder, y_hat, params, extra, minmax, channels, decode):
+        """Raster scan over the positions, the non-zero channels of a position in channel order (newnet1_joint.py:898-963).
+        Encoding gathers the per-position parameters on the device first and codes everything with one table launch;
+        decoding is serial by nature: one table launch, one D2H copy and one host decode per position."""
+        if len(channels) == 0:
+            return
+        dev = y_hat.device
+        Hy, Wy = y_hat.shape[-2:]
+        ones = torch.ones(self.M, device=dev)
+        ch = torch.as_tensor(np.asarray(channels, dtype=np.int64), device=dev)
+        bound = self.gaussian1._scale_bound_value()
+        y_pad = torch.zeros((1, self.M, Hy + 4, Wy + 4), device=dev)
+        if not decode:
+            y_pad[:, :, 2:2 + Hy, 2:2 + Wy] = y_hat
+            sc, mu = torch.empty((1, self.M, Hy, Wy), device=dev), torch.empty((1, self.M, Hy, Wy), device=dev)
+            for h in range(Hy):
+                for w in range(Wy):
+                    s_hw, m_hw = self._joint_position_params(view, y_pad, params, extra, h, w)
+                    sc[:, :, h, w], mu[:, :, h, w] = s_hw[:, :, 0, 0], m_hw[:, :, 0, 0]
+            tables = F.gmm_cdf_tables(sc, mu, ones, 1, channels, minmax, bound).cpu().numpy()
+            tables = tables.reshape(len(channels), Hy * Wy, -1).transpose(1, 0, 2).reshape(len(channels) * Hy * Wy, -1)
+            sym = (y_hat[0, ch] + minmax).to(torch.int32).reshape(len(channels), Hy * Wy).t().reshape(-1).cpu().numpy()
+            coder.push(sym, np.ascontiguousarray(tables))
+            return
+        for h in range(Hy):
+            for w in range(Wy):
+                s_hw, m_hw = self._joint_position_params(view, y_pad, params, extra, h, w)
+                tables = F.gmm_cdf_tables(s_hw, m_hw, ones, 1, channels, minmax, bound).cpu().numpy()
+                sym = torch.from_numpy(coder.decode(tables).astype(np.float32) - minmax).to(dev)
+                y_pad[0, ch, h + 2, w + 2] = sym
+        y_hat.copy_(y_pad[:, :, 2:2 + Hy, 2:2 + Wy])
+
+    def _joint_front(self, x1, x2, h_matrix):
+        size = (x1.size(-2), x1.size(-1))
+        y1 = self.encoder1(x1)[0]
+        z1 = self.h_a1(y1)
+        z1s = self.entropy_bottleneck1.compress(z1)
+        z1_hat = self.entropy_bottleneck1.decompress(z1s, z1.size()[-2:])
+        y1_hat = self._quantize(y1, "dequantize", means=None)
+        x1_hat = self.decoder1(y1_hat)[0]
+        y2 = self.encoder2(F.warp_perspective(x1, h_matrix, size), x2)
+        z2 = self.h_a2(y2)
+        z2s = self.entropy_bottleneck2.compress(z2)
+        z2_hat = self.entropy_bottleneck2.decompress(z2s, z2.size()[-2:])
+        y2_hat = self._quantize(y2, "dequantize", means=None)
+        return (y1_hat, z1_hat, z1s), (y2_hat, z2_hat, z2s), x1_hat, size
+
+    def _compress_joint(self, x1, x2, h_matrix, output_name, output_path):
+        import time
+        if self.training:
+            raise NotImplementedError("hesic_b200: compress() is an inference path; call .eval() first")
+        C.require_cuda(x1, x2, h_matrix)
+        if x1.shape[0] != 1:
+            raise ValueError("HSIC.compress codes one stereo pair per call, as the reference does")
+        (y1_hat, z1_hat, z1s), (y2_hat, z2_hat, z2s), x1_hat, size = self._joint_front(x1, x2, h_matrix)
+        out1 = os.path.join(output_path, str(output_name) + ".npz")
+        out2 = os.path.join(output_path, str(output_name) + ".bin")
+        heads = []
+        with open(out1, "wb") as f:
+            f.write(np.array(x1.shape[2:], dtype=np.uint16).tobytes())
+            for y_hat, zs in ((y1_hat, z1s), (y2_hat, z2s)):
+                yi = y_hat[0].to(torch.int64)
+                flag = (yi.abs().sum(dim=(1, 2)) > 0).cpu().numpy().astype(np.uint8)
+                minmax = int(max(int(yi.max().abs()), int(yi.min().abs()), 1))
+                if len(zs[0]) > 65535 or minmax > 64:
+                    raise ValueError("compress: z string or symbol range exceeds the reference's uint16 / table header")
+                f.write(np.array([len(zs[0]), minmax], dtype=np.uint16).tobytes())
+                f.write(np.packbits(flag).tobytes())
+                f.write(zs[0])
+                heads.append((np.flatnonzero(flag), minmax))
+        start = time.time()
+        enc = F.RangeEncoderHandle()
+        self._joint_code_view(1, enc, y1_hat, self.h_s1(z1_hat), None, heads[0][1], heads[0][0], decode=False)
+        y1_hat_warpf2 = self.gaussian1._quantize(self.encoder1(F.warp_perspective(x1_hat, h_matrix, size))[0], "dequantize")
+        self._joint_code_view(2, enc, y2_hat, self.h_s2(z2_hat), y1_hat_warpf2, heads[1][1], heads[1][0], decode=False)
+        with open(out2, "wb") as f:
+            f.write(enc.finish())
+        num_pixels = x1.shape[2] * x1.shape[3] * 2
+        return {"bpp_real": (os.path.getsize(out1) + os.path.getsize(out2)) * 8 / num_pixels, "enctime": time.time() - start,
+                "y1_hat": y1_hat, "y2_hat": y2_hat, "z1_hat": z1_hat, "z2_hat": z2_hat}
+
+    def _decompress_joint(self, x1, h_matrix, output_name, output_path):
+        import time
+        C.require_cuda(x1, h_matrix)
+        dev = x1.device
+        size, heads, dec = codec_read(self, output_name, output_path)
+        y_shape = [v // 16 for v in size]
+        z_shape = [v // 4 for v in y_shape]
+        start = time.time()
+        z1_hat = self.entropy_bottleneck1.decompress([heads[0][0]], z_shape)
+        z2_hat = self.entropy_bottleneck2.decompress([heads[1][0]], z_shape)
+        y1_hat = torch.zeros((1, self.M, *y_shape), device=dev)
+        y2_hat = torch.zeros((1, self.M, *y_shape), device=dev)
+        self._joint_code_view(1, dec, y1_hat, self.h_s1(z1_hat), None, heads[0][1], heads[0][2], decode=True)
+        x1_hat = self.decoder1(y1_hat)[0]
+        x1_hat_warp = F.warp_perspective(x1_hat, h_matrix, size)
+        y1_hat_warpf2 = self.gaussian1._quantize(self.encoder1(x1_hat_warp)[0], "dequantize")
+        self._joint_code_view(2, dec, y2_hat, self.h_s2(z2_hat), y1_hat_warpf2, heads[1][1], heads[1][2], decode=True)
         x2_hat = self.decoder2(y2_hat, x1_hat_warp)
         return {"x1_hat": x1_hat, "x2_hat": x2_hat, "y1_hat": y1_hat, "y2_hat": y2_hat, "z1_hat": z1_hat, "z2_hat": z2_hat,
                 "dectime": time.time() - start}

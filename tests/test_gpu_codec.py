@@ -73,13 +73,33 @@ def test_compress_decompress_round_trip(modname, tmp_path):
 
 def test_compress_argument_errors(tmp_path):
     import newnet1
-    import newnet1_joint
     net = newnet1.HSIC(128, 192, 5).eval().to(DEV)
     x = torch.rand(2, 3, 128, 128, device=DEV)
     with pytest.raises(ValueError):
         net.compress(x, x, torch.eye(3, device=DEV).repeat(2, 1, 1), "p", output_path=str(tmp_path))
-    with pytest.raises(NotImplementedError):
-        newnet1_joint.HSIC(128, 192, 5).eval().to(DEV).compress(x[:1], x[:1], torch.eye(3, device=DEV)[None], "p", output_path=str(tmp_path))
+
+
+def test_joint_autoregressive_codec_round_trip(tmp_path):
+    """HESIC+ (newnet1_joint.py:793-1321): raster-scan autoregressive coding -- context model on the already decoded
+    5x5 neighbourhood, Gaussian tables per position, y2 conditioned on the re-encoded warped left view."""
+    import newnet1_joint
+    net = newnet1_joint.HSIC(128, 192, 5).eval()
+    net.load_state_dict(synth.synth_state_dict(net, seed=0))
+    net = net.to(DEV)
+    net.entropy_bottleneck1.update(force=True)
+    net.entropy_bottleneck2.update(force=True)
+    x1, x2, h = (t.to(DEV) for t in synth.stereo_pairs(1, 128, 128, seed=1234))
+    fwd = net(x1, x2, h)
+    enc = net.compress(x1, x2, h, "pairj", output_path=str(tmp_path))
+    dec = net.decompress(x1, x2, h, "pairj", output_path=str(tmp_path))
+    for k in ("y1_hat", "y2_hat", "z1_hat", "z2_hat"):
+        assert torch.equal(dec[k], enc[k]), k
+    assert float((enc["y1_hat"] != fwd["y1_hat"]).double().mean()) < 2e-3
+    for k in ("x1_hat", "x2_hat"):
+        rel = float((dec[k] - fwd[k]).double().pow(2).sum().sqrt() / fwd[k].double().pow(2).sum().sqrt())
+        assert rel < 5e-3, (k, rel)
+    est = sum(float(torch.log2(v.double()).sum()) for v in fwd["likelihoods"].values()) / (-2 * 128 * 128)
+    assert 0.6 * est <= enc["bpp_real"] <= 1.05 * est, (enc["bpp_real"], est)
 
 
 def test_dsic_compress_decompress_round_trip(tmp_path):
