@@ -52,6 +52,7 @@ _sig = {
     "hesic_conv_load": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "hesic_conv_set_gdn": ([c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p], c_int),
     "hesic_conv_enable_gdn": ([c_void_p, c_int], c_int),
+    "hesic_conv_detect_kband": ([c_void_p, c_void_p, c_void_p], c_int),
     "hesic_conv_forward": ([c_void_p, _TP, _TP, c_int, c_int, c_void_p], c_int),
     "hesic_conv_forward_cat": ([c_void_p, _TP, _TP, _TP, c_int, c_int, c_void_p], c_int),
     "hesic_en_conv_create": ([c_int, c_int], c_void_p),

@@ -27,6 +27,10 @@ struct hesic_conv {
   // MaskedConv2d: bit t set = tap t (ky*kw + kx) has a non-zero mask entry; dead taps are skipped by the tcgen05 path
   // (mask type 'A' of a 5x5 kernel keeps 12 of 25 taps, compressai/layers/layers.py:36-40)
   uint64_t live_taps = ~0ull;
+  // block-banded weights (hesic_conv_detect_kband): per 128-wide N tile the range of 64-channel K chunks with non-zero
+  // weights; valid for the tile geometry (kband_bn, kband_chunks) it was computed for, 0 = not computed
+  int kband_bn = 0, kband_chunks = 0;
+  int8_t kc_lo[8] = {0}, kc_hi[8] = {0};
   // fused GDN
   bool has_gdn = false;
   int gdn_inverse = 0;

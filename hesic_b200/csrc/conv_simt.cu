@@ -368,6 +368,7 @@ extern "C" int hesic_conv_load(hesic_conv *c, const float *weight, const float *
     HESIC_CUDA(cudaMalloc(&c->w_lo, tc_elems * sizeof(__nv_bfloat16)));
   }
   c->live_taps = ~0ull;
+  c->kband_bn = c->kband_chunks = 0;
   if (mask && taps <= 64) {
     // once per load: which taps does the mask keep?  (host copy + sync; weights are loaded once per model)
     const size_t n = (size_t)c->Cout * c->Cin * taps;
@@ -424,6 +425,51 @@ extern "C" int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float 
   if (r != HESIC_OK) return r;
   c->has_gdn = true;
   c->gdn_inverse = inverse ? 1 : 0;
+  return HESIC_OK;
+}
+
+// one block per (N tile, K chunk): does the block of weights hold any non-zero entry?
+__global__ void kband_kernel(const float *__restrict__ w, int Cin, int Cout, int taps, int BN, int kchunks, int *__restrict__ flags) {
+  const int nt = blockIdx.x / kchunks, kc = blockIdx.x - nt * kchunks;
+  const int co0 = nt * BN, co1 = min(co0 + BN, Cout), ci0 = kc * 64, ci1 = min(ci0 + 64, Cin);
+  const int ncin = ci1 - ci0;
+  const size_t n = (size_t)(co1 - co0) * ncin * taps;
+  int any = 0;
+  for (size_t i = threadIdx.x; i < n && !any; i += blockDim.x) {
+    const int t = (int)(i % taps);
+    const size_t r = i / taps;
+    const int ci = ci0 + (int)(r % ncin), co = co0 + (int)(r / ncin);
+    if (w[((size_t)co * Cin + ci) * taps + t] != 0.f) any = 1;
+  }
+  if (__syncthreads_or(any) && threadIdx.x == 0) flags[blockIdx.x] = 1;
+}
+
+extern "C" int hesic_conv_detect_kband(hesic_conv *c, const float *weight, void *stream) {
+  HESIC_REQUIRE(c && weight, "hesic_conv_detect_kband: null argument");
+  c->kband_bn = c->kband_chunks = 0;
+  if (c->transposed || c->tc_kind != HESIC_TC_GENERIC) return HESIC_OK;     // plain convolutions on the generic tensor-core path only
+  const int BN = std::min(128, (c->Cout + 31) / 32 * 32), kchunks = (c->Cin + 63) / 64, n_tiles = (c->Cout + BN - 1) / BN;
+  if (kchunks < 2 || n_tiles > 8 || kchunks > 127) return HESIC_OK;
+  cudaStream_t s = as_stream(stream);
+  int *flags = nullptr;
+  const int nb = n_tiles * kchunks;
+  HESIC_CUDA(cudaMallocAsync(&flags, nb * sizeof(int), s));
+  HESIC_CUDA(cudaMemsetAsync(flags, 0, nb * sizeof(int), s));
+  kband_kernel<<<nb, 256, 0, s>>>(weight, c->Cin, c->Cout, c->kh * c->kw, BN, kchunks, flags);
+  int rc = launched("kband_kernel");
+  std::vector<int> h(nb, 1);
+  if (rc == HESIC_OK && cudaMemcpyAsync(h.data(), flags, nb * sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = HESIC_E_CUDA;
+  if (rc == HESIC_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = HESIC_E_CUDA;
+  cudaFreeAsync(flags, s);
+  if (rc != HESIC_OK) return rc;
+  for (int nt = 0; nt < n_tiles; ++nt) {
+    int lo = kchunks, hi = 0;
+    for (int kc = 0; kc < kchunks; ++kc)
+      if (h[nt * kchunks + kc]) { lo = std::min(lo, kc); hi = std::max(hi, kc + 1); }
+    if (hi <= lo) { lo = 0; hi = 1; }     // an all-zero tile still needs one step to define the accumulator
+    c->kc_lo[nt] = (int8_t)lo; c->kc_hi[nt] = (int8_t)hi;
+  }
+  c->kband_bn = BN; c->kband_chunks = kchunks;
   return HESIC_OK;
 }
 

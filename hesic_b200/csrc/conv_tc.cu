@@ -85,6 +85,7 @@ struct Params {
   int w_resident;          // all weight tiles ([tap][kchunk][hi, lo]) are loaded once and stay in smem
   int n_wtiles;            // taps * kchunks (w_resident)
   int wide_n;              // BN == 128: issue Ah.[Wh; Wl] as one N = 256 MMA
+  int8_t kc_lo[8], kc_hi[8];   // per N tile: the 64-channel K chunks [kc_lo, kc_hi) that hold non-zero weights (block-banded layers)
   int stg_sets;            // 1 or 2 staging tile pairs for the TMA-store epilogue (2: a pair does not wait for the previous pair's store)
   int stages;
   uint32_t stage_bytes, b_bytes;
@@ -113,11 +114,12 @@ __device__ __forceinline__ void walk_schedule(const Params &p, ConvStep &&conv_s
   for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x, ++lt) {
     TaskCoord tk = decode_task(p, task);
     const int t0 = p.tap_begin[tk.ph], t1 = p.tap_begin[tk.ph + 1];
-    const int ksteps = (t1 - t0) * p.kchunks;
+    const int kc0 = p.kc_lo[tk.nt & 7], kc1 = p.kc_hi[tk.nt & 7];
+    const int ksteps = (t1 - t0) * (kc1 - kc0);
     const int g = (p.gdn && lt > 0) ? min(GDN_AT, ksteps - 1) : -1;
     int ks = 0;
     for (int t = t0; t < t1; ++t) {
-      for (int kc = 0; kc < p.kchunks; ++kc, ++ks) {
+      for (int kc = kc0; kc < kc1; ++kc, ++ks) {
         if (ks == g) {
           gdn_step(lt - 1, 0);
           gdn_step(lt - 1, 1);
@@ -832,6 +834,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.n_tiles = planar ? 1 : (c->Cout + p.BN - 1) / p.BN;
   const bool rowk = c->tc_kind == HESIC_TC_ROW || c->tc_kind == HESIC_TC_ROW2;
   p.kchunks = rowk ? 1 : (c->Cin + BK - 1) / BK;
+  for (int i = 0; i < 8; ++i) { p.kc_lo[i] = 0; p.kc_hi[i] = (int8_t)p.kchunks; }
   p.in_Cs = xCs;
   p.out_fmt = y->fmt; p.out_Cs = yCs; p.y0 = y->p0; p.y1 = y->p1;
   p.Hout = y->H; p.Wout = y->W; p.B = y->B;
@@ -844,6 +847,10 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   // ROW2: the whole weight set (3 tiles, hi + lo) fits next to the pipeline -> loaded once per CTA; a stage then
   // carries only the A tiles (or, for a GDN step, the gamma tiles in the same space)
   p.n_wtiles = ntaps * p.kchunks;
+  if (c->kband_bn == p.BN && c->kband_chunks == p.kchunks && p.n_tiles <= 8 && !rowk) {
+    // block-banded weights (hesic_conv_detect_kband): skip the K chunks of an N tile that hold only zeros
+    for (int i = 0; i < p.n_tiles; ++i) { p.kc_lo[i] = c->kc_lo[i]; p.kc_hi[i] = c->kc_hi[i]; }
+  }
   p.w_resident = (c->tc_kind == HESIC_TC_ROW2 && p.n_tiles == 1 && p.b_bytes <= (uint32_t)A_TILE_BYTES) ? 1 : 0;
   if (getenv("HESIC_TC_NO_RESIDENT")) p.w_resident = 0;
   p.wide_n = (!planar && p.BN == 128 && !getenv("HESIC_TC_NARROW")) ? 1 : 0;

@@ -37,14 +37,17 @@ class Conv3dAs2d(nn.Conv3d):
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        self._plan = None
-        self._plan_key = None
+        self._plans = {}      # depth_major -> (plan, key, packed weight, packed bias)
 
-    def _plan_for(self, D):
+    def _plan_for(self, D, depth_major=False):
+        """depth_major: stack the channels as (d, f) instead of (f, d).  The 5-tap band along the depth axis then makes
+        the 2-D weight block-banded at the granularity of the tensor-core tiles (an output tile of 128 channels = 18
+        depths needs 22 input depths = 3 of the 4 64-channel K chunks), and the kernel skips the empty blocks."""
         key = (self.weight.data_ptr(), self.weight._version, self.bias.data_ptr(), self.bias._version, D,
-               self.weight.device.index)
-        if self._plan is not None and self._plan_key == key:
-            return self._plan
+               self.weight.device.index, bool(depth_major))
+        ent = self._plans.get(bool(depth_major))
+        if ent is not None and ent[1] == key:
+            return ent[0]
         Fo, Fi, kd, kh, kw = self.weight.shape
         w3 = self.weight.detach()
         w2 = torch.zeros((Fo, D, Fi, D, kh, kw), device=w3.device, dtype=torch.float32)
@@ -53,10 +56,16 @@ class Conv3dAs2d(nn.Conv3d):
             lo, hi = max(0, dd - p), min(D, dd + p + 1)
             w2[:, dd, :, lo:hi] = w3[:, :, lo - dd + p:hi - dd + p]
         plan = F.ConvPlan(Fi * D, Fo * D, (kh, kw), 1, kh // 2)
-        self._w2 = w2.reshape(Fo * D, Fi * D, kh, kw).contiguous()
-        self._b2 = self.bias.detach().repeat_interleave(D).contiguous()
-        plan.load(self._w2, self._b2)
-        self._plan, self._plan_key = plan, key
+        if depth_major:
+            wp = w2.permute(1, 0, 3, 2, 4, 5).reshape(D * Fo, D * Fi, kh, kw).contiguous()
+            bp = self.bias.detach().repeat(D).contiguous()
+        else:
+            wp = w2.reshape(Fo * D, Fi * D, kh, kw).contiguous()
+            bp = self.bias.detach().repeat_interleave(D).contiguous()
+        plan.load(wp, bp)
+        if depth_major:
+            plan.detect_kband(wp)
+        self._plans[bool(depth_major)] = (plan, key, wp, bp)
         return plan
 
     def forward(self, x):

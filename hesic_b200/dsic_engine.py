@@ -44,23 +44,43 @@ class DsicEngine(HesicEngine):
         plan.run(x_desc, d, act, self.path)
         return t, d, Ho, Wo
 
-    def _swapped_plan(self, conv_mod):
-        """Plan of cost_volume.model1[0] (conv 2N -> N over cat(h1, h2)) with its two input halves swapped, because the
-        level buffer stores [.. | h2 | h1]."""
-        key = id(conv_mod)
+    def _perm_plan(self, conv_mod, tag, in_perm=None, out_perm=None):
+        """Plan of ``conv_mod`` with its input and / or output channels permuted (new channel i = old channel perm[i]):
+        the engine's buffers store some concatenations in a different channel order than the reference's tensors."""
+        key = (id(conv_mod), tag)
         ent = self._perm_plans.get(key)
         ver = F.ConvPlan._ver(conv_mod.weight, conv_mod.bias)
         if ent is None or ent[1] != ver:
-            w = conv_mod.weight.detach()
-            half = w.shape[1] // 2
-            wp = torch.cat((w[:, half:], w[:, :half]), dim=1).contiguous()
+            w, b = conv_mod.weight.detach(), conv_mod.bias.detach() if conv_mod.bias is not None else None
+            if in_perm is not None:
+                w = w.index_select(1, torch.as_tensor(in_perm, device=w.device))
+            if out_perm is not None:
+                op = torch.as_tensor(out_perm, device=w.device)
+                w = w.index_select(0, op)
+                b = b.index_select(0, op) if b is not None else None
+            w = w.contiguous()
+            b = b.contiguous() if b is not None else None
             plan = ent[0] if ent else F.ConvPlan(conv_mod.in_channels, conv_mod.out_channels, tuple(conv_mod.kernel_size),
                                                  conv_mod.stride[0], conv_mod.padding[0])
             plan._key = None
-            plan.load(wp, conv_mod.bias)
+            plan.load(w, b)
             plan.set_gdn(None, None, False)
-            ent = self._perm_plans[key] = (plan, ver, wp)
+            ent = self._perm_plans[key] = (plan, ver, w, b)
         return ent[0]
+
+    def _swapped_plan(self, conv_mod):
+        """cost_volume.model1[0] (conv 2N -> N over cat(h1, h2)) with its two input halves swapped: the level buffer
+        stores [.. | h2 | h1]."""
+        half = conv_mod.in_channels // 2
+        return self._perm_plan(conv_mod, "swap", in_perm=list(range(half, 2 * half)) + list(range(half)))
+
+    @staticmethod
+    def _depth_major(F0, D, blocks=1, lead=0):
+        """Permutation taking (f, d)-ordered channel blocks to (d, f) order, after ``lead`` untouched channels."""
+        perm = list(range(lead))
+        for k in range(blocks):
+            perm += [lead + k * F0 * D + f * D + d for d in range(D) for f in range(F0)]
+        return perm
 
     def _gn(self, gn_mod, x_t, dst_t, c0, Cn, weight=None, bias=None):
         """GroupNorm + ReLU: NHWC fp32 tensor -> channel slice [c0, c0 + Cn) of a SPLIT buffer."""
@@ -88,16 +108,18 @@ class DsicEngine(HesicEngine):
         # model1 on cat(h1, h2) = slots [2N, 3N) ++ [N, 2N): read as the slice [N, 3N) with swapped weight halves
         u = self._conv_gn(self._swapped_plan(m1[0]), m1[1], C.split(lvl, 2 * N, N), B, H, W)
         self._conv_gn(m1[3], m1[4], u, B, H, W, dst=(cat3, 0))
-        # context volume: bilinear upsample (align_corners=True), two Conv3d as banded 2-D convs, GroupNorm(1 group)
-        D = cv.C
+        # context volume: bilinear upsample (align_corners=True), two Conv3d as block-banded 2-D convs over the
+        # (depth, feature)-ordered channels (the global-context conv already emits that order, see forward()),
+        # GroupNorm(1 group) with its per-feature affine repeated over the depths
+        D, F0 = cv.C, cv.F0
         up = _split(B, H, W, FC, self.dev)
         C.check(_lib.hesic_upsample_bilinear(C.ref(C.nhwc(ctx_t, FC, FC * j)), C.ref(C.split(up)), cv.scale_factor, C.stream()))
         g1, g2 = m2[1], m2[4]
-        exp = lambda v: _keep(v.detach().repeat_interleave(D).contiguous())
-        v = self._conv_gn(m2[0]._plan_for(D), g1, C.split(up), B, H, W, weight=exp(g1.weight), bias=exp(g1.bias))
-        self._conv_gn(m2[3]._plan_for(D), g2, v, B, H, W, dst=(cat3, N), weight=exp(g2.weight), bias=exp(g2.bias))
+        exp = lambda v: _keep(v.detach().repeat(D).contiguous())
+        v = self._conv_gn(m2[0]._plan_for(D, True), g1, C.split(up), B, H, W, weight=exp(g1.weight), bias=exp(g1.bias))
+        self._conv_gn(m2[3]._plan_for(D, True), g2, v, B, H, W, dst=(cat3, N), weight=exp(g2.weight), bias=exp(g2.bias))
         # model3 -> softmax over the disparities
-        v = self._conv_gn(m3[0], m3[1], C.split(cat3), B, H, W)
+        v = self._conv_gn(self._perm_plan(m3[0], "dm", in_perm=self._depth_major(F0, D, 1, N)), m3[1], C.split(cat3), B, H, W)
         v = self._conv_gn(m3[3], m3[4], v, B, H, W)
         raw, raw_d, _, _ = self._conv(self._plan(m3[6]), v, B, H, W, "nhwc")
         cost = _nhwc(B, H, W, cv.C, self.dev)
@@ -153,7 +175,9 @@ class DsicEngine(HesicEngine):
         v = self._conv_gn(gc[0], gc[1], y1h_d, B, Hy, Wy)
         v = self._conv_gn(gc[3], gc[4], v, B, Hy, Wy)
         v = self._conv_gn(gc[6], gc[7], v, B, Hy, Wy)
-        ctx, _, _, _ = self._conv(self._plan(gc[9]), v, B, Hy, Wy, "nhwc")          # [B, Hy, Wy, 3 * F0 * C]
+        cv1 = m._cost_volume1
+        gc_last = self._perm_plan(gc[9], "dm", out_perm=self._depth_major(cv1.F0, cv1.C, 3))
+        ctx, _, _, _ = self._conv(gc_last, v, B, Hy, Wy, "nhwc")   # [B, Hy, Wy, 3 x (C depths x F0 features)], depth-major
 
         # ---- view 2 analysis -------------------------------------------------------------------------
         self._run(m.pic2_g_a_conv1, self._rowpad("x2", C.nchw(x2), B, 3, H, W), B, H, W, "split", gdn=m.pic2_g_a_gdn1, dst=(lv[1], N))

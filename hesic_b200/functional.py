@@ -76,6 +76,12 @@ class ConvPlan:
         self._gdn_on = True
         return self
 
+    def detect_kband(self, weight):
+        """Block-banded weights: let the tensor-core path skip the all-zero (N tile, K chunk) blocks.  ``weight`` is the
+        tensor last passed to load().  Synchronises the stream once (a handful of flags are read back)."""
+        C.check(_lib.hesic_conv_detect_kband(self.h, C.ptr(_f32(weight.detach())), C.stream()))
+        return self
+
     def out_hw(self, H, W):
         Cin, Cout, kh, kw, s, p, tr, op = self.geom
         if not tr:

@@ -92,6 +92,11 @@ int hesic_conv_load(hesic_conv *c, const float *weight, const float *bias, const
  * on the device.  Pass NULLs to detach. */
 int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float *gamma, int inverse, float beta_min,
                        void *stream);
+/* Block-banded layers (the nn.Conv3d of the DSIC cost volumes evaluated as a 2-D convolution over the stacked
+ * (depth, feature) channels, ywz/DSIC/mynet6_plus.py:273-283): finds, per 128-wide tile of output channels, the range of
+ * 64-channel input chunks that hold any non-zero weight, and the tensor-core path then skips the rest.  weight: the dev
+ * fp32 tensor last given to hesic_conv_load.  Synchronises the stream (a few flags are read back); optional. */
+int hesic_conv_detect_kband(hesic_conv *c, const float *weight, void *stream);
 /* Detach (0) / re-attach (1) the GDN packed by the last hesic_conv_set_gdn without re-packing it: the same layer
  * object serves the fused engine (GDN in the epilogue) and stand-alone operator calls (plain convolution). */
 int hesic_conv_enable_gdn(hesic_conv *c, int enable);

@@ -225,3 +225,25 @@ def test_upsample_channels_last(scale):
     C.check(C.lib.hesic_upsample_bilinear(C.ref(C.split(xs)), C.ref(C.split(out2)), scale, C.stream()))
     assert_close(_from_split(out2), torch.nn.functional.interpolate(xq, scale_factor=scale, mode="bilinear", align_corners=True), 2e-5,
                  what="upsample SPLIT -> SPLIT")
+
+
+def test_conv3d_depth_major_banded_plan():
+    """The engine's form of the cost-volume Conv3d: channels stacked (depth, feature), the all-zero (N tile, K chunk)
+    blocks of the banded 2-D weight skipped by the tensor-core kernel -- same result as nn.Conv3d."""
+    from hesic_b200 import _capi as C
+    from hesic_b200.dsic import Conv3dAs2d
+    m = Conv3dAs2d(7, 7, kernel_size=5, stride=1, padding=2)
+    w, b = _rand(tuple(m.weight.shape), 8, (2.0 / 875) ** 0.5), _rand((7,), 9, 0.1)
+    m.load_state_dict({"weight": w, "bias": b})
+    x = _rand((2, 7, 32, 16, 24), 10)
+    ref = torch.nn.functional.conv3d(x, w, b, padding=2)                      # [B, F, D, H, W]
+    m = m.to(DEV)
+    plan = m._plan_for(32, True)
+    xs = _to_split(x.permute(0, 2, 1, 3, 4).reshape(2, 224, 16, 24))          # (d, f)-ordered channels
+    y = torch.empty((2, 16, 24, 224), device=DEV)
+    plan.run(C.split(xs), C.nhwc(y), C.ACT_NONE, C.PATH_TC)
+    C.check(C.lib.hesic_tc_status())
+    got = y.permute(0, 3, 1, 2).reshape(2, 32, 7, 16, 24).permute(0, 2, 1, 3, 4)
+    xq = _from_split(xs).cpu().reshape(2, 32, 7, 16, 24).permute(0, 2, 1, 3, 4)
+    assert_close(got, torch.nn.functional.conv3d(xq, w, b, padding=2), 1e-4, what="depth-major banded Conv3d")
+    assert_close(got, ref, 1e-4, what="depth-major banded Conv3d vs fp32 input")
