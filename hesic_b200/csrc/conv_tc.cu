@@ -85,7 +85,7 @@ struct Params {
   int w_resident;          // all weight tiles ([tap][kchunk][hi, lo]) are loaded once and stay in smem
   int n_wtiles;            // taps * kchunks (w_resident)
   int wide_n;              // BN == 128: issue Ah.[Wh; Wl] as one N = 256 MMA
-  int8_t kc_lo[8], kc_hi[8];   // per N tile: the 64-channel K chunks [kc_lo, kc_hi) that hold non-zero weights (block-banded layers)
+  int16_t kc_lo[8], kc_hi[8];  // per N tile: the 64-channel K chunks [kc_lo, kc_hi) that hold non-zero weights (block-banded layers)
   int stg_sets;            // 1 or 2 staging tile pairs for the TMA-store epilogue (2: a pair does not wait for the previous pair's store)
   int stages;
   uint32_t stage_bytes, b_bytes;
@@ -834,7 +834,8 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.n_tiles = planar ? 1 : (c->Cout + p.BN - 1) / p.BN;
   const bool rowk = c->tc_kind == HESIC_TC_ROW || c->tc_kind == HESIC_TC_ROW2;
   p.kchunks = rowk ? 1 : (c->Cin + BK - 1) / BK;
-  for (int i = 0; i < 8; ++i) { p.kc_lo[i] = 0; p.kc_hi[i] = (int8_t)p.kchunks; }
+  for (int i = 0; i < 8; ++i) { p.kc_lo[i] = 0; p.kc_hi[i] = (int16_t)p.kchunks; }
+  if (p.kchunks > 32767) { set_error("conv tcgen05: too many input channels"); return HESIC_E_UNSUPPORTED; }
   p.in_Cs = xCs;
   p.out_fmt = y->fmt; p.out_Cs = yCs; p.y0 = y->p0; p.y1 = y->p1;
   p.Hout = y->H; p.Wout = y->W; p.B = y->B;
