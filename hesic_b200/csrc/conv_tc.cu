@@ -552,14 +552,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           uint32_t q[32];
           tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
-          float v[32];
-          ld_chan32(beta_s + 128u * ch, v);
-          if (p.gdn == 2) {
+          // beta four at a time (a 32-float table would sit on top of xs[64] + q[32] and spill)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) xs[i * 32 + j] *= sqrt_approx(__uint_as_float(q[j]) + v[j]);
-          } else {
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 bt = ld_shared_f4(beta_s + 128u * ch + 16u * jj);
+            const float bv[4] = {bt.x, bt.y, bt.z, bt.w};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) xs[i * 32 + j] *= rsqrt_approx(__uint_as_float(q[j]) + v[j]);
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * jj + e;
+              const float nrm = __uint_as_float(q[j]) + bv[e];
+              xs[i * 32 + j] *= (p.gdn == 2) ? sqrt_approx(nrm) : rsqrt_approx(nrm);
+            }
           }
         }
         tc_fence_before();
