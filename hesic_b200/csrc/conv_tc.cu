@@ -590,6 +590,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }  // namespace tc
 }  // namespace hesic
 #include "conv_head.cuh"
+#include "conv_tc_pair.cuh"
 namespace hesic {
 namespace tc {
 
@@ -960,6 +961,43 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     c->tc_maps_bn = p.BN; c->tc_maps_gdn = want_gdn;
   }
   const CUtensorMap *m = (const CUtensorMap *)c->tc_maps;
+  // CTA-pair kernel (conv_tc_pair.cuh): plain K-heavy layers with full 128-column N tiles
+  static const bool pair_on = getenv("HESIC_TC_SINGLE_CTA") == nullptr;
+  if (pair_on && c->tc_kind == HESIC_TC_GENERIC && !planar && p.tma_store && p.BN == 128 && !p.w_resident &&
+      c->kband_bn == 0 && num_sms >= 2 && p.kchunks * ntaps >= 8) {
+    static bool pair_attr = false;
+    if (!pair_attr) {
+      HESIC_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      pair_attr = true;
+    }
+    CUtensorMap mw64;
+    {
+      uint64_t dims[3] = {(uint64_t)c->tc_k, (uint64_t)c->CoutPad, (uint64_t)c->tc_taps};
+      uint64_t strides[2] = {(uint64_t)c->tc_k * 2, (uint64_t)c->tc_k * c->CoutPad * 2};
+      uint32_t box[3] = {(uint32_t)BK, 64u, 1u};
+      int r = make_map(&mw64, c->w_hi, 3, dims, strides, box);
+      if (r != HESIC_OK) return r;
+    }
+    CUtensorMap mg_hi = mw64, mg_lo = mw64;
+    if (p.gdn) {
+      uint64_t gd[2] = {128, 128}, gs[1] = {256};
+      uint32_t gb[2] = {(uint32_t)BK, 64u};
+      int r = make_map(&mg_hi, c->gdn_g_hi, 2, gd, gs, gb);
+      if (r == HESIC_OK) r = make_map(&mg_lo, c->gdn_g_lo, 2, gd, gs, gb);
+      if (r != HESIC_OK) return r;
+    }
+    Params q = p;
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+    q.n_tiles = (c->Cout + 127) / 128;
+    q.n_tasks = ((m_tiles + 1) / 2) * p.n_phases * q.n_tiles;     // PAIR tasks
+    const int pfixed = 1024 + BAR_BYTES + CHAN_BYTES + STAGING_BYTES;
+    q.stages = std::min(8, (SMEM_LIMIT - pfixed) / PAIR_STAGE_BYTES);
+    q.stg_sets = 1;
+    const int pgrid = std::min(2 * q.n_tasks, num_sms & ~1);
+    conv_tc_pair_kernel<<<pgrid, NUM_THREADS, q.stages * PAIR_STAGE_BYTES + pfixed, s>>>(ma_hi, ma_lo, m[0], m[1], mw64, mg_hi, mg_lo, my0, my1, q);
+    HESIC_LAUNCHED("conv_tc_pair_kernel");
+    return HESIC_OK;
+  }
   const int grid = std::min(p.n_tasks, num_sms);
   conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], m[2], m[3], my0, my1, p);
   HESIC_LAUNCHED("conv_tc_kernel");
