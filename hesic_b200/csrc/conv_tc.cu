@@ -964,7 +964,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   // CTA-pair kernel (conv_tc_pair.cuh): plain K-heavy layers with full 128-column N tiles
   static const bool pair_on = getenv("HESIC_TC_SINGLE_CTA") == nullptr;
   if (pair_on && c->tc_kind == HESIC_TC_GENERIC && !planar && p.tma_store && p.BN == 128 && !p.w_resident &&
-      c->kband_bn == 0 && num_sms >= 2 && p.kchunks * ntaps >= 8) {
+      num_sms >= 2 && p.kchunks * ntaps >= 8) {
     static bool pair_attr = false;
     if (!pair_attr) {
       HESIC_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));

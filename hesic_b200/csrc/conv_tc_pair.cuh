@@ -158,12 +158,13 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const int tb = tk.mt / txy, rr = tk.mt - tb * txy;
         const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
         const int t0 = p.tap_begin[tk.ph], t1 = p.tap_begin[tk.ph + 1];
-        const int ksteps = (t1 - t0) * p.kchunks;
+        const int kc0 = p.kc_lo[tk.nt & 7], kc1 = p.kc_hi[tk.nt & 7];   // block-banded layers skip empty K chunks
+        const int ksteps = (t1 - t0) * (kc1 - kc0);
         const int g = (p.gdn && lt > 0) ? min(GDN_AT, ksteps - 1) : -1;
         int ks = 0;
         for (int t = t0; t < t1; ++t) {
           const Tap tap = p.taps[t];
-          for (int kc = 0; kc < p.kchunks; ++kc, ++ks) {
+          for (int kc = kc0; kc < kc1; ++kc, ++ks) {
             if (ks == g) { gdn_step(0); gdn_step(1); }
             mbar_wait(empty_bar(stage), phase ^ 1u, 1);
             const uint32_t sa = smem_base + (uint32_t)stage * PAIR_STAGE_BYTES;
@@ -216,7 +217,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       for (int task = first; task < n_pairs; task += step, ++lt) {
         const TaskCoord tk = decode_pair_task(p, task, 0);
         const int buf = lt & 1;
-        const int ksteps = (p.tap_begin[tk.ph + 1] - p.tap_begin[tk.ph]) * p.kchunks;
+        const int ksteps = (p.tap_begin[tk.ph + 1] - p.tap_begin[tk.ph]) * (p.kc_hi[tk.nt & 7] - p.kc_lo[tk.nt & 7]);
         const int g = (p.gdn && lt > 0) ? min(GDN_AT, ksteps - 1) : -1;
         const uint32_t d_main = tmem_base + (uint32_t)buf * ACC_STRIDE, d_small = d_main + COL_SMALL;
         for (int ks = 0; ks < ksteps; ++ks) {

@@ -15,7 +15,7 @@ timeout 300 python tools/kernel_breakdown.py en 16 > $O/en_breakdown.txt 2>&1
 timeout 300 python tools/run_en_layer.py 16 5 all > $O/en_layer_times.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 1 --cpu-iters 1 > $O/bench_ncu.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on -f"
-timeout 300 $NCU -k regex:conv_tc_kernel -s 2 -c 1 -o $O/ncu_conv2 python tools/run_dominant.py 4 16 > $O/ncu_conv2.log 2>&1
+timeout 300 $NCU -k regex:"conv_tc(_pair)?_kernel" -s 2 -c 1 -o $O/ncu_conv2 python tools/run_dominant.py 4 16 > $O/ncu_conv2.log 2>&1
 timeout 600 $NCU -k regex:"warp_kernel|gaussian_tile|conv_small_kernel|conv_head_kernel|eb_kernel|rowpad_kernel|spatial_max|upsample_kernel|sse_kernel" -c 14 -o $O/ncu_elem python bench.py --steps 1 --warmup 0 --cpu-iters 1 > $O/ncu_elem.log 2>&1
 timeout 300 $NCU -k regex:en_conv_kernel -s 1 -c 1 -o $O/ncu_en_res1 python tools/run_en_layer.py 16 1 res1 > $O/ncu_en_res1.log 2>&1
 tail -2 $O/pytest_gpu.log; tail -2 $O/smoke.log; cat $O/bench_hesic.json | cut -c1-300; cat $O/bench_hesic_plus.json | cut -c1-200; cat $O/bench_reference.json | cut -c1-200; cat $O/dsic_time.txt | tail -1; head -1 $O/en_breakdown.txt
