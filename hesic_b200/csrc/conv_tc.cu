@@ -86,6 +86,7 @@ struct Params {
   int n_wtiles;            // taps * kchunks (w_resident)
   int wide_n;              // BN == 128: issue Ah.[Wh; Wl] as one N = 256 MMA
   int16_t kc_lo[8], kc_hi[8];  // per N tile: the 64-channel K chunks [kc_lo, kc_hi) that hold non-zero weights (block-banded layers)
+  int gdn_at;              // k-step of tile t+1 before which the GDN MMAs of tile t are issued
   int stg_sets;            // 1 or 2 staging tile pairs for the TMA-store epilogue (2: a pair does not wait for the previous pair's store)
   int stages;
   uint32_t stage_bytes, b_bytes;
@@ -116,7 +117,7 @@ __device__ __forceinline__ void walk_schedule(const Params &p, ConvStep &&conv_s
     const int t0 = p.tap_begin[tk.ph], t1 = p.tap_begin[tk.ph + 1];
     const int kc0 = p.kc_lo[tk.nt & 7], kc1 = p.kc_hi[tk.nt & 7];
     const int ksteps = (t1 - t0) * (kc1 - kc0);
-    const int g = (p.gdn && lt > 0) ? min(GDN_AT, ksteps - 1) : -1;
+    const int g = (p.gdn && lt > 0) ? min(p.gdn_at, ksteps - 1) : -1;
     int ks = 0;
     for (int t = t0; t < t1; ++t) {
       for (int kc = kc0; kc < kc1; ++kc, ++ks) {
@@ -859,6 +860,8 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.w_resident = (c->tc_kind == HESIC_TC_ROW2 && p.n_tiles == 1 && p.b_bytes <= (uint32_t)A_TILE_BYTES) ? 1 : 0;
   if (getenv("HESIC_TC_NO_RESIDENT")) p.w_resident = 0;
   p.wide_n = (!planar && p.BN == 128 && !getenv("HESIC_TC_NARROW")) ? 1 : 0;
+  static const int gdn_at_env = getenv("HESIC_TC_GDN_AT") ? atoi(getenv("HESIC_TC_GDN_AT")) : GDN_AT;
+  p.gdn_at = std::max(0, gdn_at_env);
   p.stage_bytes = 2u * A_TILE_BYTES + (p.w_resident ? 0u : 2u * p.b_bytes);
   // TMA-store epilogue: channels-last outputs; for the sub-pixel phases of a transposed conv the phase
   // column is folded into the channel dimension of the output map, which needs whole store tiles.

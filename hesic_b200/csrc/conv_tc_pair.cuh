@@ -99,7 +99,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const int t0 = p.tap_begin[tk.ph], t1 = p.tap_begin[tk.ph + 1];
         const int kc0 = p.kc_lo[tk.nt & 7], kc1 = p.kc_hi[tk.nt & 7];   // block-banded layers skip empty K chunks
         const int ksteps = (t1 - t0) * (kc1 - kc0);
-        const int g = (p.gdn && lt > 0) ? min(GDN_AT, ksteps - 1) : -1;
+        const int g = (p.gdn && lt > 0) ? min(p.gdn_at, ksteps - 1) : -1;
         int ks = 0;
         for (int t = t0; t < t1; ++t) {
           const Tap tap = p.taps[t];
@@ -157,7 +157,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const TaskCoord tk = decode_pair_task(p, task, 0);
         const int buf = lt & 1;
         const int ksteps = (p.tap_begin[tk.ph + 1] - p.tap_begin[tk.ph]) * (p.kc_hi[tk.nt & 7] - p.kc_lo[tk.nt & 7]);
-        const int g = (p.gdn && lt > 0) ? min(GDN_AT, ksteps - 1) : -1;
+        const int g = (p.gdn && lt > 0) ? min(p.gdn_at, ksteps - 1) : -1;
         const uint32_t d_main = tmem_base + (uint32_t)buf * ACC_STRIDE, d_small = d_main + COL_SMALL;
         for (int ks = 0; ks < ksteps; ++ks) {
           if (ks == g) { gdn_step(lt - 1, 0); gdn_step(lt - 1, 1); }
