@@ -108,7 +108,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "stereo pairs/sec @512x512 (HSIC.forward)", "value": pps, "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.model} newnet1.HSIC forward, 1 pair 512x512 per step, torch CPU fp32 port of the reference"},
+            "config": {"workload": f"{'HESIC+ newnet1_joint' if args.model == 'hesic_plus' else 'HESIC newnet1'}.HSIC forward, 512x512 stereo pairs "
+                                   f"(BASELINE config {'3' if args.model == 'hesic_plus' else '2'}); bounded sample: 1 pair per step "
+                                   "(batch 1 is the CPU's fastest batch size per pair), torch CPU fp32 port of the reference",
+                       "pairs_per_step": 1},
             "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} forwards of 1 synthetic 512x512 pair (oracle/hesic_oracle.py, "
                                        "torch CPU fp32, all host threads)"},
