@@ -547,6 +547,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // can be handed back to the MMA warp before the (longer) store phase
         mbar_wait(norm_full, (uint32_t)lt & 1u, 8);
         tc_fence_after();
+        const bool igdn = p.gdn == 2;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int ch = 2 * i + grp;
@@ -554,17 +555,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tmem_ld32(acc + COL_SMALL + ch * 32, q);
           tmem_ld_wait();
           // beta four at a time (a 32-float table would sit on top of xs[64] + q[32] and spill)
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const float4 bt = ld_shared_f4(beta_s + 128u * ch + 16u * jj);
-            const float bv[4] = {bt.x, bt.y, bt.z, bt.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = 4 * jj + e;
-              const float nrm = __uint_as_float(q[j]) + bv[e];
-              xs[i * 32 + j] *= (p.gdn == 2) ? sqrt_approx(nrm) : rsqrt_approx(nrm);
-            }
+          // one uniform branch per 32-column chunk (not per element: `igdn ? sqrt : rsqrt` inside the unrolled loop
+          // became a branch around every group of four, 16 basic blocks whose LDS -> FADD -> MUFU -> FMUL latencies
+          // could not overlap); the chunk boundary also keeps the next chunk's TMEM load from being hoisted over
+          // this one's arithmetic, which would spill xs[]
+#define HESIC_GDN_SCALE_CHUNK(FN)                                                     \
+  _Pragma("unroll") for (int jj = 0; jj < 8; ++jj) {                                  \
+    const float4 bt = ld_shared_f4(beta_s + 128u * ch + 16u * jj);                    \
+    xs[i * 32 + 4 * jj + 0] *= FN(__uint_as_float(q[4 * jj + 0]) + bt.x);             \
+    xs[i * 32 + 4 * jj + 1] *= FN(__uint_as_float(q[4 * jj + 1]) + bt.y);             \
+    xs[i * 32 + 4 * jj + 2] *= FN(__uint_as_float(q[4 * jj + 2]) + bt.z);             \
+    xs[i * 32 + 4 * jj + 3] *= FN(__uint_as_float(q[4 * jj + 3]) + bt.w);             \
+  }
+          if (igdn) {
+            HESIC_GDN_SCALE_CHUNK(sqrt_approx)
+          } else {
+            HESIC_GDN_SCALE_CHUNK(rsqrt_approx)
           }
+#undef HESIC_GDN_SCALE_CHUNK
         }
         tc_fence_before();
         mbar_arrive(acc_empty(buf));
