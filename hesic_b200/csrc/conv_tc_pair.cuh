@@ -284,7 +284,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
         tc_fence_before();
         // both CTAs' epilogues release the accumulator buffer on the LEADER's barrier (the only MMA issuer)
-        mbar_arrive_cluster(acc_empty_leader);
+        mbar_arrive_remote(acc_empty_leader);
       } else {
         // fused GDN / IGDN, as in conv_tc_kernel; the x^2-ready signal of both CTAs goes to the leader's barrier
         float xs[64];
@@ -321,7 +321,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive_cluster(x2_full_leader);
+        mbar_arrive_remote(x2_full_leader);
         mbar_wait(norm_full, (uint32_t)lt & 1u, 8);
         tc_fence_after();
         const bool igdn = p.gdn == 2;
@@ -351,7 +351,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #undef HESIC_GDN_SCALE_CHUNK
         }
         tc_fence_before();
-        mbar_arrive_cluster(acc_empty_leader);
+        mbar_arrive_remote(acc_empty_leader);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float v[32];

@@ -236,6 +236,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Remote arrive that hands over TMEM state only (accumulator consumed / x^2 operand written: ordered by tcgen05.wait +
+// tcgen05.fence::before_thread_sync, no generic-proxy data crosses the CTA boundary): default semantics (.release.cta),
+// ONE SYNCS.ARRIVE in program order.  The .release.cluster form below costs MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR +
+// CGAERRBAR in front of the arrive -- on the accumulator hand-back of every tile.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
