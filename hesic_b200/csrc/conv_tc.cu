@@ -866,8 +866,12 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     for (int i = 0; i < p.n_tiles; ++i) { p.kc_lo[i] = c->kc_lo[i]; p.kc_hi[i] = c->kc_hi[i]; }
   }
   p.w_resident = (c->tc_kind == HESIC_TC_ROW2 && p.n_tiles == 1 && p.b_bytes <= (uint32_t)A_TILE_BYTES) ? 1 : 0;
-  if (getenv("HESIC_TC_NO_RESIDENT")) p.w_resident = 0;
-  p.wide_n = (!planar && p.BN == 128 && !getenv("HESIC_TC_NARROW")) ? 1 : 0;
+  // diagnostic switches, read once per process
+  static const bool env_no_resident = getenv("HESIC_TC_NO_RESIDENT") != nullptr, env_narrow = getenv("HESIC_TC_NARROW") != nullptr,
+                    env_direct_store = getenv("HESIC_TC_DIRECT_STORE") != nullptr,
+                    env_one_staging = getenv("HESIC_TC_ONE_STAGING") != nullptr;
+  if (env_no_resident) p.w_resident = 0;
+  p.wide_n = (!planar && p.BN == 128 && !env_narrow) ? 1 : 0;
   static const int gdn_at_env = getenv("HESIC_TC_GDN_AT") ? atoi(getenv("HESIC_TC_GDN_AT")) : GDN_AT;
   p.gdn_at = std::max(0, gdn_at_env);
   p.stage_bytes = 2u * A_TILE_BYTES + (p.w_resident ? 0u : 2u * p.b_bytes);
@@ -877,11 +881,11 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   const int esz = y->fmt == HESIC_FMT_NHWC_SPLIT ? 2 : 4;
   p.tma_store = (!planar && (yCs * esz) % 16 == 0 &&
                  (p.os == 1 || (p.os == 2 && c->Cout % store_ch == 0 && !((y->H | y->W) & 1)))) ? 1 : 0;
-  if (getenv("HESIC_TC_DIRECT_STORE")) p.tma_store = 0;
+  if (env_direct_store) p.tma_store = 0;
   int fixed = 1024 + BAR_BYTES + CHAN_BYTES + (p.tma_store ? STAGING_BYTES : 0) +
               (p.w_resident ? p.n_wtiles * 2 * (int)p.b_bytes : 0);
   p.stg_sets = 1;
-  if (p.tma_store && !getenv("HESIC_TC_ONE_STAGING")) {
+  if (p.tma_store && !env_one_staging) {
     // a second staging set where the operand pipeline keeps its depth: short-K layers are epilogue-bound and every store
     // pair otherwise waits for the previous pair to leave shared memory (r01 profile of the first analysis layer: 11 %)
     const int st2 = (SMEM_LIMIT - fixed - STAGING_BYTES) / (int)p.stage_bytes;
