@@ -252,7 +252,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
     for (int b = 0; b < NACC; ++b) acc_empty_tgt[b] = PAIR ? mapa_cta(acc_empty(b), 0) : acc_empty(b);
     auto release_acc = [&](int b) {
-      if (PAIR) mbar_arrive_cluster(acc_empty_tgt[b]);   // the leader's MMA thread waits for both CTAs' epilogues
+      if (PAIR) mbar_arrive_remote(acc_empty_tgt[b]);    // the leader's MMA thread waits for both CTAs' epilogues (TMEM-only hand-over)
       else mbar_arrive(acc_empty_tgt[b]);
     };
     for (int lt = grp, u = ufirst + grp * ustep; u < n_units; u += 2 * ustep, lt += 2) {
