@@ -229,6 +229,37 @@ def test_perspective_transform_maps_the_corners():
     assert torch.allclose(q[..., :2] / q[..., 2:], 2 * dst.double(), atol=5e-3)
 
 
+def test_warp_perspective_agrees_with_the_convention_the_reference_computes_H_in():
+    """kornia is un-vendored (warp parity unpinned), but the reference's own data pipeline fixes the convention:
+    its H comes from cv2.findHomography on keypoints in PIXEL coordinates (compressai/datasets/utils.py:52-57) and
+    is handed unchanged to kornia.warp_perspective (newnet1.py:746).  The oracle's warp must therefore agree with
+    cv2.warpPerspective for the same H: up to cv2's 5-bit interpolation weights with align_corners=True, while the
+    align_corners=False variant of kornia 0.4.x is off by half-pixel shifts (an order of magnitude more)."""
+    cv2 = pytest.importorskip("cv2")
+    x1, _, h = synth.stereo_pairs(2, 128, 160, seed=7)
+
+    def against_cv2(align):
+        w = O.warp_perspective(x1, h, (128, 160), align_corners=align)
+        worst, mean = 0.0, 0.0
+        for b in range(2):
+            ref = cv2.warpPerspective(x1[b].permute(1, 2, 0).numpy(), h[b].numpy().astype(np.float64), (160, 128),
+                                      flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+            d = np.abs(w[b].permute(1, 2, 0).numpy() - ref)
+            worst, mean = max(worst, float(d.max())), max(mean, float(d.mean()))
+        return worst, mean
+
+    worst, mean = against_cv2(True)
+    assert worst < 2e-2 and mean < 1.5e-3, (worst, mean)        # 1/32-pixel weight quantisation of cv2
+    worst_f, mean_f = against_cv2(False)
+    assert worst_f > 5 * worst and mean_f > 10 * mean, (worst_f, mean_f)
+    # identity and a whole-pixel translation are exact resamplings
+    assert (O.warp_perspective(x1[:1], torch.eye(3)[None], (128, 160)) - x1[:1]).abs().max() < 1e-4
+    shift = torch.tensor([[[1., 0, 5], [0, 1, -3], [0, 0, 1]]])
+    ref = torch.zeros_like(x1[:1])
+    ref[:, :, :-3, 5:] = x1[:1, :, 3:, :-5]
+    assert (O.warp_perspective(x1[:1], shift, (128, 160)) - ref).abs().max() < 1e-4
+
+
 def test_dsic_independent_en_oracle_vs_reference_fixture():
     from hesic_b200 import compat
     compat.install()
