@@ -121,7 +121,37 @@ def check(rc):
 
 
 def stream():
+    """Current stream of the CURRENT device: callers run under ``device_guard`` / ``torch.cuda.device(t.device)``, so
+    that is the device of the tensors being passed."""
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _first_cuda_tensor(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a
+        elif isinstance(a, (list, tuple)):
+            for b in a:
+                if isinstance(b, torch.Tensor) and b.is_cuda:
+                    return b
+    return None
+
+
+def device_guard(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current: the library allocates its packed operands
+    and launches on the current device / its current stream, so a model living on cuda:1 while cuda:0 is current must
+    switch for the duration of the call (as torch's own operators do)."""
+    import functools
+
+    @functools.wraps(fn)
+    def inner(*args, **kwargs):
+        t = _first_cuda_tensor(args, kwargs)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return inner
 
 
 def require_cuda(*tensors):

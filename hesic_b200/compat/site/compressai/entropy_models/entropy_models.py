@@ -180,6 +180,11 @@ class EntropyBottleneck(EntropyModel):
         super().__init__(*args, **kwargs)
         self.channels = int(channels)
         self.filters = tuple(int(f) for f in filters)
+        if self.filters != (3, 3, 3, 3):
+            # the only configuration on the path (newnet1.py:42-45 builds EntropyBottleneck(channels) with the default);
+            # refuse at construction rather than at the first forward
+            raise NotImplementedError(f"hesic_b200 EntropyBottleneck supports filters=(3, 3, 3, 3) only (the reference's "
+                                      f"default and the only value HSIC / DSIC use), got {self.filters}")
         self.init_scale = float(init_scale)
         self.tail_mass = float(tail_mass)
 
@@ -208,7 +213,7 @@ class EntropyBottleneck(EntropyModel):
         if self.filters != (3, 3, 3, 3):
             raise NotImplementedError("hesic_b200 EntropyBottleneck kernel is specialised for filters=(3,3,3,3)")
         ts = list(self._matrices) + list(self._biases) + list(self._factors) + [self.quantiles]
-        key = tuple((t.data_ptr(), t._version) for t in ts)
+        key = tuple((t.data_ptr(), t._version, t.device.index) for t in ts)
         if key != self._packed_key:
             self._packed = _F.eb_pack(list(self._matrices), list(self._biases), list(self._factors), self.quantiles)
             self._packed_key = key

@@ -49,6 +49,23 @@ inline int launched(const char *name) {
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+inline int current_device() {
+  int d = 0;
+  return cudaGetDevice(&d) == cudaSuccess ? d : -1;
+}
+// cudaFuncSetAttribute and friends are per device: first() is true once per device of this process (one process per
+// GPU is the normal deployment, but a model moved to another device of the same process must still launch)
+struct PerDeviceOnce {
+  unsigned long long done = 0;
+  bool first() {
+    const int d = current_device();
+    if (d < 0 || d > 63) return true;
+    if ((done >> d) & 1ull) return false;
+    done |= 1ull << d;
+    return true;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Device view of a hesic_tensor
 struct TView {

@@ -24,6 +24,7 @@ struct hesic_conv {
   int CoutPad = 0;
   int tc_kind = HESIC_TC_GENERIC, tc_taps = 0, tc_k = 0;   // w_hi/w_lo are [tc_taps][CoutPad][tc_k]
   bool loaded = false;
+  int device = -1;   // device that owns the packed operands below (the device current at the last hesic_conv_load)
   // MaskedConv2d: bit t set = tap t (ky*kw + kx) has a non-zero mask entry; dead taps are skipped by the tcgen05 path
   // (mask type 'A' of a 5x5 kernel keeps 12 of 25 taps, compressai/layers/layers.py:36-40)
   uint64_t live_taps = ~0ull;

@@ -348,18 +348,35 @@ extern "C" hesic_conv *hesic_conv_create(int Cin, int Cout, int kh, int kw, int 
   return c;
 }
 
-extern "C" void hesic_conv_destroy(hesic_conv *c) {
-  if (!c) return;
+static void conv_release(hesic_conv *c) {
   cudaFree(c->w_simt); cudaFree(c->bias); cudaFree(c->w_hi); cudaFree(c->w_lo);
   cudaFree(c->gdn_beta); cudaFree(c->gdn_w_simt); cudaFree(c->gdn_g_hi); cudaFree(c->gdn_g_lo);
+  c->w_simt = c->bias = nullptr; c->w_hi = c->w_lo = nullptr;
+  c->gdn_beta = c->gdn_w_simt = nullptr; c->gdn_g_hi = c->gdn_g_lo = nullptr;
+  c->tc_maps_bn = 0; c->tc_maps_gdn = -1;     // cached tensor maps point into the freed operands
+  c->loaded = false; c->has_gdn = false;
+}
+
+extern "C" void hesic_conv_destroy(hesic_conv *c) {
+  if (!c) return;
+  conv_release(c);
   free(c->tc_maps);
   delete c;
+}
+
+// The packed operands live on the device that was current when they were packed.  A model moved to another device
+// (`model.to('cuda:1')`) re-packs (the host side keys on the device index): free the old device's copies first.
+static void conv_claim_device(hesic_conv *c) {
+  const int dev = current_device();
+  if (c->device >= 0 && c->device != dev) conv_release(c);
+  c->device = dev;
 }
 
 extern "C" int hesic_conv_load(hesic_conv *c, const float *weight, const float *bias, const float *mask, void *stream) {
   HESIC_REQUIRE(c && weight, "hesic_conv_load: null argument");
   cudaStream_t s = as_stream(stream);
   size_t taps = (size_t)c->kh * c->kw;
+  conv_claim_device(c);
   if (!c->w_simt) {
     HESIC_CUDA(cudaMalloc(&c->w_simt, taps * c->Cin * c->Cout * sizeof(float)));
     HESIC_CUDA(cudaMalloc(&c->bias, c->Cout * sizeof(float)));
@@ -414,6 +431,8 @@ extern "C" int hesic_conv_set_gdn(hesic_conv *c, const float *beta, const float 
                                   void *stream) {
   HESIC_REQUIRE(c, "hesic_conv_set_gdn: null conv");
   if (!beta || !gamma) { c->has_gdn = false; return HESIC_OK; }
+  HESIC_REQUIRE(c->device < 0 || c->device == current_device(),
+                "hesic_conv_set_gdn: the layer's operands live on device %d, the current device is %d", c->device, current_device());
   int C = c->Cout;
   if (!c->gdn_beta) {
     HESIC_CUDA(cudaMalloc(&c->gdn_beta, C * sizeof(float)));
@@ -483,6 +502,8 @@ extern "C" int hesic_conv_enable_gdn(hesic_conv *c, int enable) {
 static int conv_forward_any(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *xb, const hesic_tensor *y, int act,
                             int path, void *stream) {
   HESIC_REQUIRE(c && c->loaded, "hesic_conv_forward: weights not loaded");
+  HESIC_REQUIRE(c->device == current_device(), "hesic_conv_forward: the layer's operands live on device %d, the current device is %d "
+                "(load the weights and launch with the tensors' device current)", c->device, current_device());
   int r;
   if ((r = check_tensor(x, "conv input")) != HESIC_OK) return r;
   if (xb && (r = check_tensor(xb, "conv input (second part)")) != HESIC_OK) return r;

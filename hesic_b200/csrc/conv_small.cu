@@ -183,11 +183,9 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const Args a) {
 template <int CIN, int COUT>
 static int launch(const Args &a, cudaStream_t s) {
   const int smem = (CIN * 25 * 4 + CIN * ROWS * PITCH) * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  if (once.first())
     HESIC_CUDA(cudaFuncSetAttribute(conv_small_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
   dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B);
   conv_small_kernel<CIN, COUT><<<grid, NT, smem, s>>>(a);
   HESIC_LAUNCHED("conv_small_kernel");

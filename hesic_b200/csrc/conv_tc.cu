@@ -750,7 +750,8 @@ template <int COUT>
 static int launch_head(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int act, cudaStream_t s) {
   using namespace tc;
   static int num_sms = 0;
-  if (!num_sms) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     int dev = 0;
     HESIC_CUDA(cudaGetDevice(&dev));
     HESIC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -815,13 +816,12 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     }
   }
   static int num_sms = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     int dev = 0;
     HESIC_CUDA(cudaGetDevice(&dev));
     HESIC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     HESIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
   }
   const int xCs = x->Cs > 0 ? x->Cs : x->C, yCs = y->Cs > 0 ? y->Cs : y->C;
   const bool planar = c->Cout <= 4;
@@ -980,11 +980,9 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   static const bool pair_on = getenv("HESIC_TC_SINGLE_CTA") == nullptr;
   if (pair_on && c->tc_kind == HESIC_TC_GENERIC && !planar && p.tma_store && p.BN == 128 && !p.w_resident &&
       num_sms >= 2 && p.kchunks * ntaps >= 8) {
-    static bool pair_attr = false;
-    if (!pair_attr) {
+    static PerDeviceOnce pair_once;
+    if (pair_once.first())
       HESIC_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-      pair_attr = true;
-    }
     CUtensorMap mw64;
     {
       uint64_t dims[3] = {(uint64_t)c->tc_k, (uint64_t)c->CoutPad, (uint64_t)c->tc_taps};

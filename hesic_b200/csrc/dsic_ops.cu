@@ -388,10 +388,11 @@ extern "C" int hesic_dense_warp(const hesic_tensor *h1, const hesic_tensor *cost
     HESIC_REQUIRE(h1->H <= 65535 && h1->B <= 65535, "dense_warp: image too tall / batch too large");
     const size_t smem = ((size_t)(DWN_TX + cost->C - 1) * h1->C + (size_t)DWN_TX * cost->C) * sizeof(float);
     HESIC_REQUIRE(smem <= 200 * 1024, "dense_warp (channels-last): %d channels x %d disparities do not fit shared memory", h1->C, cost->C);
-    static size_t attr = 0;
-    if (smem > attr) {
+    static size_t attr[64] = {0};
+    const int dv = current_device() & 63;
+    if (smem > attr[dv]) {
       HESIC_CUDA(cudaFuncSetAttribute(dense_warp_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = smem;
+      attr[dv] = smem;
     }
     dim3 grid((h1->W + DWN_TX - 1) / DWN_TX, h1->H, h1->B);
     dense_warp_nhwc_kernel<<<grid, 256, smem, as_stream(stream)>>>(view(h1), view(cost), view(out));

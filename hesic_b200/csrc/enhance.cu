@@ -40,6 +40,7 @@ struct hesic_en_conv {
   __nv_bfloat16 *w_pair = nullptr;   // CTA-pair layout [2 ranks][9][N + N/2][64], see en_pack_w_pair_kernel
   float *bias = nullptr;        // [32]
   bool loaded = false;
+  int device = -1;              // device that owns w / w_pair / bias
   CUtensorMap map_w, map_w_pair;
 };
 
@@ -480,6 +481,11 @@ extern "C" void hesic_en_conv_destroy(hesic_en_conv *c) {
 extern "C" int hesic_en_conv_load(hesic_en_conv *c, const float *weight, const float *bias, void *stream) {
   HESIC_REQUIRE(c && weight, "hesic_en_conv_load: null argument");
   cudaStream_t s = as_stream(stream);
+  if (c->device >= 0 && c->device != current_device()) {     // the model moved to another device: re-pack there
+    cudaFree(c->w); cudaFree(c->w_pair); cudaFree(c->bias);
+    c->w = c->w_pair = nullptr; c->bias = nullptr; c->loaded = false;
+  }
+  c->device = current_device();
   if (!c->w) {
     HESIC_CUDA(cudaMalloc(&c->w, (size_t)9 * 2 * c->N * 64 * sizeof(__nv_bfloat16)));
     HESIC_CUDA(cudaMalloc(&c->bias, 32 * sizeof(float)));
@@ -516,6 +522,8 @@ extern "C" int hesic_en_conv_forward(hesic_en_conv *c, const hesic_tensor *x, co
                                      const hesic_tensor *res1, const hesic_tensor *res2, void *stream) {
   using namespace en;
   HESIC_REQUIRE(c && c->loaded, "hesic_en_conv_forward: weights not loaded");
+  HESIC_REQUIRE(c->device == current_device(), "hesic_en_conv_forward: the layer's operands live on device %d, the current device is %d",
+                c->device, current_device());
   int r;
   if ((r = check_hilo32(x, "en conv input")) != HESIC_OK) return r;
   HESIC_REQUIRE(x->C >= c->Cin, "en conv: input has %d channels, layer expects %d", x->C, c->Cin);
@@ -543,7 +551,8 @@ extern "C" int hesic_en_conv_forward(hesic_en_conv *c, const hesic_tensor *x, co
   if ((int64_t)x->B * x->H * x->W == 0) return HESIC_OK;
 
   static int num_sms = 0;
-  if (!num_sms) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     int dev = 0;
     HESIC_CUDA(cudaGetDevice(&dev));
     HESIC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));

@@ -20,7 +20,7 @@ import torch
 
 from . import _capi as C
 from . import functional as F
-from .engine import _LIVE, HesicEngine, _keep, _nchw, _nhwc, _split
+from .engine import CapturedForward, HesicEngine
 
 _lib = C.lib
 
@@ -39,7 +39,7 @@ class DsicEngine(HesicEngine):
             t, c0 = dst
         else:
             c0 = 0
-            t = {"split": _split, "nhwc": _nhwc}[kind](B, Ho, Wo, Cout, self.dev) if kind != "nchw" else _nchw(B, Cout, Ho, Wo, self.dev)
+            t = {"split": self._split, "nhwc": self._nhwc}[kind](B, Ho, Wo, Cout) if kind != "nchw" else self._nchw(B, Cout, Ho, Wo)
         d = {"split": C.split, "nhwc": C.nhwc, "nchw": C.nchw}[kind](t, Cout, c0)
         plan.run(x_desc, d, act, self.path)
         return t, d, Ho, Wo
@@ -95,7 +95,7 @@ class DsicEngine(HesicEngine):
         t, _, Ho, Wo = self._conv(plan, x_desc, B, H, W, "nhwc")
         Cn = plan.geom[1]
         if dst is None:
-            dst = (_split(B, Ho, Wo, Cn, self.dev), 0)
+            dst = (self._split(B, Ho, Wo, Cn), 0)
         self._gn(gn_mod, t, dst[0], dst[1], Cn, weight, bias)
         return C.split(dst[0], Cn, dst[1])
 
@@ -104,7 +104,7 @@ class DsicEngine(HesicEngine):
         volume j (channels 224j .. 224j+223 of the NHWC fp32 global-context tensor); followed by dense_warp -> w."""
         N, FC = cv.N, cv.F0 * cv.C
         m1, m2, m3 = cv.model1, cv.model2, cv.model3
-        cat3 = _split(B, H, W, N + FC, self.dev)                      # cat(h_out, d_out)  mynet6_plus.py:308
+        cat3 = self._split(B, H, W, N + FC)                      # cat(h_out, d_out)  mynet6_plus.py:308
         # model1 on cat(h1, h2) = slots [2N, 3N) ++ [N, 2N): read as the slice [N, 3N) with swapped weight halves
         u = self._conv_gn(self._swapped_plan(m1[0]), m1[1], C.split(lvl, 2 * N, N), B, H, W)
         self._conv_gn(m1[3], m1[4], u, B, H, W, dst=(cat3, 0))
@@ -112,17 +112,17 @@ class DsicEngine(HesicEngine):
         # (depth, feature)-ordered channels (the global-context conv already emits that order, see forward()),
         # GroupNorm(1 group) with its per-feature affine repeated over the depths
         D, F0 = cv.C, cv.F0
-        up = _split(B, H, W, FC, self.dev)
+        up = self._split(B, H, W, FC)
         C.check(_lib.hesic_upsample_bilinear(C.ref(C.nhwc(ctx_t, FC, FC * j)), C.ref(C.split(up)), cv.scale_factor, C.stream()))
         g1, g2 = m2[1], m2[4]
-        exp = lambda v: _keep(v.detach().repeat(D).contiguous())
+        exp = lambda v: self._keep(v.detach().repeat(D).contiguous())
         v = self._conv_gn(m2[0]._plan_for(D, True), g1, C.split(up), B, H, W, weight=exp(g1.weight), bias=exp(g1.bias))
         self._conv_gn(m2[3]._plan_for(D, True), g2, v, B, H, W, dst=(cat3, N), weight=exp(g2.weight), bias=exp(g2.bias))
         # model3 -> softmax over the disparities
         v = self._conv_gn(self._perm_plan(m3[0], "dm", in_perm=self._depth_major(F0, D, 1, N)), m3[1], C.split(cat3), B, H, W)
         v = self._conv_gn(m3[3], m3[4], v, B, H, W)
         raw, raw_d, _, _ = self._conv(self._plan(m3[6]), v, B, H, W, "nhwc")
-        cost = _nhwc(B, H, W, cv.C, self.dev)
+        cost = self._nhwc(B, H, W, cv.C)
         C.check(_lib.hesic_softmax_channels(C.ref(raw_d), C.ref(C.nhwc(cost)), C.stream()))
         # dense_warp(h1 = g, cost) -> w
         C.check(_lib.hesic_dense_warp(C.ref(C.split(lvl, N, 2 * N)), C.ref(C.nhwc(cost)), C.ref(C.split(lvl, N, 0)), C.stream()))
@@ -137,15 +137,24 @@ class DsicEngine(HesicEngine):
         B, _, H, W = x1.shape
         if H % 64 or W % 64:
             raise ValueError("DSIC.forward needs H and W divisible by 64")
-        del _LIVE[:]
-        x1 = _keep(x1.float().contiguous())
-        x2 = _keep(x2.float().contiguous())
+        with torch.cuda.device(x1.device):
+            return self._forward(x1, x2, B, H, W)
+
+    def capture(self, x1, x2):
+        C.require_cuda(x1, x2)
+        return CapturedForward(self, (x1, x2), self.forward)
+
+    def _forward(self, x1, x2, B, H, W):
+        m = self.m
         self.dev = dev = x1.device
+        main = self._begin(dev)
+        x1 = self._keep(x1.float().contiguous())
+        x2 = self._keep(x2.float().contiguous())
         N, M, K = m.N, m.M, m.K
         acc = torch.zeros(4, device=dev, dtype=torch.float64)
         self.log2_sums = acc
         a = lambda i: acc[i:i + 1]
-        lv = [None] + [_split(B, H >> s, W >> s, 3 * N, dev) for s in (1, 2, 3, 3, 2, 1)]   # level buffers 1..6
+        lv = [None] + [self._split(B, H >> s, W >> s, 3 * N) for s in (1, 2, 3, 3, 2, 1)]   # level buffers 1..6
         g = lambda k: C.split(lv[k], N, 2 * N)
         wa = lambda k: C.split(lv[k], 2 * N, 0)
 
@@ -155,7 +164,7 @@ class DsicEngine(HesicEngine):
         self._run(e1.g_a_conv2, g(1), B, H >> 1, W >> 1, "split", gdn=e1.g_a_gdn2, dst=(lv[2], 2 * N))
         self._run(e1.g_a_conv3, g(2), B, H >> 2, W >> 2, "split", gdn=e1.g_a_gdn3, dst=(lv[3], 2 * N))
         y1, y1_d, Hy, Wy = self._run(e1.g_a_conv4, g(3), B, H >> 3, W >> 3, "nhwc")
-        y1_abs = _split(B, Hy, Wy, M, dev)
+        y1_abs = self._split(B, Hy, Wy, M)
         self._convert(y1_d, C.split(y1_abs), C.OP_ABS)
         R, L = C.ACT_RELU, C.ACT_LEAKY
         z1, z1_d, Hz, Wz = self._seq3(m._h_a1.encode_hyper, (0, 2, 4), (R, R, C.ACT_NONE), C.split(y1_abs), B, Hy, Wy, "nhwc")
@@ -189,11 +198,11 @@ class DsicEngine(HesicEngine):
         y2, y2_d, _, _ = self._run(m.pic2_g_a_conv4, wa(3), B, H >> 3, W >> 3, "nhwc")
 
         # ---- view 2 entropy model, conditioned on y1_hat (mynet6_plus.py:719-723) ---------------------
-        y2_abs = _split(B, Hy, Wy, M, dev)
+        y2_abs = self._split(B, Hy, Wy, M)
         self._convert(y2_d, C.split(y2_abs), C.OP_ABS)
         z2, z2_d, Hz, Wz = self._seq3(m._h_a2.encode_hyper, (0, 2, 4), (R, R, C.ACT_NONE), C.split(y2_abs), B, Hy, Wy, "nhwc")
         z2_hat, z2h_d, z2_lik = self._bottleneck(m.entropy_bottleneck2, z2, z2_d, B, Hz, Wz, a(3))
-        cond = _split(B, Hy, Wy, N + M, dev)                                       # cat(up(z2_hat), y1_hat)
+        cond = self._split(B, Hy, Wy, N + M)                                       # cat(up(z2_hat), y1_hat)
         C.check(_lib.hesic_upsample_bilinear(C.ref(z2h_d), C.ref(C.split(cond, N, 0)), 4, C.stream()))
         self._convert(y1h_d, C.split(cond, M, N))
         hs = m._h_s2
@@ -212,5 +221,6 @@ class DsicEngine(HesicEngine):
         self._cost_volume(m._cost_volume6, lv[6], ctx, 0, B, H >> 1, W >> 1)
         x2_hat, _, _, _ = self._run(m.pic2_g_s_conv4, wa(6), B, H >> 1, W >> 1, "nchw")
 
+        self._end(main)
         return {"x1_hat": x1_hat, "x2_hat": x2_hat,
                 "likelihoods": {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}}

@@ -29,30 +29,109 @@ from . import functional as F
 _lib = C.lib
 
 
-# Every intermediate is referenced by raw pointer from kernels queued on the stream, so the torch
-# tensors that own the memory are kept alive until the next forward() (``_LIVE``); otherwise the
-# caching allocator could hand a dropped buffer to a later layer while an earlier kernel still reads it.
-_LIVE = []
+def _none():
+    return None
 
 
-def _keep(t):
-    _LIVE.append(t)
-    return t
+class EngineBase:
+    """Ownership rules shared by the engines.
+
+    * Every intermediate is referenced by raw pointer from kernels queued on the stream, so the torch tensors that own
+      the memory are kept alive until the NEXT forward of the SAME engine (``self._live``); otherwise the caching
+      allocator could hand a dropped buffer to a later layer while an earlier kernel still reads it.  The list is
+      per engine: two models (or two threads, one per GPU) never free each other's in-flight buffers.
+    * ``self._done`` is recorded on the caller's stream at the end of a forward; the next forward -- possibly issued on
+      another stream -- waits for it before it drops the previous intermediates and before its side stream starts, so
+      a reused block is never written while the previous forward still reads it.
+    * An engine holds streams, events and device buffers: it is never copied or pickled with its model
+      (``copy.deepcopy(model)`` / ``torch.save(model)`` see ``None`` and the copy builds its own engine lazily).
+    """
+    _live = None
+    _done = None
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_none, ())
+
+    def _begin(self, dev):
+        main = torch.cuda.current_stream(dev)
+        if self._done is not None:
+            main.wait_event(self._done)
+        self._live = []
+        return main
+
+    def _end(self, main):
+        if self._done is None:
+            self._done = torch.cuda.Event()
+        self._done.record(main)
+
+    def _keep(self, t):
+        self._live.append(t)
+        return t
+
+    def _split(self, B, H, W, Cn):
+        return self._keep(torch.empty((2, B, H, W, Cn), device=self.dev, dtype=torch.bfloat16))
+
+    def _nhwc(self, B, H, W, Cn):
+        return self._keep(torch.empty((B, H, W, Cn), device=self.dev, dtype=torch.float32))
+
+    def _nchw(self, B, Cn, H, W):
+        return self._keep(torch.empty((B, Cn, H, W), device=self.dev, dtype=torch.float32))
 
 
-def _split(B, H, W, Cn, dev):
-    return _keep(torch.empty((2, B, H, W, Cn), device=dev, dtype=torch.bfloat16))
+class CapturedForward:
+    """One forward of an engine frozen into a CUDA graph for fixed input shapes: static
+    input buffers, every intermediate and output allocated once from the graph's private pool, ~60 kernel launches
+    replayed by one ``cudaGraphLaunch`` -- no per-forward ``torch.empty``, no Python between kernels.
+
+        g = net.hesic_engine.capture(x1, x2, h)        # shapes (and the weights) are frozen here
+        out = g.replay(x1b, x2b, hb)                   # copies the new inputs into the static buffers, replays
+        g.log2_sums                                    # the bpp partial sums of that replay
+
+    ``out`` are the SAME tensors on every replay (overwritten in place), as with any CUDA graph.  Re-capture after
+    changing weights (packed operands are baked into the graph's kernel arguments)."""
+
+    def __init__(self, engine, inputs, run):
+        dev = inputs[0].device
+        self.engine = engine
+        with torch.cuda.device(dev):
+            self.inputs = tuple(t.detach().float().contiguous().clone() for t in inputs)
+            # warm-up on a side stream (packs weights, sizes library scratch, primes the allocator) -- none of that may
+            # happen inside the capture
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    run(*self.inputs)
+            torch.cuda.current_stream(dev).wait_stream(s)
+            torch.cuda.synchronize(dev)
+            engine._done, engine._live = None, []     # nothing recorded outside the capture may be waited on inside it
+            self.graph = torch.cuda.CUDAGraph()
+            before = int(_lib.hesic_launch_count(0))
+            with torch.cuda.graph(self.graph):
+                self.outputs = run(*self.inputs)
+                self.log2_sums = engine.log2_sums
+            self.n_launches = int(_lib.hesic_launch_count(0)) - before
+            # the graph owns these buffers for its whole life: take them out of the engine's per-forward list
+            self._live, engine._live = engine._live, []
+            self._static = [dict(getattr(engine, "_rowpads", {})), dict(getattr(engine, "_perm_plans", {}))]
+            engine._done = None
+
+    def replay(self, *inputs):
+        if inputs:
+            if len(inputs) != len(self.inputs):
+                raise ValueError(f"expected {len(self.inputs)} inputs")
+            for d, s in zip(self.inputs, inputs):
+                if d.shape != s.shape:
+                    raise ValueError(f"captured for input shape {tuple(d.shape)}, got {tuple(s.shape)}")
+                d.copy_(s, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
 
 
-def _nhwc(B, H, W, Cn, dev):
-    return _keep(torch.empty((B, H, W, Cn), device=dev, dtype=torch.float32))
-
-
-def _nchw(B, Cn, H, W, dev):
-    return _keep(torch.empty((B, Cn, H, W), device=dev, dtype=torch.float32))
-
-
-class HesicEngine:
+class HesicEngine(EngineBase):
     def __init__(self, model, variant, align_corners=True, path=C.PATH_AUTO):
         self._rowpads = {}
         assert variant in ("newnet1", "newnet9", "joint")
@@ -95,7 +174,7 @@ class HesicEngine:
             t, c0 = dst
         else:
             c0 = 0
-            t = {"split": _split, "nhwc": _nhwc}[kind](B, Ho, Wo, Cout, dev) if kind != "nchw" else _nchw(B, Cout, Ho, Wo, dev)
+            t = {"split": self._split, "nhwc": self._nhwc}[kind](B, Ho, Wo, Cout) if kind != "nchw" else self._nchw(B, Cout, Ho, Wo)
         d = {"split": C.split, "nhwc": C.nhwc, "nchw": C.nchw, "rowpad": C.rowpad}[kind](t, Cout, c0)
         plan.run(x_desc, d, act, self.path, xb_desc)
         return t, d, Ho, Wo
@@ -107,6 +186,8 @@ class HesicEngine:
         t = self._rowpads.get(key)
         if t is None:
             t = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, slots), device=self.dev, dtype=torch.bfloat16)
+            # buffers of other shapes / devices are dropped (70 MB each at B = 16, 512 x 512), as EnhanceEngine does
+            self._rowpads = {k: v for k, v in self._rowpads.items() if k[1:4] == key[1:4] and k[5] == key[5]}
             self._rowpads[key] = t
         return t
 
@@ -150,8 +231,8 @@ class HesicEngine:
     def _bottleneck(self, eb, z, zd, B, H, W, acc):
         """EntropyBottleneck.forward: z (NHWC fp32) -> z_hat (split NHWC), likelihood (NCHW fp32)."""
         Cn = z.shape[-1]
-        z_hat = _split(B, H, W, Cn, self.dev)
-        lik = _nchw(B, Cn, H, W, self.dev)
+        z_hat = self._split(B, H, W, Cn)
+        lik = self._nchw(B, Cn, H, W)
         zh_d = C.split(z_hat)
         C.check(_lib.hesic_entropy_bottleneck(C.ref(zd), C.ptr(eb.hesic_params()), eb._lik_bound(), C.ref(zh_d),
                                               C.ref(C.nchw(lik)), C.ptr(acc), C.stream()))
@@ -161,19 +242,19 @@ class HesicEngine:
         """gmm_weights branch (newnet1.py:484-512 / 546-574): -> softmaxed weights [B, K*M]."""
         _, d, H1, W1 = self._run(seq[0], x_desc, B, H, W, "split", act=C.ACT_LEAKY)
         t, d, H2, W2 = self._run(seq[2], d, B, H1, W1, "nhwc")
-        pooled = _keep(torch.empty((B, K * M), device=self.dev, dtype=torch.float32))
+        pooled = self._keep(torch.empty((B, K * M), device=self.dev, dtype=torch.float32))
         C.check(_lib.hesic_spatial_max(C.ref(d), C.ptr(pooled), C.stream()))
         conv1x1 = seq[5]
-        out = _keep(torch.empty((B, K * M), device=self.dev, dtype=torch.float32))
+        out = self._keep(torch.empty((B, K * M), device=self.dev, dtype=torch.float32))
         w = conv1x1.weight.detach()
         C.check(_lib.hesic_mixture_weights(C.ptr(pooled), C.ptr(w), C.ptr(conv1x1.bias.detach()), B, K, M, C.ptr(out), C.stream()))
         return out
 
     def _gmm(self, gm, y_d, s_d, m_d, w, B, H, W, M, K, acc):
         """-> y_hat (NCHW, returned to the caller), likelihood (NCHW), y_hat as SPLIT planes (synthesis input)."""
-        y_hat = _nchw(B, M, H, W, self.dev)
-        lik = _nchw(B, M, H, W, self.dev)
-        yh_split_d = C.split(_split(B, H, W, M, self.dev))
+        y_hat = self._nchw(B, M, H, W)
+        lik = self._nchw(B, M, H, W)
+        yh_split_d = C.split(self._split(B, H, W, M))
         C.check(_lib.hesic_gaussian_conditional(C.ref(y_d), C.ref(s_d), C.ref(m_d), C.ptr(w), K, 1, gm._scale_bound_value(),
                                                 gm._lik_bound(), C.ref(C.nchw(y_hat)), C.ref(C.nchw(lik)), C.ref(yh_split_d),
                                                 C.ptr(acc), C.stream()))
@@ -191,11 +272,21 @@ class HesicEngine:
             raise ValueError("HSIC.forward needs H and W divisible by 64 (four stride-2 stages + two in the hyper path)")
         if tuple(h.shape) != (B, 3, 3):
             raise ValueError(f"h_matrix must be [B,3,3], got {tuple(h.shape)}")
-        del _LIVE[:]
-        x1 = _keep(x1.float().contiguous())
-        x2 = _keep(x2.float().contiguous())
-        h = _keep(h.float().contiguous())
+        with torch.cuda.device(x1.device):
+            return self._forward(x1, x2, h, B, H, W)
+
+    def capture(self, x1, x2, h):
+        """Freeze one forward for these input shapes into a CUDA graph (see ``CapturedForward``)."""
+        C.require_cuda(x1, x2, h)
+        return CapturedForward(self, (x1, x2, h), self.forward)
+
+    def _forward(self, x1, x2, h, B, H, W):
+        m = self.m
         self.dev = dev = x1.device
+        main = self._begin(dev)
+        x1 = self._keep(x1.float().contiguous())
+        x2 = self._keep(x2.float().contiguous())
+        h = self._keep(h.float().contiguous())
         M, K = m.M, m.K
         acc = torch.zeros(4, device=dev, dtype=torch.float64)  # sum log2 p: y1, y2, z1, z2
         self.log2_sums = acc
@@ -207,8 +298,8 @@ class HesicEngine:
         side = self._side_stream(dev) if self.two_streams else main
         if side is not main:
             side.wait_stream(main)
-        x1_warp = _nchw(B, 3, H, W, dev)
-        cat_out = _nchw(B, 6, H, W, dev)   # cat(after_gdn(..), x1_hat_warp)  newnet1.py:686
+        x1_warp = self._nchw(B, 3, H, W)
+        cat_out = self._nchw(B, 6, H, W)   # cat(after_gdn(..), x1_hat_warp)  newnet1.py:686
         with torch.cuda.stream(side):
             # ---- view 2 analysis -------------------------------------------------------------
             self._warp(C.nchw(x1), h, C.nchw(x1_warp))
@@ -219,7 +310,7 @@ class HesicEngine:
                 _, pre_d, _, _ = self._run(enc2.pre_conv, C.nchw(x1_warp), B, H, W, "rowpad", gdn=enc2.pre_gdn,
                                            dst=(self._rowpad_buf("pre", B, H, W), 0), xb_desc=C.nchw(x2))
             else:
-                cat_in = _nchw(B, 6, H, W, dev)
+                cat_in = self._nchw(B, 6, H, W)
                 self._convert(C.nchw(x1_warp), C.nchw(cat_in, 3, 0))
                 self._convert(C.nchw(x2), C.nchw(cat_in, 3, 3))
                 cin_d = C.nchw(cat_in) if self.path == C.PATH_SIMT else self._rowpad("cat_in", C.nchw(cat_in), B, 6, H, W)
@@ -228,7 +319,7 @@ class HesicEngine:
             y2, y2_d, Hy2, Wy2 = self._analysis(enc2, pre_d, B, H, W)
             z2_pre = None
             if not joint:
-                y2_abs = _split(B, Hy2, Wy2, M, dev)
+                y2_abs = self._split(B, Hy2, Wy2, M)
                 self._convert(y2_d, C.split(y2_abs), C.OP_ABS)
                 z2, z2_d, Hz, Wz = self._seq3(m._h_a2.encode_hyper, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_NONE),
                                               C.split(y2_abs), B, Hy2, Wy2, "nhwc")
@@ -241,7 +332,7 @@ class HesicEngine:
         if joint:
             y1_hat, y1_lik, y1h_split_d = self._joint_entropy(1, y1, y1_d, None, B, Hy, Wy, a(2), a(0))
         else:
-            y1_abs = _split(B, Hy, Wy, M, dev)
+            y1_abs = self._split(B, Hy, Wy, M)
             self._convert(y1_d, C.split(y1_abs), C.OP_ABS)
             z1, z1_d, Hz, Wz = self._seq3(m._h_a1.encode_hyper, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_NONE),
                                           C.split(y1_abs), B, Hy, Wy, "nhwc")
@@ -261,11 +352,11 @@ class HesicEngine:
 
         # ---- conditioning on the left view ----------------------------------------------
         if joint:
-            cond_buf = _split(B, Hy, Wy, 5 * M, dev)   # cat(params2, ctx2, y1_hat_warpf2)  newnet1_joint.py:722
+            cond_buf = self._split(B, Hy, Wy, 5 * M)   # cat(params2, ctx2, y1_hat_warpf2)  newnet1_joint.py:722
             cond_c0 = 4 * M
         else:
             N = m.N
-            cond_buf = _split(B, Hy, Wy, N + M, dev)   # cat(up(z2_hat), y1)                newnet1.py:565
+            cond_buf = self._split(B, Hy, Wy, N + M)   # cat(up(z2_hat), y1)                newnet1.py:565
             cond_c0 = N
         cond_slice = C.split(cond_buf, M, cond_c0)
         if self.variant == "newnet9":
@@ -306,6 +397,7 @@ class HesicEngine:
         if joint:
             z1_lik, z2_lik = self._z_liks
         out["likelihoods"] = {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}
+        self._end(main)
         return out
 
     # ---- HESIC+ entropy model of one view (newnet1_joint.py:676-692 / 706-727) ---------------
@@ -319,27 +411,27 @@ class HesicEngine:
         ctxp = getattr(m, f"context_prediction{view}")
         eb = getattr(m, f"entropy_bottleneck{view}")
         L = C.ACT_LEAKY
-        y_split = _split(B, Hy, Wy, M, dev)
+        y_split = self._split(B, Hy, Wy, M)
         self._convert(y_d, C.split(y_split))
         z, z_d, Hz, Wz = self._seq3(h_a, (0, 2, 4), (L, L, C.ACT_NONE), C.split(y_split), B, Hy, Wy, "nhwc")
         z_hat, zh_d, z_lik = self._bottleneck(eb, z, z_d, B, Hz, Wz, acc_z)
         if view == 1:
             self._z_liks = [z_lik, None]
-            buf = _split(B, Hy, Wy, 4 * M, dev)      # cat(params1, ctx_params1)  newnet1_joint.py:687-688
+            buf = self._split(B, Hy, Wy, 4 * M)      # cat(params1, ctx_params1)  newnet1_joint.py:687-688
         else:
             self._z_liks[1] = z_lik
             buf = cond_buf
         self._seq3(h_s, (0, 2, 4), (L, L, C.ACT_NONE), zh_d, B, Hz, Wz, "split", last_dst=(buf, 0))
-        yh_split = _split(B, Hy, Wy, M, dev)
+        yh_split = self._split(B, Hy, Wy, M)
         yh_d = C.split(yh_split)
         self._convert(y_d, yh_d, C.OP_ROUND)         # y_hat = round(y)  (:684-685)
-        y_hat = _nchw(B, M, Hy, Wy, dev)
+        y_hat = self._nchw(B, M, Hy, Wy)
         self._convert(yh_d, C.nchw(y_hat))
         self._run(ctxp, yh_d, B, Hy, Wy, "split", dst=(buf, 2 * M))
         gp, gp_d, _, _ = self._seq3(ep, (0, 2, 4), (L, L, C.ACT_NONE), C.split(buf), B, Hy, Wy, "nhwc")
         scales_d = C.nhwc(gp, M, 0)
         means_d = C.nhwc(gp, M, M)
-        lik = _nchw(B, M, Hy, Wy, dev)
+        lik = self._nchw(B, M, Hy, Wy)
         gc = m.gaussian_conditional1                  # the reference uses conditional1 for both views (:725)
         C.check(_lib.hesic_gaussian_conditional(C.ref(y_d), C.ref(scales_d), C.ref(means_d), None, 1, 0,
                                                 gc._scale_bound_value(), gc._lik_bound(), None, C.ref(C.nchw(lik)), None,

@@ -11,6 +11,7 @@ import torch
 
 from . import _capi as C
 from . import functional as F
+from .engine import EngineBase
 
 _lib = C.lib
 
@@ -33,6 +34,16 @@ class EnConvPlan:
         except Exception:
             pass
 
+    def __deepcopy__(self, memo):       # one owner per C handle: a copy is a fresh, unloaded plan (see ConvPlan)
+        return type(self)(*self.geom)
+
+    def __reduce__(self):
+        return (type(self), tuple(self.geom))
+
+    def invalidate(self):
+        self._key = None
+
+    @C.device_guard
     def load(self, weight, bias=None):
         key = F.ConvPlan._ver(weight, bias)
         if key != self._key:
@@ -59,7 +70,7 @@ def en_plan(conv_mod):
     return plan.load(conv_mod.weight, conv_mod.bias)
 
 
-class EnhanceEngine:
+class EnhanceEngine(EngineBase):
     def __init__(self, model, align_corners=True):
         self.m = model
         self.align_corners = align_corners
@@ -95,6 +106,7 @@ class EnhanceEngine:
         en_plan(eh.conv2).run(a, C.nchw(out), C.ACT_NONE, res1=C.nchw(x))
         return out
 
+    @C.device_guard
     def forward_mono(self, x1_hat, x2_hat):
         """mynet6_plus.Independent_EN.forward: each view enhanced on its own."""
         C.require_cuda(x1_hat, x2_hat)
@@ -104,6 +116,7 @@ class EnhanceEngine:
         return {"x1_hat": self._enhancement(self.m.EH1, x1_hat, None, torch.empty_like(x1_hat)),
                 "x2_hat": self._enhancement(self.m.EH2, x2_hat, None, torch.empty_like(x2_hat))}
 
+    @C.device_guard
     def forward(self, x1_hat, x2_hat, h_matrix):
         C.require_cuda(x1_hat, x2_hat, h_matrix)
         x1_hat, x2_hat = F._f32(x1_hat), F._f32(x2_hat)

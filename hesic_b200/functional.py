@@ -43,10 +43,27 @@ class ConvPlan:
         except Exception:
             pass
 
+    # The C handle is owned by exactly one Python object: a copy (copy.deepcopy of a module that cached a plan) or an
+    # unpickled plan (torch.save(model)) is a fresh, unloaded plan of the same geometry, never a second owner.
+    def __deepcopy__(self, memo):
+        Cin, Cout, kh, kw, stride, pad, tr, op = self.geom
+        return type(self)(Cin, Cout, (kh, kw), stride, pad, bool(tr), op)
+
+    def __reduce__(self):
+        Cin, Cout, kh, kw, stride, pad, tr, op = self.geom
+        return (type(self), (Cin, Cout, (kh, kw), stride, pad, bool(tr), op))
+
+    def invalidate(self):
+        """Force a re-pack at the next load() / set_gdn().  Needed after weight surgery through ``.data`` (``w.data.copy_()``,
+        EMA swaps): that does not bump the parameter's version counter, which is what load() keys on."""
+        self._key = None
+        self._gdn_key = None
+
     @staticmethod
     def _ver(*ts):
         return tuple((t.data_ptr(), t._version, t.device.index) if t is not None else None for t in ts)
 
+    @C.device_guard
     def load(self, weight, bias=None, mask=None):
         key = self._ver(weight, bias, mask)
         if key == self._key:
@@ -58,6 +75,7 @@ class ConvPlan:
         self._key = key
         return self
 
+    @C.device_guard
     def set_gdn(self, beta, gamma, inverse, beta_min=1e-6):
         """Attach (beta, gamma given) or detach (beta None) the fused GDN.  The packed operands are kept across a
         detach, so a layer shared by a fused engine and stand-alone operator calls toggles without re-packing."""
@@ -76,6 +94,7 @@ class ConvPlan:
         self._gdn_on = True
         return self
 
+    @C.device_guard
     def detect_kband(self, weight):
         """Block-banded weights: let the tensor-core path skip the all-zero (N tile, K chunk) blocks.  ``weight`` is the
         tensor last passed to load().  Synchronises the stream once (a handful of flags are read back)."""
@@ -96,6 +115,7 @@ class ConvPlan:
             C.check(_lib.hesic_conv_forward(self.h, C.ref(x_desc), C.ref(y_desc), act, path, C.stream()))
 
 
+@C.device_guard
 def conv2d(x, plan, act=C.ACT_NONE, path=C.PATH_AUTO):
     """NCHW fp32 in -> NCHW fp32 out through a loaded ConvPlan."""
     x = _f32(x)
@@ -125,6 +145,7 @@ def conv2d(x, plan, act=C.ACT_NONE, path=C.PATH_AUTO):
     return y
 
 
+@C.device_guard
 def gdn(x, beta, gamma, inverse=False, beta_min=1e-6):
     """compressai/layers/gdn.py:55-70 with the raw (un-reparametrised) parameters."""
     x = _f32(x)
@@ -135,6 +156,7 @@ def gdn(x, beta, gamma, inverse=False, beta_min=1e-6):
     return y
 
 
+@C.device_guard
 def warp_perspective(src, M, dsize, align_corners=True, out=None):
     """kornia.warp_perspective(src, M, dsize) -- bilinear, zero padding."""
     src = _f32(src)
@@ -147,6 +169,7 @@ def warp_perspective(src, M, dsize, align_corners=True, out=None):
     return out
 
 
+@C.device_guard
 def eb_pack(matrices, biases, factors, quantiles):
     """Pre-activate the EntropyBottleneck parameters into the 60-float-per-channel device table."""
     Cn = quantiles.shape[0]
@@ -158,6 +181,7 @@ def eb_pack(matrices, biases, factors, quantiles):
     return out
 
 
+@C.device_guard
 def entropy_bottleneck(z, params, likelihood_bound=1e-9, log2_acc=None):
     """EntropyBottleneck.forward (eval): returns (z_hat, likelihood), NCHW fp32."""
     z = _f32(z)
@@ -168,6 +192,7 @@ def entropy_bottleneck(z, params, likelihood_bound=1e-9, log2_acc=None):
     return z_hat, lik
 
 
+@C.device_guard
 def gaussian_mixture_conditional(y, scales, means, weights, K, scale_bound=0.11, likelihood_bound=1e-9, log2_acc=None):
     """GaussianMixtureConditional.forward (eval).  weights: [B, K*M, 1, 1]."""
     y, scales, means = _f32(y), _f32(scales), _f32(means)
@@ -182,6 +207,7 @@ def gaussian_mixture_conditional(y, scales, means, weights, K, scale_bound=0.11,
     return y_hat, lik
 
 
+@C.device_guard
 def gaussian_conditional(y, scales, means=None, scale_bound=0.11, likelihood_bound=1e-9, log2_acc=None):
     """GaussianConditional.forward (eval)."""
     y, scales = _f32(y), _f32(scales)
@@ -194,6 +220,7 @@ def gaussian_conditional(y, scales, means=None, scale_bound=0.11, likelihood_bou
     return y_hat, lik
 
 
+@C.device_guard
 def spatial_max(x):
     """spatial_pool2d (newnet1.py:441-453): [B,C,H,W] -> [B,C,1,1] fp32."""
     x = _f32(x)
@@ -202,6 +229,7 @@ def spatial_max(x):
     return out.reshape(x.shape[0], x.shape[1], 1, 1)
 
 
+@C.device_guard
 def mixture_weights(pooled, w1x1, bias, K, M):
     """LeakyReLU -> conv1x1 -> softmax over the K components: [B,K*M(,1,1)] -> [B,K*M,1,1]."""
     B = pooled.shape[0]
@@ -212,6 +240,7 @@ def mixture_weights(pooled, w1x1, bias, K, M):
     return out.reshape(B, K * M, 1, 1)
 
 
+@C.device_guard
 def upsample_bilinear(x, scale):
     x = _f32(x)
     y = torch.empty((x.shape[0], x.shape[1], x.shape[2] * scale, x.shape[3] * scale), device=x.device, dtype=torch.float32)
@@ -219,6 +248,7 @@ def upsample_bilinear(x, scale):
     return y
 
 
+@C.device_guard
 def round_half_even(x):
     x = _f32(x)
     y = torch.empty_like(x)
@@ -226,6 +256,7 @@ def round_half_even(x):
     return y
 
 
+@C.device_guard
 def prepare_symbols(x, means=None):
     """int32 symbols = round_half_even(x - means), [B, C*H*W] (EntropyModel.compress prep).
     ``means``: None, a [1,C,1,1] / [C] per-channel tensor, or a full tensor like x."""
@@ -252,6 +283,7 @@ def build_indexes_channel(size, device):
     return out
 
 
+@C.device_guard
 def build_indexes_scale(scales, table, scale_bound=0.11):
     scales = _f32(scales)
     table = _f32(table)
@@ -261,6 +293,7 @@ def build_indexes_scale(scales, table, scale_bound=0.11):
     return out
 
 
+@C.device_guard
 def sum_squared_error(a, b, acc):
     a, b = _f32(a), _f32(b)
     C.check(_lib.hesic_sum_squared_error(C.ref(C.nchw(a)), C.ref(C.nchw(b)), C.ptr(acc), C.stream()))
@@ -280,7 +313,22 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
-class RansEncoderHandle:
+class _OwnedHandle:
+    """A Python object that owns one C handle (destroyed in ``__del__``).  A copy or an unpickled instance is a FRESH
+    coder object, never a second owner of the same handle: entropy models keep their coder as an attribute, so
+    ``copy.deepcopy(model)`` / ``torch.save(model)`` reach these (a shared handle was a double free)."""
+
+    def _ctor_args(self):
+        return ()
+
+    def __deepcopy__(self, memo):
+        return type(self)(*self._ctor_args())
+
+    def __reduce__(self):
+        return (type(self), self._ctor_args())
+
+
+class RansEncoderHandle(_OwnedHandle):
     def __init__(self):
         self.h = _lib.hesic_rans_encoder_create()
 
@@ -311,7 +359,7 @@ class RansEncoderHandle:
         return buf.tobytes()
 
 
-class RansDecoderHandle:
+class RansDecoderHandle(_OwnedHandle):
     def __init__(self):
         self.h = _lib.hesic_rans_decoder_create()
         self._buf = None
@@ -338,6 +386,7 @@ class RansDecoderHandle:
 
 # ---------------------------------------------------------------------------------------------
 # operators of the DSIC variant (ywz/DSIC/mynet6_plus.py)
+@C.device_guard
 def group_norm(x, groups, weight=None, bias=None, eps=1e-5, relu=False):
     """nn.GroupNorm(groups, C) (+ the ReLU that follows it everywhere in mynet6_plus.py:224-290)."""
     x = _f32(x)
@@ -349,6 +398,7 @@ def group_norm(x, groups, weight=None, bias=None, eps=1e-5, relu=False):
     return y
 
 
+@C.device_guard
 def softmax_channels(x):
     """nn.functional.softmax(x, dim=-3) (mynet6_plus.py:311)."""
     x = _f32(x)
@@ -357,6 +407,7 @@ def softmax_channels(x):
     return y
 
 
+@C.device_guard
 def dense_warp(h1, cost):
     """dense_warp.forward (mynet6_plus.py:316-345): sum_d cost[:, d] * (h1 shifted left by d pixels)."""
     h1, cost = _f32(h1), _f32(cost)
@@ -367,6 +418,7 @@ def dense_warp(h1, cost):
 
 # ---------------------------------------------------------------------------------------------
 # file codec of the stereo models (newnet1.py:823-1273)
+@C.device_guard
 def gmm_cdf_tables(scales, means, weights, K, channels, minmax, scale_bound=0.11):
     """Per-element cumulative-frequency rows of the K-component mixture (newnet1.py:934-978) for the given channels of a
     [1, K*M, H, W] parameter set: int32 [len(channels)*H*W, 2*minmax+2] on the device, rows in (channel, h, w) order."""
@@ -383,7 +435,7 @@ def gmm_cdf_tables(scales, means, weights, K, channels, minmax, scale_bound=0.11
     return out
 
 
-class RangeEncoderHandle:
+class RangeEncoderHandle(_OwnedHandle):
     """Host range coder (csrc/coder.cpp): one symbol per cumulative-frequency row."""
 
     def __init__(self):
@@ -412,7 +464,10 @@ class RangeEncoderHandle:
         return buf.tobytes()
 
 
-class RangeDecoderHandle:
+class RangeDecoderHandle(_OwnedHandle):
+    def _ctor_args(self):
+        return (self._buf.tobytes(),)
+
     def __init__(self, data):
         self._buf = np.frombuffer(bytes(data), dtype=np.uint8)
         self.h = _lib.hesic_range_decoder_create(self._buf.ctypes.data if self._buf.size else None, self._buf.size)

@@ -538,22 +538,27 @@ def dsic_global_context(sd, y1, Fn, Cn, p="_global_context.global_net"):
 
 
 # mynet6_plus.py:249-313
-def dsic_cost_volume(sd, p, h1, h2, d, scale, Fn, Cn):
+def dsic_cost_volume(sd, p, h1, h2, d, scale, Fn, Cn, taps=None):
+    """``taps`` (optional dict) receives every stage boundary, so that a test can feed a kernel the oracle's own
+    input of that stage: m1a, h_out, d_up, v1, d_out, m3a, m3b, logits."""
+    T = taps if taps is not None else {}
     F0 = Fn // 3
     x = torch.cat((h1, h2), dim=1)
-    x = _gn_relu(sd, p + ".model1.1", conv(x, *_cw(sd, p + ".model1.0"), stride=1), 4)
-    h_out = _gn_relu(sd, p + ".model1.4", conv(x, *_cw(sd, p + ".model1.3"), stride=1), 4)
+    x = T["m1a"] = _gn_relu(sd, p + ".model1.1", conv(x, *_cw(sd, p + ".model1.0"), stride=1), 4)
+    h_out = T["h_out"] = _gn_relu(sd, p + ".model1.4", conv(x, *_cw(sd, p + ".model1.3"), stride=1), 4)
     d_in = torch.reshape(d, (-1, d.size(-3), d.size(-2), d.size(-1)))
-    d_up = F.interpolate(d_in, scale_factor=scale, mode="bilinear", align_corners=True)   # nn.UpsamplingBilinear2d
+    d_up = T["d_up"] = F.interpolate(d_in, scale_factor=scale, mode="bilinear", align_corners=True)   # nn.UpsamplingBilinear2d
     v = torch.reshape(d_up, (-1, F0, Cn, d_up.size(-2), d_up.size(-1)))
     for i, gn in ((0, 1), (3, 4)):
         v = F.conv3d(v, sd[f"{p}.model2.{i}.weight"], sd[f"{p}.model2.{i}.bias"], stride=1, padding=2)
         v = F.relu(F.group_norm(v, 1, sd[f"{p}.model2.{gn}.weight"], sd[f"{p}.model2.{gn}.bias"], 1e-5))
-    d_out = torch.reshape(v, (-1, F0 * Cn, v.size(-2), v.size(-1)))
+        if i == 0:
+            T["v1"] = v
+    d_out = T["d_out"] = torch.reshape(v, (-1, F0 * Cn, v.size(-2), v.size(-1)))
     x = torch.cat((h_out, d_out), dim=1)
-    x = _gn_relu(sd, p + ".model3.1", conv(x, *_cw(sd, p + ".model3.0"), stride=1), 4)
-    x = _gn_relu(sd, p + ".model3.4", conv(x, *_cw(sd, p + ".model3.3"), stride=1), 4)
-    x = conv(x, *_cw(sd, p + ".model3.6"), stride=1)
+    x = T["m3a"] = _gn_relu(sd, p + ".model3.1", conv(x, *_cw(sd, p + ".model3.0"), stride=1), 4)
+    x = T["m3b"] = _gn_relu(sd, p + ".model3.4", conv(x, *_cw(sd, p + ".model3.3"), stride=1), 4)
+    x = T["logits"] = conv(x, *_cw(sd, p + ".model3.6"), stride=1)
     return F.softmax(x, dim=-3)
 
 
@@ -571,7 +576,8 @@ def dsic_forward(sd, x1, x2, K=5, Fn=21, Cn=32, taps=None):
     T = taps if taps is not None else {}
     M = sd["encoder1.g_a_conv4.weight"].shape[0]
     cat = lambda a, b: torch.cat((a, b), dim=-3)
-    cv = lambda i, h1, h2, d, s: dsic_cost_volume(sd, f"_cost_volume{i}", h1, h2, d, s, Fn, Cn)
+    cv = lambda i, h1, h2, d, s: dsic_cost_volume(sd, f"_cost_volume{i}", h1, h2, d, s, Fn, Cn,
+                                                  taps=T.setdefault(f"cv{i}", {}))
     y1, g1_1, g1_2, g1_3 = dsic_encoder1(sd, x1)
     z1_hat, z1_lik = entropy_bottleneck(encode_hyper(sd, y1, "_h_a1"), *eb_params(sd, "entropy_bottleneck1"))
     y1_hat, y1_lik = gmm_conditional(y1, *gmm_hyper_y1(sd, z1_hat, "_h_s1", K, M), K)
@@ -597,6 +603,8 @@ def dsic_forward(sd, x1, x2, K=5, Fn=21, Cn=32, taps=None):
     s3 = _gdn(sd, "pic2_g_s_gdn3", deconv(cat(w5, s2), *_cw(sd, "pic2_g_s_conv3")), True)
     w6 = dsic_dense_warp(g1_6, cv(6, g1_6, s3, ctx[0], 8))
     x2_hat = deconv(cat(w6, s3), *_cw(sd, "pic2_g_s_conv4"))
-    T.update(y1=y1, y1_hat=y1_hat, g1_1=g1_1, a1=a1, cost1=c1, warp1=w1, y2=y2, y2_hat=y2_hat, ctx0=ctx[0])
+    T.update(y1=y1, y1_hat=y1_hat, g1_1=g1_1, g1_2=g1_2, g1_3=g1_3, g1_4=g1_4, g1_5=g1_5, g1_6=g1_6, a1=a1, a2=a2, a3=a3,
+             s1=s1, s2=s2, s3=s3, cost1=c1, warp1=w1, warp2=w2, warp3=w3, y2=y2, y2_hat=y2_hat, ctx0=ctx[0], ctx1=ctx[1],
+             ctx2=ctx[2])
     return {"x1_hat": x1_hat, "x2_hat": x2_hat,
             "likelihoods": {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}}

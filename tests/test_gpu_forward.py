@@ -22,15 +22,16 @@ def _model(modname):
     return net.to(DEV), sd
 
 
-def _check_against(out, ref, x1, x2, sym_tol=2e-3, what=""):
-    """Symbols may flip at exact x.5 ties (fp32 summation order); everything else is tight."""
+def _check_against(out, ref, x1, x2, sym_tol=2e-4, what=""):
+    """Symbols may flip where fp32 summation order moves a latent across x.5 (a handful per million on these seeds; the
+    bars are 10x tighter than round 1's so that a real regression shows); everything else is tight."""
     for k in ("y1_hat", "y2_hat"):
         if k in out and k in ref:
             assert mismatch_fraction(out[k], ref[k]) < sym_tol, (what, k)
     for k in ("x1_hat", "x2_hat"):
         a, b = out[k].cpu().double(), torch.as_tensor(ref[k]).double()
         rel = float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt())
-        assert rel < 5e-3, (what, k, rel)
+        assert rel < 5e-4, (what, k, rel)
     m = synth.rd_metrics({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in out.items() if k != "likelihoods"}
                          | {"likelihoods": {k: v.cpu() for k, v in out["likelihoods"].items()}}, x1, x2)
     return m
@@ -48,9 +49,9 @@ def test_forward_small_vs_reference_fixture(name, modname):
     ref = {k: (T(v.astype(np.float32)) if k.endswith("_hat") else T(v)) for k, v in gold.items()}
     m = _check_against(out, ref, x1, x2, what=name)
     for k, v in meta["metrics"].items():
-        assert math.isclose(m[k], v, rel_tol=2e-3, abs_tol=2e-3), (k, m[k], v)
+        assert math.isclose(m[k], v, rel_tol=2e-4, abs_tol=2e-4), (k, m[k], v)
     # view-1 quantities do not depend on tie-flips of view 2: tight comparison
-    assert_close(out["likelihoods"]["z1"], gold["lik_z1"], 1e-3, floor=1e-9, what="z1 likelihood")
+    assert_close(out["likelihoods"]["z1"], gold["lik_z1"], 1e-4, floor=1e-9, what="z1 likelihood")
     # fused bpp partial sums agree with the likelihood tensors they summarise
     sums = net.hesic_engine.log2_sums.cpu()
     for i, k in enumerate(("y1", "y2", "z1", "z2")):
@@ -69,7 +70,7 @@ def test_forward_full_size_metrics(name, modname):
     cpu["likelihoods"] = {k: v.cpu() for k, v in out["likelihoods"].items()}
     m = synth.rd_metrics(cpu, x1, x2)
     for k, v in meta["metrics_512"].items():
-        assert math.isclose(m[k], v, rel_tol=2e-3, abs_tol=2e-3), (k, m[k], v)
+        assert math.isclose(m[k], v, rel_tol=2e-4, abs_tol=2e-4), (k, m[k], v)
     with torch.no_grad():
         ref = O.hsic_joint_forward(sd, x1, x2, h) if name == "hsic_joint" else O.hsic_forward(sd, x1, x2, h)
     _check_against(out, ref, x1, x2, what=name + " 512")
@@ -205,7 +206,7 @@ def test_driver_flow_test3real():
     m = _check_against(out_net2, {"x1_hat": ref2["x1_hat"], "x2_hat": ref2["x2_hat"]}, d1, d2, what="driver flow")
     m_ref = synth.rd_metrics({"x1_hat": ref2["x1_hat"], "x2_hat": ref2["x2_hat"], "likelihoods": ref["likelihoods"]}, d1, d2)
     for k in ("bpp", "psnr1", "psnr2"):
-        assert math.isclose(m[k], m_ref[k], rel_tol=2e-3, abs_tol=2e-3), (k, m[k], m_ref[k])
+        assert math.isclose(m[k], m_ref[k], rel_tol=2e-4, abs_tol=2e-4), (k, m[k], m_ref[k])
     # the driver's criterion (test3real.py:90-124; MS-SSIM left out: pytorch_msssim is not installed here)
     mse = torch.nn.MSELoss()
     num_pixels = d1d.size(0) * d1d.size(2) * d1d.size(3)
@@ -244,7 +245,7 @@ def test_forward_kitti_size_vs_oracle():
     m = _check_against(out, ref, x1, x2, what="kitti size")
     r = synth.rd_metrics(ref, x1, x2)
     for k in ("bpp", "psnr1", "psnr2"):
-        assert math.isclose(m[k], r[k], rel_tol=2e-3, abs_tol=2e-3), (k, m[k], r[k])
+        assert math.isclose(m[k], r[k], rel_tol=2e-4, abs_tol=2e-4), (k, m[k], r[k])
     en = newnet1.Independent_EN().eval()
     sd_en = synth.synth_state_dict(en, seed=0)
     en.load_state_dict(sd_en)

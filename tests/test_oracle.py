@@ -272,3 +272,27 @@ def test_dsic_independent_en_oracle_vs_reference_fixture():
     g = load_npz("dsic_independent_en")
     assert_close(o["x1_hat"], g["x1_hat"], 1e-5, what="DSIC EN x1")
     assert_close(o["x2_hat"], g["x2_hat"], 1e-5, what="DSIC EN x2")
+
+
+@pytest.mark.parametrize("name", ["hsic_newnet1", "hsic_newnet9", "hsic_joint", "dsic", "independent_en"])
+def test_default_state_matches_the_reference_constructors(name):
+    """oracle/default_state.py rebuilds the constructor-fixed tensors (bounds, pedestals, bottleneck target / matrices,
+    masks) from the key table alone; each one is SHA-1-equal to what the unmodified reference constructed, and the
+    seeded weights derived from it equal the ones the fixtures were generated with.  bench.py's CPU arm relies on this
+    to build its weights without instantiating a model of this repository."""
+    import hashlib
+    from hesic_b200 import synth
+    from oracle import default_state as D
+    meta = load_json(name)
+    tab = meta["state_dict_init"]
+    sd = D.initial_state_dict(tab)
+    sha = lambda t: hashlib.sha1(t.detach().contiguous().numpy().tobytes()).hexdigest() if t.numel() else ""
+    assert set(sd) == set(tab)
+    for k, g in tab.items():
+        assert tuple(sd[k].shape) == tuple(g["shape"]) and str(sd[k].dtype).replace("torch.", "") == g["dtype"], k
+        if D.rule_governed(k) or sd[k].numel() == 0:
+            assert sha(sd[k]) == g["sha1"], f"constructor value of {k} differs from the reference"
+    if "synth_sha1" in meta:
+        ss = synth.synth_state_dict(sd, seed=0)
+        for k, h in meta["synth_sha1"].items():
+            assert sha(ss[k]) == h, f"seeded value of {k} differs from the fixture's"
