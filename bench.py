@@ -499,7 +499,9 @@ def run_extras(args, dev, build, call, timed, C, F, synth, sets, net, model):
                 g.replay()
             ms = timed(lambda i: g.replay(), 20, reduce=False) / 20
             r[f"B{Bl}"] = {"ms": ms, "pairs_per_s": Bl / ms * 1e3, "kernels_per_forward": g.n_launches}
-            # the same call issued eagerly (Python-driven launches)
+            # the same call issued eagerly (Python-driven launches, per-forward allocations)
+            for _ in range(3):
+                net(a, b, hh)
             ms_e = timed(lambda i: net(a, b, hh), 20, reduce=False) / 20
             r[f"B{Bl}"]["eager_ms"] = ms_e
         r["workload"] = f"{MODEL_INFO[model][0]} forward latency at 512x512, CUDA-graph replay vs eager launches"

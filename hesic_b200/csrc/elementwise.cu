@@ -688,7 +688,20 @@ __global__ void __launch_bounds__(256) indexes_scale_kernel(const TView sc, cons
 // File codec (HSIC.compress / decompress, newnet1.py:934-978): per latent element the integer cumulative-frequency
 // row of its K-component mixture.  Thread = element; the arithmetic follows the reference's op sequence in fp32
 // (torch elementwise ops for the pmf, then numpy: clip, pairwise-summed normalisation, round half even, running sum).
-constexpr int CDF_MAX_S = 129;   // 2 * minmax + 1 <= 129
+//
+// These integers ARE the code: encoder and decoder must derive identical rows.  The one operation of that sequence
+// whose result is implementation-defined is erfc -- the reference calls torch.erfc on whatever device it runs on (CUDA's
+// erfcf on 'cuda:0', SLEEF / libm on a CPU), and those differ in the last bit.  The table arithmetic therefore uses the
+// CORRECTLY ROUNDED fp32 erfc: evaluated in fp64 on the fp32 argument and rounded once (cdf_std_cumulative).  Every
+// other step is a single IEEE fp32 operation, so the rows are reproducible bit for bit by any implementation -- the
+// CPU oracle (oracle/hesic_oracle.py:codec_cdf_tables) does exactly that and tests/test_gpu_codec.py holds equality.
+constexpr int CDF_MAX_S = 129;   // rows of up to 129 samples (minmax <= 64) are built in registers / local memory;
+                                 // longer ones in place in the output row (any minmax)
+
+__device__ __forceinline__ float cdf_std_cumulative(float v) {
+  const float t = __fmul_rn(-0.70710678118654752440f, v);      // float(-(2 ** -0.5)) * inputs   (newnet1.py:795-797)
+  return __fmul_rn(0.5f, (float)erfc((double)t));
+}
 
 // numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src: pairwise_sum) for a contiguous fp32 vector
 __device__ float np_pairwise_sum(const float *a, int n) {
@@ -725,7 +738,10 @@ __global__ void __launch_bounds__(128) gmm_cdf_kernel(const TView scales, const 
   const int ci = e / HW, pos = e - ci * HW;
   const int c = channels[ci], yy = pos / scales.W, xx = pos - yy * scales.W;
   const int S = 2 * minmax + 1;
-  float pmf[CDF_MAX_S];
+  int32_t *row = out + (size_t)e * (S + 1);
+  float local[CDF_MAX_S];
+  // pmf[s] of a long row lives in the slot row[s + 1] it is finally replaced by (read, then written, by this thread only)
+  float *pmf = S <= CDF_MAX_S ? local : reinterpret_cast<float *>(row + 1);
   for (int k = 0; k < K; ++k) {
     const int ck = k * M + c;
     const float mu = __fadd_rn(tload(means, 0, ck, yy, xx), (float)minmax);      // means + minmax  (newnet1.py:950)
@@ -733,15 +749,14 @@ __global__ void __launch_bounds__(128) gmm_cdf_kernel(const TView scales, const 
     const float w = weights[ck];
     for (int sidx = 0; sidx < S; ++sidx) {
       const float v = fabsf(__fsub_rn((float)sidx, mu));
-      const float up = std_cumulative(__fdiv_rn(__fsub_rn(0.5f, v), sc));
-      const float lo = std_cumulative(__fdiv_rn(__fsub_rn(-0.5f, v), sc));
+      const float up = cdf_std_cumulative(__fdiv_rn(__fsub_rn(0.5f, v), sc));
+      const float lo = cdf_std_cumulative(__fdiv_rn(__fsub_rn(-0.5f, v), sc));
       const float term = __fmul_rn(__fsub_rn(up, lo), w);
       pmf[sidx] = k == 0 ? term : __fadd_rn(pmf[sidx], term);
     }
   }
   for (int sidx = 0; sidx < S; ++sidx) pmf[sidx] = fminf(fmaxf(pmf[sidx], 1.0f / 65536.0f), 1.0f);   // np.clip
   const float tot = np_pairwise_sum(pmf, S);
-  int32_t *row = out + (size_t)e * (S + 1);
   float acc = 0.f;
   row[0] = 0;
   for (int sidx = 0; sidx < S; ++sidx) {
@@ -1032,7 +1047,7 @@ extern "C" int hesic_gmm_cdf_tables(const hesic_tensor *scales, const hesic_tens
   HESIC_REQUIRE(K >= 1 && M >= 1 && scales->C == K * M && means->C == K * M, "cdf tables: scales/means need K*M channels");
   HESIC_REQUIRE(scales->B == 1 && means->B == 1 && means->H == scales->H && means->W == scales->W,
                 "cdf tables: one image at a time (as the reference's codec), scales and means of the same size");
-  HESIC_REQUIRE(minmax >= 1 && 2 * minmax + 1 <= CDF_MAX_S, "cdf tables: minmax must be in [1, %d]", (CDF_MAX_S - 1) / 2);
+  HESIC_REQUIRE(minmax >= 1 && minmax <= 32767, "cdf tables: minmax must be in [1, 32767]");
   HESIC_REQUIRE(n_channels >= 0 && n_channels <= M, "cdf tables: bad channel count");
   const int n = n_channels * scales->H * scales->W;
   if (n == 0) return HESIC_OK;

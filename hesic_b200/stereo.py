@@ -288,7 +288,7 @@ def codec_write(model, shape_hw, views, output_name, output_path):
             yi = y_hat[0].to(torch.int64)
             flag = (yi.abs().sum(dim=(1, 2)) > 0).cpu().numpy().astype(np.uint8)
             minmax = int(max(int(yi.max().abs()), int(yi.min().abs()), 1))
-            if len(zs[0]) > 65535 or minmax > 64:
+            if len(zs[0]) > 65535 or minmax > 32767:
                 raise ValueError("compress: z string or symbol range exceeds the reference's uint16 / table header")
             f.write(np.array([len(zs[0]), minmax], dtype=np.uint16).tobytes())
             f.write(np.packbits(flag).tobytes())
@@ -310,7 +310,7 @@ def codec_read(model, output_name, output_path):
         heads = []
         for _ in range(2):
             length, minmax = (int(v) for v in np.frombuffer(f.read(4), dtype=np.uint16))
-            flag = np.unpackbits(np.frombuffer(f.read(model.M // 8), dtype=np.uint8))
+            flag = np.unpackbits(np.frombuffer(f.read((model.M + 7) // 8), dtype=np.uint8))[:model.M]
             heads.append((f.read(length), minmax, np.flatnonzero(flag)))
     with open(os.path.join(output_path, str(output_name) + ".bin"), "rb") as f:
         dec = F.RangeDecoderHandle(f.read())
@@ -507,7 +507,7 @@ class _HSICBase(CompressionModel):
                 yi = y_hat[0].to(torch.int64)
                 flag = (yi.abs().sum(dim=(1, 2)) > 0).cpu().numpy().astype(np.uint8)
                 minmax = int(max(int(yi.max().abs()), int(yi.min().abs()), 1))
-                if len(zs[0]) > 65535 or minmax > 64:
+                if len(zs[0]) > 65535 or minmax > 32767:
                     raise ValueError("compress: z string or symbol range exceeds the reference's uint16 / table header")
                 f.write(np.array([len(zs[0]), minmax], dtype=np.uint16).tobytes())
                 f.write(np.packbits(flag).tobytes())

@@ -416,9 +416,20 @@ def independent_en_forward(sd, x1_hat, x2_hat, h, align_corners=True):
 # File codec of the stereo models (newnet1.py:934-978 / 1135-1180) -- SURVEY 8f rank 2.  The reference evaluates the
 # pmf with torch ops (on 'cuda:0', hard-coded) and the integer table with numpy on the host; this follows the same
 # op sequence on the CPU.  `range_coder` itself is un-vendored and un-pinned: parity of the byte stream is unpinned.
+def std_cumulative_cr(x):
+    """``_standardized_cumulative`` (newnet1.py:795-797: 0.5 * erfc(float(-(2 ** -0.5)) * x)) with a CORRECTLY ROUNDED
+    fp32 erfc: the fp32 argument is evaluated in fp64 and rounded once.  torch.erfc itself is implementation-defined in
+    the last bit (SLEEF on a CPU, CUDA's erfcf on the 'cuda:0' the reference hard-codes), and the integer tables built
+    from it are the code both ends of the codec must agree on; the correctly rounded value is the one result every
+    implementation can reproduce.  Used for the codec tables only -- the likelihood path keeps torch.erfc."""
+    t = torch.tensor(-(2 ** -0.5), dtype=torch.float32) * x
+    return 0.5 * torch.erfc(t.double()).float()
+
+
 def codec_cdf_tables(scales, means, weights, K, channels, minmax, scale_bound=0.11):
     """-> int array [len(channels)*H*W, 2*minmax+2]: per latent element the cumulative-frequency row the reference passes
-    to RangeEncoder.encode / RangeDecoder.decode, rows in the coding order (channel, h, w)."""
+    to RangeEncoder.encode / RangeDecoder.decode, rows in the coding order (channel, h, w).  Same op sequence as
+    newnet1.py:934-978, every step one IEEE fp32 operation, erfc correctly rounded (``std_cumulative_cr``)."""
     import numpy as np
     M = scales.shape[1] // K
     H, W = scales.shape[-2:]
@@ -433,16 +444,15 @@ def codec_cdf_tables(scales, means, weights, K, channels, minmax, scale_bound=0.
         for k in range(K):
             values = torch.abs(samples - mu[k])
             sc = torch.max(sigma[k], torch.tensor([scale_bound]))
-            upper = std_cumulative((0.5 - values) / sc)
-            lower = std_cumulative((-0.5 - values) / sc)
+            upper = std_cumulative_cr((0.5 - values) / sc)
+            lower = std_cumulative_cr((-0.5 - values) / sc)
             term = (upper - lower) * w_all[idx[k]]
             pmf = term if pmf is None else pmf + term
         pmf = pmf.numpy()
-        for h in range(H):
-            for w in range(W):
-                p = np.clip(pmf[:, h, w], 1.0 / 65536, 1.0)
-                p = np.round(p / np.sum(p) * 65536)
-                rows.append([0] + [int(v) for v in np.add.accumulate(p)])
+        p = np.clip(pmf.reshape(S, H * W).T.copy(), np.float32(1.0 / 65536), np.float32(1.0))    # [H*W, S] rows, fp32
+        for r in range(H * W):
+            q = np.round(p[r] / np.sum(p[r]) * 65536)
+            rows.append(np.concatenate(([0], np.add.accumulate(q))).astype(np.int64))
     return np.asarray(rows, dtype=np.int64).reshape(-1, S + 1)
 
 

@@ -19,6 +19,9 @@ DEV = "cuda:0"
 
 
 def test_cdf_tables_vs_oracle():
+    """Bit-exact: the table arithmetic is one IEEE fp32 operation per step with a correctly rounded erfc, on both sides
+    (csrc/elementwise.cu:gmm_cdf_kernel, oracle.codec_cdf_tables), so an encoder and a decoder on different
+    implementations derive the same code.  Includes a symbol range beyond 64 (rows built in place in the output)."""
     from hesic_b200 import functional as F
     g = torch.Generator().manual_seed(5)
     K, M, H, W = 5, 16, 6, 5
@@ -26,13 +29,28 @@ def test_cdf_tables_vs_oracle():
     scales[0, :10] = 0.01                                    # below the 0.11 bound
     means = (torch.rand(1, K * M, H, W, generator=g) - 0.5) * 14
     weights = torch.softmax(torch.randn(K, M, generator=g), 0).reshape(1, K * M, 1, 1)
-    for minmax, channels in ((1, [0]), (7, [0, 3, 4, 15]), (40, [2, 9])):
+    for minmax, channels in ((1, [0]), (7, [0, 3, 4, 15]), (40, [2, 9]), (64, [1]), (65, [5]), (150, [0, 7])):
         ref = O.codec_cdf_tables(scales, means, weights, K, channels, minmax)
         got = F.gmm_cdf_tables(scales.to(DEV), means.to(DEV), weights.to(DEV), K, channels, minmax).cpu().numpy()
-        assert got.shape == ref.shape and (got[:, 0] == 0).all() and (np.diff(got, axis=1) >= 1).all()
+        assert got.shape == ref.shape and (got[:, 0] == 0).all() and (np.diff(got, axis=1) >= 0).all()
+        if minmax <= 64:
+            assert (np.diff(got, axis=1) >= 1).all()
         diff = np.abs(got.astype(np.int64) - ref)
-        # CPU erfc and CUDA erfcf may differ in the last ulp, which can move a rounding: rare and by one count
-        assert diff.max() <= 2 and (diff > 0).mean() < 2e-3, (minmax, diff.max(), (diff > 0).mean())
+        assert diff.max() == 0, (minmax, int(diff.max()), float((diff > 0).mean()))
+
+
+def test_cdf_tables_at_the_configured_latent_size():
+    """192 channels x 32 x 32 positions (one 512x512 view), realistic parameter ranges: still bit-exact."""
+    from hesic_b200 import functional as F
+    g = torch.Generator().manual_seed(11)
+    K, M, H, W = 5, 192, 32, 32
+    scales = torch.rand(1, K * M, H, W, generator=g) * 3
+    means = torch.randn(1, K * M, H, W, generator=g) * 2.5
+    weights = torch.softmax(torch.randn(K, M, generator=g), 0).reshape(1, K * M, 1, 1)
+    channels = [0, 17, 101, 191]
+    ref = O.codec_cdf_tables(scales, means, weights, K, channels, 12)
+    got = F.gmm_cdf_tables(scales.to(DEV), means.to(DEV), weights.to(DEV), K, channels, 12).cpu().numpy()
+    assert np.array_equal(got.astype(np.int64), ref)
 
 
 @pytest.mark.parametrize("modname", ["newnet1", "newnet9"])
@@ -121,3 +139,29 @@ def test_dsic_compress_decompress_round_trip(tmp_path):
         assert rel < 2e-2, (k, rel)
     est = sum(float(torch.log2(v.double()).sum()) for v in fwd["likelihoods"].values()) / (-2 * 64 * 256)
     assert 0.7 * est <= enc["bpp_real"] <= 1.02 * est, (enc["bpp_real"], est)
+
+
+@pytest.mark.parametrize("tag,modname", [("hsic_newnet1", "newnet1"), ("hsic_joint", "newnet1_joint")])
+def test_codec_files_match_the_committed_golden(tag, modname, tmp_path):
+    """Format / table drift guard: compressing the fixture pair reproduces the committed ``.npz`` header and ``.bin``
+    stream byte for byte (tests/golden/make_codec_golden.py wrote them on a B200), and the committed files decode to the
+    latents the encoder coded."""
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = {e: os.path.join(gdir, f"codec_{tag}.{e}") for e in ("npz", "bin")}
+    if not all(os.path.exists(p) for p in gold.values()):
+        pytest.skip("golden codec files not generated yet (tests/golden/make_codec_golden.py)")
+    mod = __import__(modname)
+    net = mod.HSIC(128, 192, 5).eval()
+    net.load_state_dict(synth.synth_state_dict(net, seed=0))
+    net = net.to(DEV)
+    net.entropy_bottleneck1.update(force=True)
+    net.entropy_bottleneck2.update(force=True)
+    x1, x2, h = (t.to(DEV) for t in synth.stereo_pairs(1, 128, 128, seed=1234))
+    enc = net.compress(x1, x2, h, "codec_" + tag, output_path=str(tmp_path))
+    for e in ("npz", "bin"):
+        a, b = open(tmp_path / f"codec_{tag}.{e}", "rb").read(), open(gold[e], "rb").read()
+        assert a == b, f"{tag}.{e}: {len(a)} bytes written, golden has {len(b)}; first difference at " \
+                       f"{next((i for i, (u, v) in enumerate(zip(a, b)) if u != v), min(len(a), len(b)))}"
+    dec = net.decompress(x1, x2, h, "codec_" + tag, output_path=gdir)
+    for k in ("y1_hat", "y2_hat", "z1_hat", "z2_hat"):
+        assert torch.equal(dec[k], enc[k]), k

@@ -79,24 +79,25 @@ def test_configured_batch_16_at_512_vs_oracle(name, modname, fwd):
     m, r = synth.rd_metrics(out, x1, x2), synth.rd_metrics(ref, x1, x2)
     rel = {k: abs(m[k] - r[k]) / abs(r[k]) for k in ("bpp", "bpp1", "bpp2")}
     dps = {k: abs(m[k] - r[k]) for k in ("psnr1", "psnr2")}
-    # per pair: which pairs are flip-free in view 1 -- no y1 symbol differs and no z1 symbol either (a z1 flip moves that
-    # pair's z1 likelihoods by far more than 1e-3); every view-1 tensor of such a pair must then agree tightly
+    # element-wise where a flip cannot reach: the z1 likelihoods of pairs without a z1 flip (a flipped z1 symbol moves its
+    # likelihood by far more than 1e-3), and the y1 likelihoods of the symbols that did not flip in those pairs
     from tests.helpers import close_stats
-    clean = [i for i in range(16) if torch.equal(out["y1_hat"][i], ref["y1_hat"][i])
-             and close_stats(out["likelihoods"]["z1"][i], ref["likelihoods"]["z1"][i], floor=1e-9) < 1e-3]
-    lik_y1 = max([close_stats(out["likelihoods"]["y1"][i], ref["likelihoods"]["y1"][i], floor=1e-6) for i in clean] or [0.0])
-    x1c = max([close_stats(out["x1_hat"][i], ref["x1_hat"][i]) for i in clean] or [0.0])
-    _note(f"b16_512_{name}", flips=flips, x_hat_rel_l2=l2, bpp_rel=rel, psnr_abs=dps, flip_free_pairs_view1=len(clean),
-          y1_lik_rel_clean=lik_y1, x1_hat_rel_clean=x1c, bpp=m["bpp"], bpp_oracle=r["bpp"])
+    zrel = [close_stats(out["likelihoods"]["z1"][i], ref["likelihoods"]["z1"][i], floor=1e-9) for i in range(16)]
+    zclean = [i for i in range(16) if zrel[i] < 1e-3]
+    same = out["y1_hat"] == ref["y1_hat"]
+    lik_y1 = 0.0
+    for i in zclean:
+        a_, b_ = out["likelihoods"]["y1"][i][same[i]], ref["likelihoods"]["y1"][i][same[i]]
+        lik_y1 = max(lik_y1, close_stats(a_, b_, floor=1e-6))
+    _note(f"b16_512_{name}", flips=flips, x_hat_rel_l2=l2, bpp_rel=rel, psnr_abs=dps, pairs_without_z1_flip=len(zclean),
+          z1_lik_rel=max(zrel[i] for i in zclean) if zclean else None, y1_lik_rel_unflipped=lik_y1, bpp=m["bpp"], bpp_oracle=r["bpp"])
     assert flips["y1_hat"] < 2e-4 and flips["y2_hat"] < 2e-4, flips
-    assert l2["x1_hat"] < 5e-4 and l2["x2_hat"] < 5e-4, l2
-    assert max(rel.values()) < 2e-4, rel
-    assert max(dps.values()) < 2e-3, dps
-    assert len(clean) >= 1
-    for i in clean[:4]:
-        assert_close(out["likelihoods"]["z1"][i], ref["likelihoods"]["z1"][i], 1e-4, floor=1e-9, what=f"z1 likelihood, pair {i}")
-        assert_close(out["likelihoods"]["y1"][i], ref["likelihoods"]["y1"][i], 5e-3, floor=1e-6, what=f"y1 likelihood, pair {i}")
-        assert_close(out["x1_hat"][i], ref["x1_hat"][i], 1e-4, what=f"x1_hat, pair {i}")
+    assert l2["x1_hat"] < 1e-3 and l2["x2_hat"] < 1e-3, l2
+    assert max(rel.values()) < 2e-5, rel
+    assert max(dps.values()) < 5e-4, dps
+    assert len(zclean) >= 12
+    assert max(zrel[i] for i in zclean) < 1e-4
+    assert lik_y1 < 5e-3, lik_y1
     # the fused partial sums are the sums of the returned likelihoods
     for i, k in enumerate(("y1", "y2", "z1", "z2")):
         direct = float(torch.log2(out["likelihoods"][k].double()).sum())
