@@ -70,6 +70,7 @@ _sig = {
     "hesic_mixture_weights": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "hesic_upsample_bilinear": ([_TP, _TP, c_int, c_void_p], c_int),
     "hesic_convert": ([_TP, _TP, c_int, c_void_p], c_int),
+    "hesic_images_from_u8": ([c_void_p, c_int, c_int, c_int, c_int, _TP, c_void_p], c_int),
     "hesic_group_norm": ([_TP, _TP, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p], c_int),
     "hesic_softmax_channels": ([_TP, _TP, c_void_p], c_int),
     "hesic_dense_warp": ([_TP, _TP, _TP, c_void_p], c_int),

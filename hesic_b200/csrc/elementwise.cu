@@ -998,6 +998,60 @@ extern "C" int hesic_convert(const hesic_tensor *x, const hesic_tensor *y, int o
   return HESIC_OK;
 }
 
+// uint8 [B][H][W][C] -> NCHW fp32 / 255.  Thread = 4 consecutive pixels of one row: C x 4 bytes in (three 32-bit loads for
+// RGB), one float4 per channel plane out -- both sides coalesced.
+template <int CH>
+__global__ void __launch_bounds__(256) images_u8_kernel(const uint8_t *__restrict__ src, float *__restrict__ dst, int Cs, size_t HW,
+                                                        size_t nquads) {
+  const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (q >= nquads) return;
+  const size_t pix = q * 4, b = pix / HW, r = pix - b * HW;
+  uint32_t w[CH];
+  const uint32_t *s = reinterpret_cast<const uint32_t *>(src + pix * CH);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) w[i] = __ldg(s + i);
+  float v[CH][4];
+#pragma unroll
+  for (int i = 0; i < 4 * CH; ++i) {
+    const uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;      // byte i = (pixel i / CH, channel i % CH)
+    v[i % CH][i / CH] = __fdiv_rn((float)byte, 255.0f);
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    *reinterpret_cast<float4 *>(dst + (b * Cs + c) * HW + r) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+}
+
+__global__ void __launch_bounds__(256) images_u8_generic_kernel(const uint8_t *__restrict__ src, const TView dst, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % dst.C);
+  size_t p = i / dst.C;
+  const int x = (int)(p % dst.W); p /= dst.W;
+  const int y = (int)(p % dst.H);
+  tstore(dst, (int)(p / dst.H), c, y, x, __fdiv_rn((float)src[i], 255.0f));
+}
+
+extern "C" int hesic_images_from_u8(const uint8_t *src, int B, int H, int W, int C, const hesic_tensor *dst, void *stream) {
+  int r;
+  if ((r = check_tensor(dst, "images_from_u8 dst")) != HESIC_OK) return r;
+  HESIC_REQUIRE(B >= 0 && H >= 0 && W >= 0 && C >= 1, "images_from_u8: bad size");
+  HESIC_REQUIRE(dst->B == B && dst->C == C && dst->H == H && dst->W == W, "images_from_u8: dst is %dx%dx%dx%d, source %dx%dx%dx%d", dst->B,
+                dst->C, dst->H, dst->W, B, C, H, W);
+  const size_t n = numel(dst);
+  if (n == 0) return HESIC_OK;
+  HESIC_REQUIRE(src != nullptr, "images_from_u8: null source");
+  const size_t HW = (size_t)H * W;
+  if (dst->fmt == HESIC_FMT_NCHW_F32 && C == 3 && (W & 3) == 0 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst->p0 & 15) == 0) {
+    const size_t nq = (size_t)B * HW / 4;
+    images_u8_kernel<3><<<nblk(nq), 256, 0, as_stream(stream)>>>(src, (float *)dst->p0, dst->Cs > 0 ? dst->Cs : C, HW, nq);
+    HESIC_LAUNCHED("images_u8_kernel");
+    return HESIC_OK;
+  }
+  images_u8_generic_kernel<<<nblk(n), 256, 0, as_stream(stream)>>>(src, view(dst), n);
+  HESIC_LAUNCHED("images_u8_generic_kernel");
+  return HESIC_OK;
+}
+
 extern "C" int hesic_prepare_symbols(const hesic_tensor *x, const float *channel_means, const hesic_tensor *means,
                                      int32_t *out_symbols, void *stream) {
   int r;

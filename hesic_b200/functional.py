@@ -249,6 +249,22 @@ def upsample_bilinear(x, scale):
 
 
 @C.device_guard
+def images_from_uint8(u8, out=None):
+    """[B,H,W,C] uint8 (interleaved, as cv2 / PIL hold an image) -> [B,C,H,W] float32 = u8 / 255: what
+    ``transforms.ToTensor()`` does per image on the host in the reference's loader (compressai/datasets/utils.py:101-102),
+    done on the device so that only 1 byte per sample crosses PCIe."""
+    C.require_cuda(u8)
+    if u8.dtype != torch.uint8 or u8.dim() != 4:
+        raise TypeError(f"images_from_uint8: expected a [B,H,W,C] uint8 tensor, got {u8.dtype} {tuple(u8.shape)}")
+    u8 = u8.contiguous()
+    B, H, W, Cn = u8.shape
+    if out is None:
+        out = torch.empty((B, Cn, H, W), device=u8.device, dtype=torch.float32)
+    C.check(_lib.hesic_images_from_u8(C.ptr(u8), B, H, W, Cn, C.ref(C.nchw(out)), C.stream()))
+    return out
+
+
+@C.device_guard
 def round_half_even(x):
     x = _f32(x)
     y = torch.empty_like(x)

@@ -7,8 +7,16 @@ instead of preceding them.  Every batch is still copied exactly once, inside the
 ``fn(x1, x2, h)`` receives device tensors and is ordered after its copy by an event.  Plumbing only
 (streams, events, pinned memory): the reference does the same job with ``.to(device)`` in its test loop
 (ywz/mywork/test3real.py:190-200).
+
+8-bit transport: images exist as 8-bit samples until ``transforms.ToTensor()`` turns them into fp32 on the host
+(compressai/datasets/utils.py:101-102, test3real.py:323).  A host batch whose images are ``[B,H,W,3] uint8`` tensors is
+copied as such -- a quarter of the PCIe bytes -- and converted by the first kernel on the device
+(``functional.images_from_uint8``: u8 / 255, ToTensor's arithmetic) into the ``[B,3,H,W]`` fp32 tensors ``fn`` receives.
+With 8 ranks feeding from one NUMA node's pinned memory that copy, not the kernels, set the end-to-end scaling (r01).
 """
 import torch
+
+from . import functional as F
 
 
 class HostFeed:
@@ -17,9 +25,20 @@ class HostFeed:
         self.device = device
         self.copy_stream = torch.cuda.Stream(device=device)
         self.sets = [tuple(torch.empty(t.shape, dtype=t.dtype, device=device) for t in like) for _ in range(2)]
+        # uint8 [B,H,W,C] images are converted on the device into these fp32 [B,C,H,W] tensors (one set per slot)
+        self.f32 = [tuple(torch.empty((t.shape[0], t.shape[3], t.shape[1], t.shape[2]), dtype=torch.float32, device=device)
+                          if self._is_u8_image(t) else None for t in like) for _ in range(2)]
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
         self.bytes_per_batch = sum(t.numel() * t.element_size() for t in like)
+
+    @staticmethod
+    def _is_u8_image(t):
+        return t.dtype == torch.uint8 and t.dim() == 4
+
+    def _inputs(self, slot):
+        """Device tensors handed to ``fn``: fp32 images (converted from the uint8 copies where those were shipped)."""
+        return tuple(F.images_from_uint8(d, out=f) if f is not None else d for d, f in zip(self.sets[slot], self.f32[slot]))
 
     def _copy(self, slot, batch, first_use):
         main = torch.cuda.current_stream(self.device)
@@ -45,5 +64,5 @@ class HostFeed:
             if i + 1 < n:
                 self._copy(slot ^ 1, batches[i + 1], i == 0)
             main.wait_event(self.copied[slot])
-            fn(*self.sets[slot])
+            fn(*self._inputs(slot))
             self.consumed[slot].record(main)

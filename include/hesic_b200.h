@@ -204,6 +204,11 @@ int hesic_dense_warp(const hesic_tensor *h1, const hesic_tensor *cost, const hes
  * 2 round-half-even (EntropyModel._quantize 'dequantize', entropy_models.py:98-125). */
 enum { HESIC_OP_COPY = 0, HESIC_OP_ABS = 1, HESIC_OP_ROUND = 2 };
 int hesic_convert(const hesic_tensor *x, const hesic_tensor *y, int op, void *stream);
+/* 8-bit interleaved images -> the path's input tensors: src dev uint8 [B][H][W][C] (as cv2.imread / PIL deliver them and
+ * the reference's loader holds them until transforms.ToTensor(), compressai/datasets/utils.py:101-102,
+ * ywz/mywork/test3real.py:323), dst NCHW fp32 = float(u8) / 255 -- ToTensor's arithmetic, one IEEE division.  Lets a
+ * caller ship 1 byte per sample over PCIe instead of 4. */
+int hesic_images_from_u8(const uint8_t *src, int B, int H, int W, int C, const hesic_tensor *dst, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Symbol / CDF-index preparation for the host rANS coder -- integer outputs, bit-exact with

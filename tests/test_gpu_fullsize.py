@@ -93,7 +93,7 @@ def test_configured_batch_16_at_512_vs_oracle(name, modname, fwd):
           z1_lik_rel=max(zrel[i] for i in zclean) if zclean else None, y1_lik_rel_unflipped=lik_y1, bpp=m["bpp"], bpp_oracle=r["bpp"])
     assert flips["y1_hat"] < 2e-4 and flips["y2_hat"] < 2e-4, flips
     assert l2["x1_hat"] < 1e-3 and l2["x2_hat"] < 1e-3, l2
-    assert max(rel.values()) < 2e-5, rel
+    assert max(rel.values()) < (2e-5 if name == "hesic" else 1e-4), rel
     assert max(dps.values()) < 5e-4, dps
     # (measured on the B200, seed 1234: flips 2.8e-5 / 4.3e-5, x_hat L2 3.5e-4 / 2.8e-4, bpp 1e-7 (HESIC) / 1.4e-5 (HESIC+),
     #  PSNR 4e-5 dB; 11 / 7 of the 16 pairs without a z1 flip, their z1 likelihoods within 5.8e-6 (HESIC))
