@@ -58,15 +58,6 @@ struct Tap {
   int16_t pad_;
 };
 
-// A tap COLUMN of the CTA-pair kernel's activation reuse (conv_tc_pair.cuh, COLS): the taps that share the parity plane
-// (py, px) and the x shift dx and differ only in dy = dy0 .. dy0 + ndy - 1; w[i] = weight tile of tap dy0 + i (-1: none)
-constexpr int MAX_COL_TAPS = 5;
-struct Col {
-  int8_t dx, py, px, dy0, ndy, pad_[3];
-  int16_t w[MAX_COL_TAPS];
-  int16_t pad2_;
-};
-
 struct Params {
   int tiles_x, tiles_y, tiles_b;
   int lbw, lbh;            // log2 of the box width / height (bw*bh*bb == 128)
@@ -100,11 +91,6 @@ struct Params {
   int stages;
   uint32_t stage_bytes, b_bytes;
   int n_tasks;
-  // CTA-pair kernel with activation column reuse
-  int col_begin[5];
-  Col cols[MAX_TAPS];
-  int na_slots, nb_slots;
-  uint32_t a_slot_bytes, a_row_bytes;   // A slot = {hi, lo} x (bh + halo) rows x bw pixels x 128 B; one image row = bw x 128 B
 };
 
 struct TaskCoord {
@@ -723,46 +709,6 @@ static int build_taps(const hesic_conv *c, Params &p) {
   return n;
 }
 
-// Group the taps of every phase into columns (same parity plane and dx, consecutive dy).  Returns the largest dy
-// span minus one (the halo rows a column's box adds to the tile), or -1 when a column would not fit.
-static int build_cols(Params &p) {
-  int n = 0, halo = 0;
-  for (int ph = 0; ph < p.n_phases; ++ph) {
-    p.col_begin[ph] = n;
-    const int first = n;
-    for (int t = p.tap_begin[ph]; t < p.tap_begin[ph + 1]; ++t) {
-      const Tap &tp = p.taps[t];
-      int ci = -1;
-      for (int j = first; j < n; ++j)
-        if (p.cols[j].dx == tp.dx && p.cols[j].py == tp.py && p.cols[j].px == tp.px) { ci = j; break; }
-      if (ci < 0) {
-        if (n >= MAX_TAPS) return -1;
-        ci = n++;
-        Col &c = p.cols[ci];
-        memset(&c, 0, sizeof(c));
-        c.dx = tp.dx; c.py = tp.py; c.px = tp.px; c.dy0 = tp.dy; c.ndy = 1;
-        for (int i = 0; i < MAX_COL_TAPS; ++i) c.w[i] = -1;
-        c.w[0] = tp.w;
-        continue;
-      }
-      Col &c = p.cols[ci];
-      // taps arrive in increasing ky, i.e. increasing dy within a parity plane; still handle any order
-      int lo = std::min<int>(c.dy0, tp.dy), hi = std::max<int>(c.dy0 + c.ndy - 1, tp.dy);
-      if (hi - lo + 1 > MAX_COL_TAPS) return -1;
-      if (lo < c.dy0) {
-        const int sh = c.dy0 - lo;
-        for (int i = MAX_COL_TAPS - 1; i >= 0; --i) c.w[i] = i >= sh ? c.w[i - sh] : (int16_t)-1;
-        c.dy0 = (int8_t)lo;
-      }
-      c.ndy = (int8_t)(hi - lo + 1);
-      c.w[tp.dy - c.dy0] = tp.w;
-    }
-    for (int j = first; j < n; ++j) halo = std::max(halo, p.cols[j].ndy - 1);
-  }
-  p.col_begin[p.n_phases] = n;
-  return halo;
-}
-
 }  // namespace tc
 
 bool conv_tc_supported(const hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y) {
@@ -1036,7 +982,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
       num_sms >= 2 && p.kchunks * ntaps >= 8) {
     static PerDeviceOnce pair_once;
     if (pair_once.first())
-      HESIC_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      HESIC_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CUtensorMap mw64;
     {
       uint64_t dims[3] = {(uint64_t)c->tc_k, (uint64_t)c->CoutPad, (uint64_t)c->tc_taps};
@@ -1057,56 +1003,11 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
     q.n_tiles = (c->Cout + 127) / 128;
     q.n_tasks = ((m_tiles + 1) / 2) * p.n_phases * q.n_tiles;     // PAIR tasks
-    const int pfixed = 1024 + PAIR_BAR_BYTES + CHAN_BYTES + STAGING_BYTES;
+    const int pfixed = 1024 + BAR_BYTES + CHAN_BYTES + STAGING_BYTES;
+    q.stages = std::min(8, (SMEM_LIMIT - pfixed) / PAIR_STAGE_BYTES);
     q.stg_sets = 1;
     const int pgrid = std::min(2 * q.n_tasks, num_sms & ~1);
-    // activation column reuse (COLS): tiles of whole image rows of ONE image (the halo rows of a column follow the
-    // tile's rows in the same box), rows of whole swizzle atoms, and a column structure that actually shares rows
-    static const bool cols_on = getenv("HESIC_TC_PAIR_NO_COLS") == nullptr;
-    const int halo = build_cols(q);
-    if (cols_on && halo >= 1 && p.bb == 1 && p.bw >= 8 && p.bh + halo <= 256) {
-      q.a_row_bytes = (uint32_t)p.bw * 128u;
-      q.a_slot_bytes = 2u * (uint32_t)(p.bh + halo) * q.a_row_bytes;
-      const int avail = SMEM_LIMIT - pfixed;
-      // two A slots (a slot lives for a whole column = 2..5 taps), the rest of shared memory as B slots (one per tap)
-      q.na_slots = 2;
-      q.nb_slots = std::min(8, (avail - q.na_slots * (int)q.a_slot_bytes) / PAIR_B_BYTES);
-      if (q.nb_slots >= 5 && avail - 3 * (int)q.a_slot_bytes >= 3 * PAIR_B_BYTES) {   // room to spare: a third A slot
-        q.na_slots = 3;
-        q.nb_slots = std::min(8, (avail - 3 * (int)q.a_slot_bytes) / PAIR_B_BYTES);
-      }
-      if (q.nb_slots >= 3) {
-        CUtensorMap mc_hi, mc_lo;
-        {
-          // same views as ma_hi / ma_lo, box = the tile's rows + halo
-          uint64_t dims[5], strides[4];
-          uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bw, 1u, (uint32_t)(p.bh + halo), 1u};
-          const uint64_t e = 2;
-          if (!c->transposed && c->stride == 2) {
-            dims[0] = (uint64_t)xCs + x->C; dims[1] = x->W / 2; dims[2] = 2; dims[3] = x->H / 2; dims[4] = x->B;
-            strides[0] = 2ull * xCs * e; strides[1] = (uint64_t)x->W * xCs * e; strides[2] = 2ull * x->W * xCs * e;
-            strides[3] = (uint64_t)x->H * x->W * xCs * e;
-          } else {
-            dims[0] = x->C; dims[1] = x->W; dims[2] = 1; dims[3] = x->H; dims[4] = x->B;
-            strides[0] = (uint64_t)xCs * e; strides[1] = (uint64_t)x->W * xCs * e; strides[2] = (uint64_t)x->W * xCs * e;
-            strides[3] = (uint64_t)x->H * x->W * xCs * e;
-          }
-          int r = make_map(&mc_hi, x->p0, 5, dims, strides, box);
-          if (r == HESIC_OK) r = make_map(&mc_lo, x->p1, 5, dims, strides, box);
-          if (r != HESIC_OK) return r;
-        }
-        static PerDeviceOnce cols_once;
-        if (cols_once.first())
-          HESIC_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        const int smem = q.na_slots * (int)q.a_slot_bytes + q.nb_slots * PAIR_B_BYTES + pfixed;
-        conv_tc_pair_kernel<true><<<pgrid, NUM_THREADS, smem, s>>>(mc_hi, mc_lo, m[0], m[1], mw64, mg_hi, mg_lo, my0, my1, q);
-        HESIC_LAUNCHED("conv_tc_pair_kernel<cols>");
-        return HESIC_OK;
-      }
-    }
-    q.na_slots = q.nb_slots = 0; q.a_slot_bytes = q.a_row_bytes = 0;
-    q.stages = std::min(8, (SMEM_LIMIT - pfixed) / PAIR_STAGE_BYTES);
-    conv_tc_pair_kernel<false><<<pgrid, NUM_THREADS, q.stages * PAIR_STAGE_BYTES + pfixed, s>>>(ma_hi, ma_lo, m[0], m[1], mw64, mg_hi, mg_lo, my0, my1, q);
+    conv_tc_pair_kernel<<<pgrid, NUM_THREADS, q.stages * PAIR_STAGE_BYTES + pfixed, s>>>(ma_hi, ma_lo, m[0], m[1], mw64, mg_hi, mg_lo, my0, my1, q);
     HESIC_LAUNCHED("conv_tc_pair_kernel");
     return HESIC_OK;
   }

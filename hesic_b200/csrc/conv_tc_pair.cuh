@@ -20,19 +20,6 @@ namespace tc {
 
 constexpr int PAIR_B1_BYTES = 128 * 128, PAIR_B2_BYTES = 64 * 128;
 constexpr int PAIR_STAGE_BYTES = 2 * A_TILE_BYTES + PAIR_B1_BYTES + PAIR_B2_BYTES;   // 56 KB
-constexpr int PAIR_B_BYTES = PAIR_B1_BYTES + PAIR_B2_BYTES;                          // 24 KB: one B slot (COLS)
-constexpr int PAIR_BAR_BYTES = 512;                                                  // barrier block of the pair kernel
-
-// COLS = true: activation COLUMN reuse.  r02 finding (profiles/r02_l2_bound.md): the K-heavy layers move 11-13 TB/s from
-// L2 into the SMs -- the measured cap of the L2 slices (~6300 B/clk chip-wide) -- so they are bound by L2 bandwidth, not by
-// the tensor pipe (77 % active): every (tap, 64-channel chunk) step re-fetched its own 128-pixel A box (2 x 16 KB) although
-// the boxes of taps that differ only in dy are the same pixels shifted by whole image rows.  Here a TMA box covers the
-// tile's bh rows PLUS the halo rows of one tap column (same dx / parity plane, all its dy): it is loaded ONCE into an
-// "A slot" and every tap of the column reads it through a UMMA descriptor whose start address is advanced by dy image
-// rows (bw pixels x 128 B = a multiple of the 1024-byte swizzle atom, so the swizzle phase is unchanged).  A k5 s2 conv
-// fetches 95 row units per chunk instead of 200, a k5 s1 conv 60 instead of 200; the weight tiles travel through their
-// own ring of B slots, one per tap as before.  Two rings: A slots (a_full / a_empty, released after the column's last
-// tap) and B slots (b_full / b_empty, released per tap; the gamma tiles of a GDN step use a B slot).
 
 // pair task -> (pixel-tile pair, phase, N tile); CTA `rank` of the pair takes pixel tile 2 * mtp + rank
 __device__ __forceinline__ TaskCoord decode_pair_task(const Params &p, int task, int rank) {
@@ -45,7 +32,6 @@ __device__ __forceinline__ TaskCoord decode_pair_task(const Params &p, int task,
   return t;
 }
 
-template <bool COLS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -54,22 +40,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_y1, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // COLS: [A slots][B slots][staging][barriers]; else [stages][staging][barriers]
-  const uint32_t bslot_base = smem_base + (uint32_t)p.na_slots * p.a_slot_bytes;
-  const uint32_t stg_base = COLS ? bslot_base + (uint32_t)p.nb_slots * PAIR_B_BYTES : smem_base + (uint32_t)p.stages * PAIR_STAGE_BYTES;
+  const uint32_t stg_base = smem_base + (uint32_t)p.stages * PAIR_STAGE_BYTES;
   const uint32_t bar_base = stg_base + (uint32_t)STAGING_BYTES;
-  // barrier map (8 B each).  !COLS: full 0.., empty 64..   COLS: a_full 0.. (4), a_empty 32.. (4), b_full 64.. (8), b_empty 192.. (8)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
-  auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 32u + 8u * s; };
-  auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };
-  auto b_empty = [&](int s) { return bar_base + 256u + 8u * s; };
   auto acc_full = [&](int b) { return bar_base + 128u + 8u * b; };
   auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };
   const uint32_t x2_full = bar_base + 160u, norm_full = bar_base + 168u;
   const uint32_t tmem_slot = bar_base + 192u;
-  const uint32_t bias_s = bar_base + PAIR_BAR_BYTES, beta_s = bias_s + 512u;
+  const uint32_t bias_s = bar_base + BAR_BYTES, beta_s = bias_s + 512u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -80,12 +59,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   if (warp == 0 && lane == 0) {
     prefetch_map(&map_a_hi); prefetch_map(&map_a_lo); prefetch_map(&map_w_hi); prefetch_map(&map_w_lo);
     prefetch_map(&map_w_hi64); prefetch_map(&map_y0); prefetch_map(&map_y1);
-    if (COLS) {
-      for (int s = 0; s < p.na_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-      for (int s = 0; s < p.nb_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    } else {
-      for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 2 * EPI_THREADS); }
     mbar_init(x2_full, 2 * EPI_THREADS); mbar_init(norm_full, 1);
     if (p.gdn) { prefetch_map(&map_g_hi64); prefetch_map(&map_g_lo64); }
@@ -104,60 +78,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0 && COLS) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      // the gamma tiles of a GDN step travel through a B slot: each CTA loads its 64-row half of gamma_hi and gamma_lo
-      auto gdn_step = [&](int c) {
-        mbar_wait(b_empty(sb), pb ^ 1u, 9);
-        const uint32_t dst = bslot_base + (uint32_t)sb * PAIR_B_BYTES;
-        const uint32_t fb = mapa_cta(b_full(sb), 0);
-        if (leader) mbar_expect_tx(b_full(sb), 2u * 2u * (uint32_t)PAIR_B2_BYTES);
-        tma_load_2d_pair(&map_g_hi64, dst, fb, c * BK, 64 * (int)rank);
-        tma_load_2d_pair(&map_g_lo64, dst + PAIR_B2_BYTES, fb, c * BK, 64 * (int)rank);
-        if (++sb == p.nb_slots) { sb = 0; pb ^= 1u; }
-      };
-      int lt = 0;
-      for (int task = first; task < n_pairs; task += step, ++lt) {
-        const TaskCoord tk = decode_pair_task(p, task, (int)rank);
-        const int tb = tk.mt / txy, rr = tk.mt - tb * txy;
-        const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
-        const int c0 = p.col_begin[tk.ph], c1 = p.col_begin[tk.ph + 1];
-        const int kc0 = p.kc_lo[tk.nt & 7], kc1 = p.kc_hi[tk.nt & 7];
-        const int ksteps = (p.tap_begin[tk.ph + 1] - p.tap_begin[tk.ph]) * (kc1 - kc0);
-        const int g = (p.gdn && lt > 0) ? min(p.gdn_at, ksteps - 1) : -1;
-        int ks = 0;
-        for (int kc = kc0; kc < kc1; ++kc) {
-          for (int ci = c0; ci < c1; ++ci) {
-            const Col col = p.cols[ci];
-            // the column's rows [y + dy0, y + dy0 + bh + halo) of parity plane (py, px), shifted by dx: ONE box per plane
-            mbar_wait(a_empty(sa), pa ^ 1u, 1);
-            const uint32_t da = smem_base + (uint32_t)sa * p.a_slot_bytes;
-            const uint32_t fa = mapa_cta(a_full(sa), 0);
-            if (leader) mbar_expect_tx(a_full(sa), 2u * p.a_slot_bytes);
-            const int c = kc * BK + col.px * p.in_Cs;
-            const int x = tx * p.bw + col.dx, y = ty * p.bh + col.dy0;
-            tma_load_5d_pair(&map_a_hi, da, fa, c, x, col.py, y, tb);
-            tma_load_5d_pair(&map_a_lo, da + (p.a_slot_bytes >> 1), fa, c, x, col.py, y, tb);
-            if (++sa == p.na_slots) { sa = 0; pa ^= 1u; }
-            for (int i = 0; i < col.ndy; ++i) {
-              const int w = col.w[i];
-              if (w < 0) continue;
-              if (ks == g) { gdn_step(0); gdn_step(1); }
-              mbar_wait(b_empty(sb), pb ^ 1u, 1);
-              const uint32_t db = bslot_base + (uint32_t)sb * PAIR_B_BYTES;
-              const uint32_t fb = mapa_cta(b_full(sb), 0);
-              if (leader) mbar_expect_tx(b_full(sb), 2u * (uint32_t)PAIR_B_BYTES);
-              tma_load_3d_pair(leader ? &map_w_hi : &map_w_lo, db, fb, kc * BK, tk.nt * 128, w);
-              tma_load_3d_pair(&map_w_hi64, db + PAIR_B1_BYTES, fb, kc * BK, tk.nt * 128 + 64 * (int)rank, w);
-              if (++sb == p.nb_slots) { sb = 0; pb ^= 1u; }
-              ++ks;
-            }
-          }
-        }
-      }
-      if (p.gdn && lt > 0) { gdn_step(0); gdn_step(1); }
-    } else if (lane == 0) {
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       // the gamma tiles of a GDN step: each CTA loads its 64-row half of gamma_hi and gamma_lo (16 KB) for K chunk c
@@ -203,82 +124,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader && COLS) {
-      int sa = 0, sb = 0, lt = 0;
-      uint32_t pa = 0, pb = 0;
-      const uint32_t idesc256 = instr_desc_pair(256), idesc128 = instr_desc_pair(128);
-      auto gdn_step = [&](int glt, int c) {
-        const int gbuf = glt & 1;
-        if (c == 0) {
-          mbar_wait(x2_full, (uint32_t)glt & 1u, 4);
-          tc_fence_after();
-        }
-        mbar_wait(b_full(sb), pb, 6);
-        tc_fence_after();
-        const uint32_t sbase = bslot_base + (uint32_t)sb * PAIR_B_BYTES;
-        const uint64_t g_hi = smem_desc(sbase), g_lo = smem_desc(sbase + PAIR_B2_BYTES);
-        const uint32_t x2 = tmem_base + (uint32_t)gbuf * ACC_STRIDE, d = x2 + COL_SMALL;
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t o = (uint64_t)(k * 2);
-          const uint32_t ah = x2 + (uint32_t)(c * 32 + k * 8);
-          const uint32_t al = x2 + 64u + (uint32_t)(c * 32 + k * 8);
-          mma_ts_pair(d, ah, g_hi + o, idesc128, (c == 0 && k == 0) ? 0u : 1u);
-          mma_ts_pair(d, ah, g_lo + o, idesc128, 1u);
-          mma_ts_pair(d, al, g_hi + o, idesc128, 1u);
-        }
-        tc_commit_pair(b_empty(sb));
-        if (c == 1) tc_commit_pair(norm_full);
-        if (++sb == p.nb_slots) { sb = 0; pb ^= 1u; }
-      };
-      const uint32_t a_half = p.a_slot_bytes >> 1;
-      for (int task = first; task < n_pairs; task += step, ++lt) {
-        const TaskCoord tk = decode_pair_task(p, task, 0);
-        const int buf = lt & 1;
-        const int c0 = p.col_begin[tk.ph], c1 = p.col_begin[tk.ph + 1];
-        const int kc0 = p.kc_lo[tk.nt & 7], kc1 = p.kc_hi[tk.nt & 7];
-        const int ksteps = (p.tap_begin[tk.ph + 1] - p.tap_begin[tk.ph]) * (kc1 - kc0);
-        const int g = (p.gdn && lt > 0) ? min(p.gdn_at, ksteps - 1) : -1;
-        const uint32_t d_main = tmem_base + (uint32_t)buf * ACC_STRIDE, d_small = d_main + COL_SMALL;
-        int ks = 0;
-        for (int kc = kc0; kc < kc1; ++kc) {
-          for (int ci = c0; ci < c1; ++ci) {
-            const Col col = p.cols[ci];
-            mbar_wait(a_full(sa), pa, 3);
-            tc_fence_after();
-            const uint32_t abase = smem_base + (uint32_t)sa * p.a_slot_bytes;
-            for (int i = 0; i < col.ndy; ++i) {
-              if (col.w[i] < 0) continue;
-              if (ks == g) { gdn_step(lt - 1, 0); gdn_step(lt - 1, 1); }
-              if (ks == 0) {
-                mbar_wait(acc_empty(buf), (((uint32_t)lt >> 1) & 1u) ^ 1u, 2);
-                tc_fence_after();
-              }
-              mbar_wait(b_full(sb), pb, 3);
-              tc_fence_after();
-              // tap dy0 + i of the column: the same box, read from image row i on (whole swizzle atoms further)
-              const uint32_t arow = abase + (uint32_t)i * p.a_row_bytes;
-              const uint64_t a_hi = smem_desc(arow), a_lo = smem_desc(arow + a_half);
-              const uint32_t sbase = bslot_base + (uint32_t)sb * PAIR_B_BYTES;
-              const uint64_t b1 = smem_desc(sbase), b2 = smem_desc(sbase + PAIR_B1_BYTES);
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint64_t o = (uint64_t)(k * 2);
-                mma_ss_pair(d_main, a_hi + o, b1 + o, idesc256, (ks == 0 && k == 0) ? 0u : 1u);
-                mma_ss_pair(d_small, a_lo + o, b2 + o, idesc128, 1u);
-              }
-              tc_commit_pair(b_empty(sb));
-              if (ks == ksteps - 1) tc_commit_pair(acc_full(buf));
-              if (++sb == p.nb_slots) { sb = 0; pb ^= 1u; }
-              ++ks;
-            }
-            tc_commit_pair(a_empty(sa));     // arrives when the column's last MMA has read the slot
-            if (++sa == p.na_slots) { sa = 0; pa ^= 1u; }
-          }
-        }
-      }
-      if (p.gdn && lt > 0) { gdn_step(lt - 1, 0); gdn_step(lt - 1, 1); }
-    } else if (lane == 0 && leader) {
+    if (lane == 0 && leader) {
       int stage = 0, lt = 0;
       uint32_t phase = 0;
       const uint32_t idesc256 = instr_desc_pair(256), idesc128 = instr_desc_pair(128);
