@@ -20,6 +20,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
 OP_COPY, OP_ABS, OP_ROUND = 0, 1, 2
 EB_PARAMS = 60
+GN_SLOTS = 8
 
 
 class HesicError(RuntimeError):
@@ -72,6 +73,8 @@ _sig = {
     "hesic_convert": ([_TP, _TP, c_int, c_void_p], c_int),
     "hesic_images_from_u8": ([c_void_p, c_int, c_int, c_int, c_int, _TP, c_void_p], c_int),
     "hesic_group_norm": ([_TP, _TP, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p], c_int),
+    "hesic_conv_forward_gn": ([c_void_p, _TP, _TP, c_int, c_void_p, c_int, c_void_p], c_int),
+    "hesic_group_norm_apply": ([_TP, _TP, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p], c_int),
     "hesic_softmax_channels": ([_TP, _TP, c_void_p], c_int),
     "hesic_dense_warp": ([_TP, _TP, _TP, c_void_p], c_int),
     "hesic_prepare_symbols": ([_TP, c_void_p, _TP, c_void_p, c_void_p], c_int),

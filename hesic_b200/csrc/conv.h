@@ -12,6 +12,7 @@
 //   ROW2     Cin <= 4, k5, stride 2 (the first analysis layer, RGB -> N): input in ROWPAD format with 4 channel
 //            slots; one k-step per PAIR of kernel rows, K = 2 rows x 8 pixels x 4 slots, 3 k-steps instead of 5;
 //            weights [3][CoutPad][64] stay resident in shared memory for the whole kernel
+constexpr int HESIC_GN_SLOTS = 8;   // partial-sum slots per (image, group): spreads the epilogues' atomics
 enum { HESIC_TC_GENERIC = 0, HESIC_TC_ROW = 1, HESIC_TC_SCATTER = 2, HESIC_TC_ROW2 = 3 };
 
 struct hesic_conv {
@@ -38,6 +39,10 @@ struct hesic_conv {
   float *gdn_beta = nullptr;    // reparametrised beta [Cout]
   float *gdn_w_simt = nullptr;  // fp32 [Cout(j)][Cout(i)] = gamma[i][j]
   __nv_bfloat16 *gdn_g_hi = nullptr, *gdn_g_lo = nullptr;  // bf16 planes [Cout(i)][Cout(j)] (K-major)
+  // GroupNorm statistics fused into the epilogue (hesic_conv_forward_gn): set for the duration of one launch
+  double *gn_stats = nullptr;   // [B][groups][HESIC_GN_SLOTS][2] partial (sum, sum of squares), zeroed by the caller
+  int gn_groups = 0;
+  bool gn_fused = false;        // out: the launched kernel accumulated the statistics
   // tcgen05 path: cached TMA tensor maps of the static operands (w_hi, w_lo, gamma_hi, gamma_lo)
   unsigned char *tc_maps = nullptr;
   int tc_maps_bn = 0, tc_maps_gdn = -1;

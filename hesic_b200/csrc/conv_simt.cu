@@ -542,6 +542,26 @@ extern "C" int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const he
   return conv_forward_any(c, x, nullptr, y, act, path, stream);
 }
 
+namespace hesic { int gn_stats_slotted(const hesic_tensor *x, int groups, double *stats, cudaStream_t st); }
+
+// Convolution whose NHWC fp32 output is followed by nn.GroupNorm: also produces the group statistics
+// stats[B][groups][HESIC_GN_SLOTS][2] = partial (sum, sum of squares) -- in the tensor-core epilogue where the tile
+// geometry allows (no second pass over the output), else with the statistics kernel.
+extern "C" int hesic_conv_forward_gn(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y, int path, double *stats, int groups,
+                                     void *stream) {
+  HESIC_REQUIRE(c && y && stats && groups >= 1, "hesic_conv_forward_gn: null argument");
+  HESIC_REQUIRE(y->fmt == HESIC_FMT_NHWC_F32 && c->Cout % groups == 0, "hesic_conv_forward_gn: NHWC fp32 output, channels divisible by groups");
+  cudaStream_t s = as_stream(stream);
+  HESIC_CUDA(cudaMemsetAsync(stats, 0, (size_t)y->B * groups * HESIC_GN_SLOTS * 2 * sizeof(double), s));
+  static const bool unfused = getenv("HESIC_GN_UNFUSED") != nullptr;     // diagnostic: always use the statistics kernel
+  c->gn_stats = unfused ? nullptr : stats; c->gn_groups = groups; c->gn_fused = false;
+  const int r = conv_forward_any(c, x, nullptr, y, HESIC_ACT_NONE, path, stream);
+  const bool fused = c->gn_fused;
+  c->gn_stats = nullptr; c->gn_groups = 0; c->gn_fused = false;
+  if (r != HESIC_OK || fused) return r;
+  return gn_stats_slotted(y, groups, stats, s);
+}
+
 extern "C" int hesic_conv_forward_cat(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y,
                                       int act, int path, void *stream) {
   HESIC_REQUIRE(xb != nullptr, "hesic_conv_forward_cat: null second input");

@@ -91,7 +91,33 @@ struct Params {
   int stages;
   uint32_t stage_bytes, b_bytes;
   int n_tasks;
+  // GroupNorm statistics of the output (nn.GroupNorm follows the conv, mynet6_plus.py:224-290): every epilogue warp adds
+  // the (sum, sum of squares) of its 32 pixels x 32 channels to stats[b][group][slot] -- the separate statistics pass
+  // over the conv output (one full read of the tensor) disappears.  Requires one image per tile and 32-channel chunks
+  // that do not straddle groups.
+  double *stats;
+  int stat_cpg, stat_groups;
 };
+
+// (sum, sum of squares) of v[32] over the warp's valid pixels -> one pair of fp64 atomics per warp and chunk
+__device__ __forceinline__ void gn_accumulate(const Params &p, const float (&v)[32], bool valid, int b, int chan0) {
+  float s = 0.f, ss = 0.f;
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { s += v[j]; ss = fmaf(v[j], v[j], ss); }
+  }
+  double ds = (double)s, dss = (double)ss;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dss += __shfl_xor_sync(0xffffffffu, dss, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    double *d = p.stats + ((((size_t)b * p.stat_groups + chan0 / p.stat_cpg) * HESIC_GN_SLOTS) + (blockIdx.x & (HESIC_GN_SLOTS - 1))) * 2;
+    atomicAdd(d, ds);
+    atomicAdd(d + 1, dss);
+  }
+}
 
 struct TaskCoord {
   int mt, ph, nt;
@@ -161,7 +187,23 @@ __device__ __forceinline__ void store_chunk(const Params &p, const float (&v)[32
   }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EPI_WARPS = 8: two epilogue groups of four warps, 64 channels per thread (all layers).
+// EPI_WARPS = 16 (fused-GDN layers whose K loop is too short to hide the epilogue -- the first analysis layer): four
+// groups, 32 channels per thread.  r02 profile of that layer (profiles/r02_ncu_conv1_stalls.md): the epilogue warps issue
+// one instruction every ~7 cycles (fixed-latency dependencies, TMEM / shared-memory round trips, instruction fetch) and
+// with two warps per scheduler nothing covers those gaps; twice the warps at half the registers do.
+template <int EPI_WARPS>
+__device__ __forceinline__ void epi_bar_all() {
+  if (EPI_WARPS == 16) asm volatile("bar.sync 1, 512;" ::: "memory");
+  else asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_half(int half) {
+  if (half == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+  else asm volatile("bar.sync 3, 256;" ::: "memory");
+}
+
+template <int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
@@ -189,8 +231,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (p.gdn) { prefetch_map(&map_g_hi); prefetch_map(&map_g_lo); }
     if (p.tma_store) { prefetch_map(&map_y0); prefetch_map(&map_y1); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), p.planar ? 128 : EPI_THREADS); }
-    mbar_init(x2_full, EPI_THREADS); mbar_init(norm_full, 1); mbar_init(w_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), p.planar ? 128 : 32 * EPI_WARPS); }
+    mbar_init(x2_full, 32 * EPI_WARPS); mbar_init(norm_full, 1); mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -328,6 +370,121 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             advance();
           });
     }
+  } else if (EPI_WARPS == 16) {
+    // ===================== epilogue, four groups (fused GDN, SPLIT output through TMA stores) =====================
+    // group g = (warp - 2) / 4 owns the 32-channel chunk g; chunks (0, 1) and (2, 3) each fill one staging tile pair
+    // (64 channels: hi tile + lo tile) and have their own store barrier and issuing thread.
+    const int quad = warp & 3, grp = (warp - 2) >> 2, half = grp >> 1;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int txy = p.tiles_x * p.tiles_y;
+    const bool is_issuer = (int)threadIdx.x == 64 + 256 * half;
+    const uint32_t stg_set = stg_base + (uint32_t)half * (uint32_t)STAGING_BYTES;
+    const uint32_t row_off = stg_set + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    const bool igdn = p.gdn == 2;
+    int lt = 0;
+    for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x, ++lt) {
+      const TaskCoord tk = decode_task(p, task);
+      const int buf = lt & 1;
+      const int tb = tk.mt / txy, rr = tk.mt - tb * txy;
+      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      const int ry = tk.ph / p.os, rx = tk.ph - ry * p.os;
+      const int n0 = tk.nt * p.BN;
+      const uint32_t acc = tmem_base + lane_addr + (uint32_t)buf * ACC_STRIDE;
+      const int c_fold = rx * p.out_Cs, mx = tx * p.bw, my = ty * p.bh, mb = tb * p.bb;
+
+      epi_bar_all<16>();
+      const int ci = (int)threadIdx.x - 64;
+      if (ci < 128) {
+        st_shared_f32(bias_s + 4u * ci, (n0 + ci < p.Cout) ? __ldg(p.bias + n0 + ci) : 0.f);
+        st_shared_f32(beta_s + 4u * ci, __ldg(p.beta + ci));
+      }
+      epi_bar_all<16>();
+
+      mbar_wait(acc_full(buf), ((uint32_t)lt >> 1) & 1u, 7);
+      tc_fence_after();
+      // pass 1: x = main + small + bias, 16 columns at a time
+      float xs[32];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[16], q[16];
+        tmem_ld16(acc + grp * 32 + hh * 16, r);
+        tmem_ld16(acc + COL_SMALL + grp * 32 + hh * 16, q);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = ld_shared_f4(bias_s + 128u * grp + 64u * hh + 16u * j);
+          xs[hh * 16 + 4 * j + 0] = (__uint_as_float(r[4 * j + 0]) + __uint_as_float(q[4 * j + 0])) + t.x;
+          xs[hh * 16 + 4 * j + 1] = (__uint_as_float(r[4 * j + 1]) + __uint_as_float(q[4 * j + 1])) + t.y;
+          xs[hh * 16 + 4 * j + 2] = (__uint_as_float(r[4 * j + 2]) + __uint_as_float(q[4 * j + 2])) + t.z;
+          xs[hh * 16 + 4 * j + 3] = (__uint_as_float(r[4 * j + 3]) + __uint_as_float(q[4 * j + 3])) + t.w;
+        }
+      }
+      // every group has its chunk in registers before the main columns are overwritten by the x^2 operand
+      tc_fence_before();
+      epi_bar_all<16>();
+      tc_fence_after();
+      {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = xs[2 * j], c = xs[2 * j + 1];
+          split_pair(a * a, c * c, hi[j], lo[j]);
+        }
+        tmem_st16(acc + grp * 16, hi);
+        tmem_st16(acc + 64u + grp * 16, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(x2_full);
+      // pass 2: y = x * rsqrt(beta + norm)   (IGDN: * sqrt)
+      mbar_wait(norm_full, (uint32_t)lt & 1u, 8);
+      tc_fence_after();
+      {
+        uint32_t q[32];
+        tmem_ld32(acc + COL_SMALL + grp * 32, q);
+        tmem_ld_wait();
+#define HESIC_GDN_SCALE16(FN)                                                         \
+  _Pragma("unroll") for (int jj = 0; jj < 8; ++jj) {                                  \
+    const float4 bt = ld_shared_f4(beta_s + 128u * grp + 16u * jj);                   \
+    xs[4 * jj + 0] *= FN(__uint_as_float(q[4 * jj + 0]) + bt.x);                      \
+    xs[4 * jj + 1] *= FN(__uint_as_float(q[4 * jj + 1]) + bt.y);                      \
+    xs[4 * jj + 2] *= FN(__uint_as_float(q[4 * jj + 2]) + bt.z);                      \
+    xs[4 * jj + 3] *= FN(__uint_as_float(q[4 * jj + 3]) + bt.w);                      \
+  }
+        if (igdn) {
+          HESIC_GDN_SCALE16(sqrt_approx)
+        } else {
+          HESIC_GDN_SCALE16(rsqrt_approx)
+        }
+#undef HESIC_GDN_SCALE16
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(buf));
+      // store: this half's 64 channels as one (hi, lo) staging tile pair; the group fills bytes [64 (grp & 1), +64) of a row
+      if (is_issuer) bulk_wait_read<0>();      // the half's previous tile pair has left shared memory
+      epi_bar_half(half);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_pair(xs[g * 8 + 0], xs[g * 8 + 1], h0, l0);
+        split_pair(xs[g * 8 + 2], xs[g * 8 + 3], h1, l1);
+        split_pair(xs[g * 8 + 4], xs[g * 8 + 5], h2, l2);
+        split_pair(xs[g * 8 + 6], xs[g * 8 + 7], h3, l3);
+        const uint32_t o = row_off + (((uint32_t)((grp & 1) * 4 + g) ^ sw) << 4);
+        st_shared_v4(o, h0, h1, h2, h3);
+        st_shared_v4(o + A_TILE_BYTES, l0, l1, l2, l3);
+      }
+      fence_async_smem();
+      epi_bar_half(half);
+      if (is_issuer) {
+        const int c0 = c_fold + n0 + half * 64;
+        tma_store_5d(&map_y0, stg_set, c0, mx, ry, my, mb);
+        tma_store_5d(&map_y1, stg_set + A_TILE_BYTES, c0, mx, ry, my, mb);
+        bulk_commit();
+      }
+    }
+    if (is_issuer) bulk_wait_all();
   } else if (!(p.planar && warp >= 6)) {
     // ===================== epilogue =====================
     // Two groups of four warps; warp w reads TMEM lane quadrant w % 4 (= 32 pixels of the tile) and group
@@ -500,6 +657,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const float t = (__uint_as_float(r[j]) + __uint_as_float(q[j])) + v[j];
               v[j] = fmaxf(t, t * act_slope);
             }
+            if (p.stats) gn_accumulate(p, v, valid, b, n0 + ch * 32);
           }
           emit(v, i, active);
         }
@@ -587,7 +745,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   }
 
-  if (p.tma_store && threadIdx.x == 64) bulk_wait_all();   // staged tiles fully written before the CTA retires
+  if (EPI_WARPS == 8 && p.tma_store && threadIdx.x == 64) bulk_wait_all();   // staged tiles fully written before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -821,7 +979,8 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     int dev = 0;
     HESIC_CUDA(cudaGetDevice(&dev));
     HESIC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    HESIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    HESIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    HESIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   }
   const int xCs = x->Cs > 0 ? x->Cs : x->C, yCs = y->Cs > 0 ? y->Cs : y->C;
   const bool planar = c->Cout <= 4;
@@ -858,6 +1017,12 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   p.beta = c->gdn_beta;
   p.pl_gamma = c->gdn_w_simt;
   p.b_bytes = (uint32_t)p.BN * 128u;
+  c->gn_fused = false;
+  if (c->gn_stats && c->gn_groups >= 1 && !planar && !p.gdn && y->fmt == HESIC_FMT_NHWC_F32 && p.bb == 1 && c->Cout % 32 == 0 &&
+      c->Cout % c->gn_groups == 0 && (c->gn_groups == 1 || (c->Cout / c->gn_groups) % 32 == 0) && c->tc_kind == HESIC_TC_GENERIC) {
+    p.stats = c->gn_stats; p.stat_groups = c->gn_groups; p.stat_cpg = c->Cout / c->gn_groups;
+    c->gn_fused = true;
+  }
   // ROW2: the whole weight set (3 tiles, hi + lo) fits next to the pipeline -> loaded once per CTA; a stage then
   // carries only the A tiles (or, for a GDN step, the gamma tiles in the same space)
   p.n_wtiles = ntaps * p.kchunks;
@@ -1012,7 +1177,15 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     return HESIC_OK;
   }
   const int grid = std::min(p.n_tasks, num_sms);
-  conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], m[2], m[3], my0, my1, p);
+  // fused GDN on a short K loop (the first analysis layer): 16 epilogue warps, 32 channels per thread
+  static const bool epi16_on = getenv("HESIC_TC_EPI8") == nullptr;
+  if (epi16_on && p.gdn && !planar && p.tma_store && y->fmt == HESIC_FMT_NHWC_SPLIT && p.BN == 128 && p.n_tiles == 1 &&
+      p.stg_sets == 2 && c->Cout == 128) {
+    conv_tc_kernel<16><<<grid, 64 + 32 * 16, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], m[2], m[3], my0, my1, p);
+    HESIC_LAUNCHED("conv_tc_kernel<16>");
+    return HESIC_OK;
+  }
+  conv_tc_kernel<8><<<grid, NUM_THREADS, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], m[2], m[3], my0, my1, p);
   HESIC_LAUNCHED("conv_tc_kernel");
   return HESIC_OK;
 }

@@ -204,7 +204,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       const int n0 = tk.nt * 128;
       const uint32_t acc = tmem_base + lane_addr + (uint32_t)buf * ACC_STRIDE;
       const int c_fold = rx * p.out_Cs, mx = tx * p.bw, my = ty * p.bh, mb = tb * p.bb;
-      (void)xi; (void)yi; (void)bi;
+      // only the GroupNorm statistics need to know which of the tile's pixels exist (the TMA stores clip by themselves)
+      const bool valid = (tx * p.bw + xi) * p.os + rx < p.Wout && (ty * p.bh + yi) * p.os + ry < p.Hout && tb * p.bb + bi < p.B;
 
       epi_bar();
       const int ci = (int)threadIdx.x - 64;
@@ -279,6 +280,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               const float t = (__uint_as_float(r[j]) + __uint_as_float(q[j])) + v[j];
               v[j] = fmaxf(t, t * act_slope);
             }
+            if (p.stats) gn_accumulate(p, v, valid, tb * p.bb + bi, n0 + ch * 32);
           }
           emit(v, i, active);
         }

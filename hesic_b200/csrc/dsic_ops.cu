@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "conv.h"
 
 namespace hesic {
 
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(256) dense_warp_kernel(const TView h1, const T
 //
 // Statistics: block = R pixel rows x C/4 channel quads (a thread keeps ONE channel quad, hence one group, for the
 // whole kernel), fp64 accumulation, shared-memory atomics per group, one global atomic per (block, group).
-__global__ void __launch_bounds__(256) gn_stats_nhwc_kernel(const TView x, int G, int rows_per_block, double *__restrict__ stats) {
+__global__ void __launch_bounds__(256) gn_stats_nhwc_kernel(const TView x, int G, int rows_per_block, double *__restrict__ stats,
+                                                           int slot_stride) {
   extern __shared__ double gsum[];   // [2 * G]
   const int C4 = x.C >> 2, cpg = x.C / G;
   const int b = blockIdx.y;
@@ -149,18 +151,25 @@ __global__ void __launch_bounds__(256) gn_stats_nhwc_kernel(const TView x, int G
     atomicAdd(&gsum[2 * g + 1], ss);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(size_t)b * 2 * G + i], gsum[i]);
+  // stats[b][g][slot][2]: `slot_stride` doubles between groups (2 for the plain layout, 2 * HESIC_GN_SLOTS for the slotted one)
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x)
+    atomicAdd(&stats[((size_t)b * G + (i >> 1)) * slot_stride + (slot_stride > 2 ? 2 * (blockIdx.x & (HESIC_GN_SLOTS - 1)) : 0) + (i & 1)], gsum[i]);
 }
 
 // per (b, c): y = x * scale + shift with scale = rstd * weight[c], shift = bias[c] - mean * scale
-__global__ void gn_finalize_kernel(const double *__restrict__ stats, int B, int C, int G, double count,
+__global__ void gn_finalize_kernel(const double *__restrict__ stats, int slots, int B, int C, int G, double count,
                                    const float *__restrict__ weight, const float *__restrict__ bias, float eps,
                                    float *__restrict__ scale, float *__restrict__ shift) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C, g = c / (C / G);
-  const double mean = stats[2 * (b * G + g)] / count;
-  const double var = fmax(stats[2 * (b * G + g) + 1] / count - mean * mean, 0.0);
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < slots; ++k) {       // partial sums in a fixed order
+    s += stats[((size_t)(b * G + g) * slots + k) * 2];
+    ss += stats[((size_t)(b * G + g) * slots + k) * 2 + 1];
+  }
+  const double mean = s / count;
+  const double var = fmax(ss / count - mean * mean, 0.0);
   const double rstd = 1.0 / sqrt(var + (double)eps);
   const double w = weight ? (double)weight[c] : 1.0, bb = (weight && bias) ? (double)bias[c] : 0.0;
   scale[i] = (float)(rstd * w);
@@ -316,10 +325,10 @@ extern "C" int hesic_group_norm(const hesic_tensor *x, const hesic_tensor *y, in
     cudaMemsetAsync(stats, 0, stat_bytes, st);
     const int rows = 256 / C4;
     const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((HW + rows - 1) / rows, 2048 / std::max(1, x->B)));
-    gn_stats_nhwc_kernel<<<dim3(bx, x->B), 256, 2 * groups * sizeof(double), st>>>(view(x), groups, rows, stats);
+    gn_stats_nhwc_kernel<<<dim3(bx, x->B), 256, 2 * groups * sizeof(double), st>>>(view(x), groups, rows, stats, 2);
     int rc = launched("gn_stats_nhwc_kernel");
     if (rc == HESIC_OK) {
-      gn_finalize_kernel<<<(x->B * x->C + 255) / 256, 256, 0, st>>>(stats, x->B, x->C, groups, (double)cpg * (double)HW, weight, bias, eps,
+      gn_finalize_kernel<<<(x->B * x->C + 255) / 256, 256, 0, st>>>(stats, 1, x->B, x->C, groups, (double)cpg * (double)HW, weight, bias, eps,
                                                                   scale, shift);
       rc = launched("gn_finalize_kernel");
     }
@@ -345,6 +354,53 @@ extern "C" int hesic_group_norm(const hesic_tensor *x, const hesic_tensor *y, in
     rc = launched("gn_apply_kernel");
   }
   cudaFreeAsync(stats, st);
+  return rc;
+}
+
+// Statistics of an NHWC fp32 tensor into the slotted layout [B][groups][HESIC_GN_SLOTS][2] (the route for outputs whose
+// producing convolution could not accumulate them in its epilogue); `stats` zeroed by the caller.
+namespace hesic {
+int gn_stats_slotted(const hesic_tensor *x, int groups, double *stats, cudaStream_t st) {
+  const int C4 = x->C / 4;
+  HESIC_REQUIRE(x->fmt == HESIC_FMT_NHWC_F32 && x->C % 4 == 0 && (x->C / groups) % 4 == 0 && C4 <= 256 && x->B <= 65535,
+                "group-norm statistics: NHWC fp32 input with channels per group a multiple of 4 required");
+  const size_t HW = (size_t)x->H * x->W;
+  const int rows = 256 / C4;
+  const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((HW + rows - 1) / rows, 2048 / std::max(1, x->B)));
+  gn_stats_nhwc_kernel<<<dim3(bx, x->B), 256, 2 * groups * sizeof(double), st>>>(view(x), groups, rows, stats, 2 * HESIC_GN_SLOTS);
+  return launched("gn_stats_nhwc_kernel");
+}
+}  // namespace hesic
+
+extern "C" int hesic_group_norm_apply(const hesic_tensor *x, const hesic_tensor *y, int groups, const float *weight,
+                                      const float *bias, float eps, int relu, const double *stats, void *stream) {
+  int r;
+  if ((r = check_tensor(x, "group_norm input")) != HESIC_OK) return r;
+  if ((r = check_tensor(y, "group_norm output")) != HESIC_OK) return r;
+  HESIC_REQUIRE(same_shape(x, y) && stats, "group_norm_apply: shape mismatch or null statistics");
+  HESIC_REQUIRE(groups >= 1 && x->C % groups == 0, "group_norm: %d channels are not divisible into %d groups", x->C, groups);
+  HESIC_REQUIRE(x->fmt == HESIC_FMT_NHWC_F32 && (y->fmt == HESIC_FMT_NHWC_SPLIT || y->fmt == HESIC_FMT_NHWC_F32),
+                "group_norm_apply: NHWC fp32 input, NHWC fp32 or SPLIT output");
+  const int xCs = x->Cs > 0 ? x->Cs : x->C, yCs = y->Cs > 0 ? y->Cs : y->C;
+  HESIC_REQUIRE(x->C % 4 == 0 && xCs % 4 == 0 && yCs % 4 == 0 && ((uintptr_t)x->p0 & 15) == 0 && ((uintptr_t)y->p0 & 7) == 0 &&
+                    (y->fmt != HESIC_FMT_NHWC_SPLIT || ((uintptr_t)y->p1 & 7) == 0),
+                "group_norm_apply: channel counts / strides must be multiples of 4 and the tensors aligned");
+  const size_t n = numel(x);
+  if (n == 0) return HESIC_OK;
+  cudaStream_t st = as_stream(stream);
+  float *scale = nullptr;
+  const size_t aff = (size_t)x->B * x->C;
+  HESIC_CUDA(cudaMallocAsync(&scale, 2 * aff * sizeof(float), st));
+  float *shift = scale + aff;
+  const int cpg = x->C / groups;
+  gn_finalize_kernel<<<(unsigned)((aff + 255) / 256), 256, 0, st>>>(stats, HESIC_GN_SLOTS, x->B, x->C, groups,
+                                                                  (double)cpg * (double)x->H * (double)x->W, weight, bias, eps, scale, shift);
+  int rc = launched("gn_finalize_kernel");
+  if (rc == HESIC_OK) {
+    gn_apply_nhwc_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(view(x), view(y), scale, shift, relu, n / 4);
+    rc = launched("gn_apply_nhwc_kernel");
+  }
+  cudaFreeAsync(scale, st);
   return rc;
 }
 

@@ -92,11 +92,19 @@ class DsicEngine(HesicEngine):
     def _conv_gn(self, conv_or_plan, gn_mod, x_desc, B, H, W, dst=None, weight=None, bias=None):
         """conv -> GroupNorm -> ReLU; returns the SPLIT descriptor of the result (a fresh buffer unless dst is given)."""
         plan = conv_or_plan if isinstance(conv_or_plan, F.ConvPlan) else self._plan(conv_or_plan)
-        t, _, Ho, Wo = self._conv(plan, x_desc, B, H, W, "nhwc")
+        Ho, Wo = plan.out_hw(H, W)
         Cn = plan.geom[1]
+        G = gn_mod.num_groups
+        t = self._nhwc(B, Ho, Wo, Cn)
+        # the conv's epilogue also accumulates the GroupNorm statistics: no separate pass over its output
+        stats = self._keep(torch.empty((B, G, C.GN_SLOTS, 2), device=self.dev, dtype=torch.float64))
+        C.check(_lib.hesic_conv_forward_gn(plan.h, C.ref(x_desc), C.ref(C.nhwc(t)), self.path, C.ptr(stats), G, C.stream()))
         if dst is None:
             dst = (self._split(B, Ho, Wo, Cn), 0)
-        self._gn(gn_mod, t, dst[0], dst[1], Cn, weight, bias)
+        w = gn_mod.weight.detach() if weight is None else weight
+        b = gn_mod.bias.detach() if bias is None else bias
+        C.check(_lib.hesic_group_norm_apply(C.ref(C.nhwc(t)), C.ref(C.split(dst[0], Cn, dst[1])), G, C.ptr(w), C.ptr(b),
+                                            float(gn_mod.eps), 1, C.ptr(stats), C.stream()))
         return C.split(dst[0], Cn, dst[1])
 
     def _cost_volume(self, cv, lvl, ctx_t, j, B, H, W):

@@ -110,7 +110,7 @@ class CapturedForward:
             engine._done, engine._live = None, []     # nothing recorded outside the capture may be waited on inside it
             self.graph = torch.cuda.CUDAGraph()
             before = int(_lib.hesic_launch_count(0))
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.outputs = run(*self.inputs)
                 self.log2_sums = engine.log2_sums
             self.n_launches = int(_lib.hesic_launch_count(0)) - before

@@ -193,6 +193,14 @@ int hesic_upsample_bilinear(const hesic_tensor *x, const hesic_tensor *y, int sc
  * Formats: NCHW fp32 -> NCHW fp32, or NHWC fp32 -> NHWC_SPLIT / NHWC fp32 (channels per group a multiple of 4). */
 int hesic_group_norm(const hesic_tensor *x, const hesic_tensor *y, int groups, const float *weight, const float *bias,
                      float eps, int relu, void *stream);
+/* conv -> nn.GroupNorm(+ReLU) (mynet6_plus.py:224-290) without a separate statistics pass: hesic_conv_forward_gn writes the
+ * convolution's NHWC fp32 output AND the per-(image, group) partial sums stats[B][groups][8][2] (fp64: sum, sum of squares;
+ * accumulated by the tensor-core epilogue where the tile geometry allows, else by the statistics kernel);
+ * hesic_group_norm_apply normalises with them (x NHWC fp32 -> y NHWC fp32 or SPLIT, channel slices allowed). */
+int hesic_conv_forward_gn(hesic_conv *conv, const hesic_tensor *x, const hesic_tensor *y, int path, double *stats, int groups,
+                          void *stream);
+int hesic_group_norm_apply(const hesic_tensor *x, const hesic_tensor *y, int groups, const float *weight, const float *bias,
+                           float eps, int relu, const double *stats, void *stream);
 /* nn.functional.softmax(x, dim=-3): over the disparity channels of a cost volume (mynet6_plus.py:311).
  * NCHW fp32, or NHWC fp32 with C <= 64. */
 int hesic_softmax_channels(const hesic_tensor *x, const hesic_tensor *y, void *stream);

@@ -32,3 +32,17 @@ for tag, modname in (("hsic_newnet1", "newnet1"), ("hsic_joint", "newnet1_joint"
     dec = net.decompress(x1, x2, h, "codec_" + tag, output_path=out)
     assert all(torch.equal(dec[k], enc[k]) for k in ("y1_hat", "y2_hat", "z1_hat", "z2_hat"))
     print(tag, "bpp_real", enc["bpp_real"], {e: os.path.getsize(os.path.join(out, f"codec_{tag}.{e}")) for e in ("npz", "bin")})
+
+# DSIC (mynet6_plus.py:799-1350): same tables, coder and file layout; one 64x256 pair
+import mynet6_plus  # noqa: E402
+
+net = mynet6_plus.DSIC(128, 192, 21, 32, 5).eval()
+net.load_state_dict(synth.synth_state_dict(net, seed=0))
+net = net.to("cuda:0")
+net.entropy_bottleneck1.update(force=True)
+net.entropy_bottleneck2.update(force=True)
+x1, x2, _ = (t.to("cuda:0") for t in synth.stereo_pairs(1, 64, 256, seed=1234))
+enc = net.compress(x1, x2, "codec_dsic", output_path=out)
+dec = net.decompress("cuda:0", "codec_dsic", output_path=out)
+assert all(torch.equal(dec[k], enc[k]) for k in ("y1_hat", "y2_hat", "z1_hat", "z2_hat"))
+print("dsic bpp_real", enc["bpp_real"], {e: os.path.getsize(os.path.join(out, f"codec_dsic.{e}")) for e in ("npz", "bin")})

@@ -165,3 +165,24 @@ def test_codec_files_match_the_committed_golden(tag, modname, tmp_path):
     dec = net.decompress(x1, x2, h, "codec_" + tag, output_path=gdir)
     for k in ("y1_hat", "y2_hat", "z1_hat", "z2_hat"):
         assert torch.equal(dec[k], enc[k]), k
+
+
+def test_dsic_codec_files_match_the_committed_golden(tmp_path):
+    """Same drift guard for DSIC.compress / decompress (mynet6_plus.py:799-1350)."""
+    import mynet6_plus
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = {e: os.path.join(gdir, f"codec_dsic.{e}") for e in ("npz", "bin")}
+    if not all(os.path.exists(p) for p in gold.values()):
+        pytest.skip("golden codec files not generated yet (tests/golden/make_codec_golden.py)")
+    net = mynet6_plus.DSIC(128, 192, 21, 32, 5).eval()
+    net.load_state_dict(synth.synth_state_dict(net, seed=0))
+    net = net.to(DEV)
+    net.entropy_bottleneck1.update(force=True)
+    net.entropy_bottleneck2.update(force=True)
+    x1, x2, _ = (t.to(DEV) for t in synth.stereo_pairs(1, 64, 256, seed=1234))
+    enc = net.compress(x1, x2, "codec_dsic", output_path=str(tmp_path))
+    for e in ("npz", "bin"):
+        assert open(tmp_path / f"codec_dsic.{e}", "rb").read() == open(gold[e], "rb").read(), e
+    dec = net.decompress("cuda:0", "codec_dsic", output_path=gdir)
+    for k in ("y1_hat", "y2_hat", "z1_hat", "z2_hat"):
+        assert torch.equal(dec[k], enc[k]), k

@@ -295,3 +295,41 @@ def test_conv3d_depth_major_banded_plan():
     xq = _from_split(xs).cpu().reshape(2, 32, 7, 16, 24).permute(0, 2, 1, 3, 4)
     assert_close(got, torch.nn.functional.conv3d(xq, w, b, padding=2), 1e-4, what="depth-major banded Conv3d")
     assert_close(got, ref, 1e-4, what="depth-major banded Conv3d vs fp32 input")
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W,groups", [(64, 128, 16, 24, 4), (64, 128, 8, 8, 4), (32, 224, 16, 16, 1), (64, 672, 16, 16, 21),
+                                                  (64, 128, 40, 56, 4)])
+def test_conv_with_fused_group_norm_statistics(Cin, Cout, H, W, groups):
+    """conv -> GroupNorm -> ReLU with the statistics accumulated by the conv epilogue (hesic_conv_forward_gn +
+    hesic_group_norm_apply) against torch; includes tiles that straddle images (statistics-kernel route), a one-group norm
+    over 224 channels, 21 groups of 32, and an image whose edge tiles are partly outside."""
+    from hesic_b200 import _capi as C
+    from hesic_b200 import functional as F
+    B = 3
+    x = _rand((B, Cin, H, W), 71)
+    w = _rand((Cout, Cin, 5, 5), 72, (2.0 / (Cin * 25)) ** 0.5)
+    b = _rand((Cout,), 73, 0.1)
+    gw, gb = 1 + _rand((Cout,), 74, 0.1), _rand((Cout,), 75, 0.1)
+    plan = F.ConvPlan(Cin, Cout, 5, 1, 2)
+    wd, bd = w.to(DEV), b.to(DEV)
+    plan.load(wd, bd)
+    xs = _to_split(x)
+    xq = _from_split(xs).cpu()
+    conv_ref = torch.nn.functional.conv2d(xq, w, b, padding=2)
+    ref = torch.relu(torch.nn.functional.group_norm(conv_ref, groups, gw, gb, 1e-5))
+    y = torch.empty((B, H, W, Cout), device=DEV)
+    stats = torch.full((B, groups, C.GN_SLOTS, 2), float("nan"), device=DEV, dtype=torch.float64)   # the call zeroes it
+    C.check(C.lib.hesic_conv_forward_gn(plan.h, C.ref(C.split(xs)), C.ref(C.nhwc(y)), C.PATH_TC, C.ptr(stats), groups, C.stream()))
+    C.check(C.lib.hesic_tc_status())
+    assert_close(y.permute(0, 3, 1, 2), conv_ref, 1e-4, what="conv output")
+    # the statistics are those of the tensor the kernel wrote (fp32 partial sums of 32 values, then fp64)
+    s = stats.sum(2).cpu()
+    cg = y.permute(0, 3, 1, 2).double().reshape(B, groups, -1).cpu()
+    scale = cg.abs().sum(-1)
+    assert ((s[..., 0] - cg.sum(-1)).abs() <= 2e-6 * scale).all(), "group sums"
+    assert ((s[..., 1] - cg.pow(2).sum(-1)).abs() <= 2e-6 * cg.pow(2).sum(-1)).all(), "group sums of squares"
+    out = torch.zeros((2, B, H, W, Cout + 16), device=DEV, dtype=torch.bfloat16)
+    gwd, gbd = gw.to(DEV), gb.to(DEV)
+    C.check(C.lib.hesic_group_norm_apply(C.ref(C.nhwc(y)), C.ref(C.split(out, Cout, 8)), groups, C.ptr(gwd), C.ptr(gbd), 1e-5, 1,
+                                         C.ptr(stats), C.stream()))
+    assert_close(_from_split(out, Cout, 8), ref, 1e-4, what="conv -> GroupNorm -> ReLU")
