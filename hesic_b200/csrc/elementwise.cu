@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(256) indexes_scale_kernel(const TView sc, cons
 // erfcf on 'cuda:0', SLEEF / libm on a CPU), and those differ in the last bit.  The table arithmetic therefore uses the
 // CORRECTLY ROUNDED fp32 erfc: evaluated in fp64 on the fp32 argument and rounded once (cdf_std_cumulative).  Every
 // other step is a single IEEE fp32 operation, so the rows are reproducible bit for bit by any implementation -- the
-// CPU oracle (oracle/hesic_oracle.py:codec_cdf_tables) does exactly that and tests/test_gpu_codec.py holds equality.
+// CPU checker of the test suite restates exactly that and tests/test_gpu_codec.py holds equality.
 constexpr int CDF_MAX_S = 129;   // rows of up to 129 samples (minmax <= 64) are built in registers / local memory;
                                  // longer ones in place in the output row (any minmax)
 

@@ -37,11 +37,10 @@
 struct hesic_en_conv {
   int Cin = 0, Cout = 0, N = 0;
   __nv_bfloat16 *w = nullptr;   // [9][2N][64]: rows [0,N) = (hi[ci 0..31] | 0), rows [N,2N) = (lo[ci] | hi[ci]) of tap t
-  __nv_bfloat16 *w_pair = nullptr;   // CTA-pair layout [2 ranks][9][N + N/2][64], see en_pack_w_pair_kernel
   float *bias = nullptr;        // [32]
   bool loaded = false;
-  int device = -1;              // device that owns w / w_pair / bias
-  CUtensorMap map_w, map_w_pair;
+  int device = -1;              // device that owns w / bias
+  CUtensorMap map_w;
 };
 
 namespace hesic {
@@ -97,12 +96,9 @@ __device__ __forceinline__ void add_chunk(float *v, const uint4 &h, const uint4 
   v[6] += bf_lo(h.w) + bf_lo(l.w); v[7] += bf_hi(h.w) + bf_hi(l.w);
 }
 
-// PAIR: two CTAs of one TPC (cluster 2x1x1, cta_group::2) take two pixel tiles and each supplies half of every weight
-// operand -- rank 0 holds, per tap, the N main rows [Wh | 0] + small rows 0..N/2, rank 1 the N small rows [Wl | Wh] + small
-// rows N/2..N, so the 2N-wide MMA reads N rows and the N-wide one N/2 rows from each CTA (B reads per tap 6 -> 3 KB;
-// protocol as in conv_tc_pair.cuh: loads complete on the leader's barriers, the leader issues and multicasts its commits,
-// the peer's epilogue releases accumulators by remote arrive).
-template <bool PAIR>
+// (A CTA-pair variant that shared the weight tiles between two SMs was built and measured in r01 -- 381-388 us per layer
+// against 340 us: only the weight reads shrink, 9 % of the shared-memory traffic, while two SMs become lock-stepped --
+// and removed in r02; profiles/r01_en_pair_layer_times.txt keeps the measurement.)
 __global__ void __launch_bounds__(NT, 1)
 en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r1,
@@ -120,14 +116,12 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   auto res_full_bar = [&](int g) { return bar_base + 208u + 8u * g; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
-  const uint32_t wt_rows = PAIR ? (uint32_t)(p.N + p.N / 2) : 2u * (uint32_t)p.N;   // rows of one resident tap tile
+  const uint32_t wt_rows = 2u * (uint32_t)p.N;   // rows of one resident tap tile
   const uint32_t wt_bytes = wt_rows * 128u;
-  // work units: a tile, or (PAIR) a pair of tiles 2u, 2u + 1 (the second may lie past the end: loads zero-fill, stores clip)
-  const int n_units = PAIR ? (p.n_tasks + 1) / 2 : p.n_tasks;
-  const int ufirst = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  auto tile_of = [&](int u) { return PAIR ? 2 * u + (int)rank : u; };
+  // work units = tiles, dealt round-robin to the persistent CTAs
+  const int n_units = p.n_tasks;
+  const int ufirst = (int)blockIdx.x, ustep = (int)gridDim.x;
+  auto tile_of = [&](int u) { return u; };
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&map_x); prefetch_map(&map_w);
@@ -135,23 +129,17 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (p.res1) prefetch_map(&map_r1);
     if (p.res2) prefetch_map(&map_r2);
     for (int s = 0; s < NSLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < NACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), PAIR ? 256 : 128); }
+    for (int b = 0; b < NACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
     mbar_init(w_full, 1);
     mbar_init(res_full_bar(0), 1); mbar_init(res_full_bar(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS_EN) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS_EN) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS_EN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if (PAIR) cluster_sync_all();
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
@@ -161,15 +149,8 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (PAIR) {
-        const uint32_t wf = mapa_cta(w_full, 0);
-        if (leader) mbar_expect_tx(w_full, 2u * 9u * wt_bytes);
-        for (int t = 0; t < 9; ++t)
-          tma_load_2d_pair(&map_w, w_base + (uint32_t)t * wt_bytes, wf, 0, (int)((rank * 9u + (uint32_t)t) * wt_rows));
-      } else {
-        mbar_expect_tx(w_full, 9u * wt_bytes);
-        for (int t = 0; t < 9; ++t) tma_load_2d(&map_w, w_base + (uint32_t)t * wt_bytes, w_full, 0, t * 2 * p.N);
-      }
+      mbar_expect_tx(w_full, 9u * wt_bytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d(&map_w, w_base + (uint32_t)t * wt_bytes, w_full, 0, t * 2 * p.N);
       int slot = 0;
       uint32_t phase = 0;
       for (int u = ufirst; u < n_units; u += ustep) {
@@ -179,30 +160,18 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int c = 0; c < 3; ++c) {
           mbar_wait(empty_bar(slot), phase ^ 1u, 1);
           const uint32_t dst = slot_base + (uint32_t)slot * SLOT_BYTES;
-          if (PAIR) {
-            if (leader) mbar_expect_tx(full_bar(slot), 2u * (uint32_t)SLOT_BYTES);
-            tma_load_4d_pair(&map_x, dst, mapa_cta(full_bar(slot), 0), 0, tx * TW + c - 1, ty * TH - 1, tb);
-          } else {
-            mbar_expect_tx(full_bar(slot), (uint32_t)SLOT_BYTES);
-            tma_load_4d(&map_x, dst, full_bar(slot), 0, tx * TW + c - 1, ty * TH - 1, tb);
-          }
+          mbar_expect_tx(full_bar(slot), (uint32_t)SLOT_BYTES);
+          tma_load_4d(&map_x, dst, full_bar(slot), 0, tx * TW + c - 1, ty * TH - 1, tb);
           if (++slot == NSLOTS) { slot = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && leader) {
-      const uint32_t idesc = PAIR ? instr_desc_pair(2 * p.N) : instr_desc(2 * p.N);
-      const uint32_t idesc_n = PAIR ? instr_desc_pair(p.N) : instr_desc(p.N);
-      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
-        if (PAIR) mma_ss_pair(d, a, b, id, acc);
-        else mma_ss(d, a, b, id, acc);
-      };
-      auto commit = [&](uint32_t bar) {
-        if (PAIR) tc_commit_pair(bar);
-        else tc_commit(bar);
-      };
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(2 * p.N), idesc_n = instr_desc(p.N);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) { mma_ss(d, a, b, id, acc); };
+      auto commit = [&](uint32_t bar) { tc_commit(bar); };
       mbar_wait(w_full, 0, 5);
       tc_fence_after();
       int slot = 0, lt = 0;
@@ -249,13 +218,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     float bias[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias[j] = j < p.Cout ? __ldg(p.bias + j) : 0.f;
-    uint32_t acc_empty_tgt[NACC];
-#pragma unroll
-    for (int b = 0; b < NACC; ++b) acc_empty_tgt[b] = PAIR ? mapa_cta(acc_empty(b), 0) : acc_empty(b);
-    auto release_acc = [&](int b) {
-      if (PAIR) mbar_arrive_remote(acc_empty_tgt[b]);    // the leader's MMA thread waits for both CTAs' epilogues (TMEM-only hand-over)
-      else mbar_arrive(acc_empty_tgt[b]);
-    };
+    auto release_acc = [&](int b) { mbar_arrive(acc_empty(b)); };
     for (int lt = grp, u = ufirst + grp * ustep; u < n_units; u += 2 * ustep, lt += 2) {
       const int task = tile_of(u);
       const int buf = lt & (NACC - 1);
@@ -371,33 +334,11 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   }
 
   tc_fence_before();
-  if (PAIR) cluster_sync_all();
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_EN) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_EN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_EN) : "memory");
   }
-}
-
-// CTA-pair weight layout [2 ranks][9 taps][N + N/2 rows][64]: rank 0 rows = N main rows (hi | 0) then small rows 0..N/2,
-// rank 1 rows = N small rows (lo | hi) then small rows N/2..N
-__global__ void en_pack_w_pair_kernel(const float *__restrict__ w, int Cin, int Cout, int N, __nv_bfloat16 *__restrict__ out) {
-  const int rows = N + N / 2;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * 9 * rows * 32) return;
-  const int ci = i & 31, r = (i >> 5) % rows, t = (i / (32 * rows)) % 9, rk = i / (32 * rows * 9);
-  int co;
-  bool main_row;
-  if (rk == 0) { main_row = r < N; co = main_row ? r : r - N; }
-  else { main_row = false; co = r < N ? r : N / 2 + (r - N); }
-  float v = 0.f;
-  if (ci < Cin && co < Cout) v = w[((size_t)co * Cin + ci) * 9 + t];
-  __nv_bfloat16 hi, lo;
-  split_bf16(v, hi, lo);
-  __nv_bfloat16 *o = out + (((size_t)rk * 9 + t) * rows + r) * 64;
-  if (main_row) { o[ci] = hi; o[32 + ci] = __float2bfloat16_rn(0.f); }
-  else { o[ci] = lo; o[32 + ci] = hi; }
 }
 
 // weight [Cout][Cin][3][3] fp32 -> [9][2N][64] bf16: rows [0,N) = (hi | 0), rows [N,2N) = (lo | hi), zero padded
@@ -474,7 +415,7 @@ extern "C" hesic_en_conv *hesic_en_conv_create(int Cin, int Cout) {
 
 extern "C" void hesic_en_conv_destroy(hesic_en_conv *c) {
   if (!c) return;
-  cudaFree(c->w); cudaFree(c->w_pair); cudaFree(c->bias);
+  cudaFree(c->w); cudaFree(c->bias);
   delete c;
 }
 
@@ -482,8 +423,8 @@ extern "C" int hesic_en_conv_load(hesic_en_conv *c, const float *weight, const f
   HESIC_REQUIRE(c && weight, "hesic_en_conv_load: null argument");
   cudaStream_t s = as_stream(stream);
   if (c->device >= 0 && c->device != current_device()) {     // the model moved to another device: re-pack there
-    cudaFree(c->w); cudaFree(c->w_pair); cudaFree(c->bias);
-    c->w = c->w_pair = nullptr; c->bias = nullptr; c->loaded = false;
+    cudaFree(c->w); cudaFree(c->bias);
+    c->w = nullptr; c->bias = nullptr; c->loaded = false;
   }
   c->device = current_device();
   if (!c->w) {
@@ -493,14 +434,7 @@ extern "C" int hesic_en_conv_load(hesic_en_conv *c, const float *weight, const f
     const uint32_t box[2] = {64, (uint32_t)(2 * c->N)};
     int r = tc::make_tensor_map(&c->map_w, c->w, 2, dims, strides, box);
     if (r != HESIC_OK) return r;
-    const int prow = c->N + c->N / 2;
-    HESIC_CUDA(cudaMalloc(&c->w_pair, (size_t)2 * 9 * prow * 64 * sizeof(__nv_bfloat16)));
-    const uint64_t pdims[2] = {64, (uint64_t)2 * 9 * prow};
-    const uint32_t pbox[2] = {64, (uint32_t)prow};
-    if ((r = tc::make_tensor_map(&c->map_w_pair, c->w_pair, 2, pdims, strides, pbox)) != HESIC_OK) return r;
   }
-  en::en_pack_w_pair_kernel<<<(2 * 9 * (c->N + c->N / 2) * 32 + 255) / 256, 256, 0, s>>>(weight, c->Cin, c->Cout, c->N, c->w_pair);
-  HESIC_LAUNCHED("en_pack_w_pair_kernel");
   en::en_pack_w_kernel<<<(9 * c->N * 32 + 255) / 256, 256, 0, s>>>(weight, c->Cin, c->Cout, c->N, c->w);
   HESIC_LAUNCHED("en_pack_w_kernel");
   HESIC_CUDA(cudaMemsetAsync(c->bias, 0, 32 * sizeof(float), s));
@@ -556,8 +490,7 @@ extern "C" int hesic_en_conv_forward(hesic_en_conv *c, const hesic_tensor *x, co
     int dev = 0;
     HESIC_CUDA(cudaGetDevice(&dev));
     HESIC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    HESIC_CUDA(cudaFuncSetAttribute(en_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    HESIC_CUDA(cudaFuncSetAttribute(en_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    HESIC_CUDA(cudaFuncSetAttribute(en_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
   EParams p;
   memset(&p, 0, sizeof(p));
@@ -585,29 +518,8 @@ extern "C" int hesic_en_conv_forward(hesic_en_conv *c, const hesic_tensor *x, co
   if (!planar && res1 && (r = tc::make_tensor_map(&mr1, res1->p0, 4, dims, strides, box_out)) != HESIC_OK) return r;
   if (!planar && res2 && (r = tc::make_tensor_map(&mr2, res2->p0, 4, dims, strides, box_out)) != HESIC_OK) return r;
   if (!planar && !res1 && res2) { mr1 = mr2; p.res1 = p.res2; p.res2 = nullptr; }
-  // CTA-pair variant: correct (same tests) but measured SLOWER here (plain layer 388 us vs 340 us, B = 16): this kernel keeps only
-  // two tiles in flight (6 halo slots), and lock-stepping two SMs adds the cross-CTA commit / arrive latency to every tile
-  // while saving just the weight-operand reads (9 % of the shared-memory traffic).  Opt-in for experiments.
-  static const bool pair_on = getenv("HESIC_EN_PAIR") != nullptr;
-  if (pair_on && num_sms >= 2 && p.n_tasks >= 2) {
-    const int n_units = (p.n_tasks + 1) / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)std::min(2 * n_units, num_sms & ~1));
-    cfg.blockDim = dim3(NT);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    HESIC_CUDA(cudaLaunchKernelEx(&cfg, en_conv_kernel<true>, mx, c->map_w_pair, my, mr1, mr2, p));
-    HESIC_LAUNCHED("en_conv_kernel<pair>");
-    return HESIC_OK;
-  }
   const int grid = std::min(p.n_tasks, num_sms);
-  en_conv_kernel<false><<<grid, NT, SMEM_BYTES, as_stream(stream)>>>(mx, c->map_w, my, mr1, mr2, p);
+  en_conv_kernel<<<grid, NT, SMEM_BYTES, as_stream(stream)>>>(mx, c->map_w, my, mr1, mr2, p);
   HESIC_LAUNCHED("en_conv_kernel");
   return HESIC_OK;
 }

@@ -68,7 +68,8 @@ def test_tensor_core_kernels_are_tcgen05_and_tma(sass, needle, exclude):
         assert _count(ins, "HMMA") == 0 and _count(ins, "HGMMA") == 0, f"{name}: legacy mma.sync / wgmma present"
     pair = funcs[_one(funcs, "conv_tc_pair_kernel")[0]]
     assert all(".2CTA" in i for i in pair if i.startswith("UTCHMMA")), "pair kernel must issue cta_group::2 MMAs only"
-    assert _count(pair, "UTMASTG") > 0 and _count(funcs[_one(funcs, "conv_tc_kernelE")[0]], "UTMASTG") > 0  # TMA-store epilogue
+    assert _count(pair, "UTMASTG") > 0 and _count(funcs[_one(funcs, "conv_tc_kernelILi8E")[0]], "UTMASTG") > 0  # TMA-store epilogue
+    assert _count(funcs[_one(funcs, "conv_tc_kernelILi16E")[0]], "UTMASTG") > 0                      # 16-warp epilogue (first analysis layer)
 
 
 def test_pair_kernel_hands_tiles_back_without_gpu_scope_fences(sass):
@@ -76,13 +77,13 @@ def test_pair_kernel_hands_tiles_back_without_gpu_scope_fences(sass):
     pair = funcs[_one(funcs, "conv_tc_pair_kernel")[0]]
     # exactly the two cluster-wide syncs at kernel start and end (barrier.cluster.arrive.release) remain
     assert _count(pair, "MEMBAR.ALL.GPU") == 2, _count(pair, "MEMBAR.ALL.GPU")
-    single = funcs[_one(funcs, "conv_tc_kernelE")[0]]
-    assert _count(single, "MEMBAR.ALL.GPU") == 0
-    for name in _one(funcs, "en_conv_kernelILb0"):          # the default (single-CTA) enhancement kernel
+    for name in _one(funcs, "conv_tc_kernelILi"):           # the single-CTA kernel, 8- and 16-warp epilogues
+        assert _count(funcs[name], "MEMBAR.ALL.GPU") == 0
+    for name in _one(funcs, "en_conv_kernel"):              # the enhancement kernel
         assert _count(funcs[name], "MEMBAR.ALL.GPU") == 0
 
 
-@pytest.mark.parametrize("needle", ["conv_tc_kernelE", "conv_tc_pair_kernel"])
+@pytest.mark.parametrize("needle", ["conv_tc_kernelILi8E", "conv_tc_pair_kernel"])
 def test_gdn_scale_pass_is_one_block_per_chunk(sass, needle):
     """Between the first and the last MUFU.SQRT of the kernel (the IGDN side of epilogue pass 2: 2 chunks x 32
     columns) there are only a handful of branches; one per four elements would be >= 16."""
@@ -101,7 +102,7 @@ def test_gdn_scale_pass_is_one_block_per_chunk(sass, needle):
 
 
 def test_register_budget_of_the_conv_kernels():
-    """320-thread CTAs are capped at 168 registers; spills in the epilogue were a measured cost (d9140f8).  Checked
+    """320-thread CTAs are capped at 168 registers (the 576-thread one at 96); spills in the epilogue were a measured cost (d9140f8).  Checked
     from the resource usage cuobjdump reports for the built cubin."""
     if not os.path.exists(CUOBJDUMP):
         pytest.skip("cuobjdump not available")
@@ -114,4 +115,4 @@ def test_register_budget_of_the_conv_kernels():
         seen += 1
         assert reg <= 168, (name, reg)
         assert stack <= 64, f"{name}: {stack} bytes of stack (spills) -- the epilogue must stay in registers"
-    assert seen == 2
+    assert seen == 3      # conv_tc_kernel<8>, conv_tc_kernel<16>, conv_tc_pair_kernel
