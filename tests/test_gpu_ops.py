@@ -493,3 +493,37 @@ def test_sum_squared_error_and_channels_last_max():
     out = torch.empty((2, 960), device=DEV)
     C.check(C.lib.hesic_spatial_max(C.ref(C.nhwc(xn)), C.ptr(out), C.stream()))
     assert torch.equal(out.cpu(), x.amax(dim=(2, 3)))
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96, 3), (1, 33, 30, 3), (2, 16, 20, 1), (1, 8, 12, 4)])
+def test_images_from_uint8_is_totensor(shape):
+    """uint8 [B,H,W,C] -> fp32 [B,C,H,W] / 255 on the device: bit-identical to what transforms.ToTensor() computes on
+    the host (compressai/datasets/utils.py:101-102: `img.permute(2, 0, 1).float().div(255)`), fast path and generic path."""
+    from hesic_b200 import functional as F
+    g = torch.Generator().manual_seed(7)
+    u8 = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8)
+    ref = u8.permute(0, 3, 1, 2).float().div(255)
+    got = F.images_from_uint8(u8.to(DEV))
+    assert got.shape == ref.shape and torch.equal(got.cpu(), ref)
+    with pytest.raises(TypeError):
+        F.images_from_uint8(u8.to(DEV).float())
+
+
+def test_hostfeed_uint8_transport_equals_fp32_transport():
+    """HostFeed with [B,H,W,3] uint8 host images hands fn the same fp32 tensors as shipping the ToTensor()'d images."""
+    from hesic_b200.hostfeed import HostFeed
+    g = torch.Generator().manual_seed(3)
+    batches8, batches32 = [], []
+    for _ in range(3):
+        a, b = (torch.randint(0, 256, (2, 64, 64, 3), generator=g, dtype=torch.uint8) for _ in range(2))
+        h = torch.eye(3).repeat(2, 1, 1) + 0.01 * torch.randn(2, 3, 3, generator=g)
+        batches8.append((a.pin_memory(), b.pin_memory(), h.pin_memory()))
+        batches32.append(tuple(t.permute(0, 3, 1, 2).float().div(255).contiguous().pin_memory() for t in (a, b)) + (h.pin_memory(),))
+    seen8, seen32 = [], []
+    HostFeed(torch.device(DEV), batches8[0]).run(batches8, lambda x1, x2, hh: seen8.append((x1.clone(), x2.clone(), hh.clone())))
+    HostFeed(torch.device(DEV), batches32[0]).run(batches32, lambda x1, x2, hh: seen32.append((x1.clone(), x2.clone(), hh.clone())))
+    torch.cuda.synchronize()
+    assert len(seen8) == len(seen32) == 3
+    for p8, p32 in zip(seen8, seen32):
+        for u, v in zip(p8, p32):
+            assert u.dtype == torch.float32 and torch.equal(u, v)
