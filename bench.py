@@ -293,7 +293,8 @@ def run_ours(args):
     # parity of the timed computation itself: pair 0 of this rank's last timed batch against the CPU oracle
     parity = None
     if rank == 0:
-        out = step(*sets[last_set])
+        # rank 0 alone: the forward only -- NO collective here (the other ranks have left the timed loops)
+        out = call(net, model, *sets[last_set])
         torch.cuda.synchronize()
         one = {k: v[:1].cpu() for k, v in out.items() if k != "likelihoods"}
         one["likelihoods"] = {k: v[:1].cpu() for k, v in out["likelihoods"].items()}
