@@ -311,6 +311,13 @@ def run_ours(args):
                                       for k in ("x1_hat", "x2_hat"))}
         if "y1_hat" in one and "y1_hat" in ref:
             parity["flips"] = max(float((one[k] != ref[k]).double().mean()) for k in ("y1_hat", "y2_hat"))
+        # a hyper-latent (z) symbol that sits within ~1e-5 of a rounding boundary may round the other way under a different
+        # fp32 summation order; it moves the mixture parameters of a 4x4 latent block and with them a few hundred bits of
+        # this ONE pair (the 16-pair batch agrees to 1e-7, tests/test_gpu_fullsize.py) -- visible as a likelihood that jumps
+        zrel = max(float(((one["likelihoods"][k].double() - ref["likelihoods"][k].double()).abs()
+                          / ref["likelihoods"][k].double().clamp(min=1e-9)).max()) for k in ("z1", "z2"))
+        parity["z_likelihood_max_rel"] = zrel
+        parity["z_symbol_flipped"] = bool(zrel > 1e-2)
         parity["batch_metrics_all_ranks"] = m_dev
 
     if rank != 0:
