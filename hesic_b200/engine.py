@@ -63,8 +63,10 @@ class EngineBase:
         return main
 
     def _end(self, main):
-        if self._done is None:
+        # an event belongs to the device it is first recorded on: a model that moved gets a new one
+        if self._done is None or getattr(self, "_done_dev", None) != main.device:
             self._done = torch.cuda.Event()
+            self._done_dev = main.device
         self._done.record(main)
 
     def _keep(self, t):
