@@ -758,6 +758,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }  // namespace hesic
 #include "conv_head.cuh"
 #include "conv_tc_pair.cuh"
+#include "conv_tc_first.cuh"
 namespace hesic {
 namespace tc {
 
@@ -783,7 +784,8 @@ static EncodeTiledFn encode_fn() {
 
 // rank-n tensor map (bf16 unless stated), 128B swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..n-1.
 static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
-                    const uint32_t *box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+                    const uint32_t *box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return HESIC_E_CUDA; }
   cuuint64_t gd[5], gs[4];
@@ -791,7 +793,7 @@ static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
   CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,..] box=[%u,%u,%u,..]", (int)r, rank,
@@ -1174,6 +1176,52 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     const int pgrid = std::min(2 * q.n_tasks, num_sms & ~1);
     conv_tc_pair_kernel<<<pgrid, NUM_THREADS, q.stages * PAIR_STAGE_BYTES + pfixed, s>>>(ma_hi, ma_lo, m[0], m[1], mw64, mg_hi, mg_lo, my0, my1, q);
     HESIC_LAUNCHED("conv_tc_pair_kernel");
+    return HESIC_OK;
+  }
+  // first analysis layer (conv_tc_first.cuh): two tiles interleaved in the epilogue, one activation box per tile
+  static const bool first_on = getenv("HESIC_TC_NO_FIRST") == nullptr;
+  if (first_on && c->tc_kind == HESIC_TC_ROW2 && p.gdn == 1 && p.w_resident && y->fmt == HESIC_FMT_NHWC_SPLIT && c->Cout == 128 &&
+      p.tma_store && y->W >= FIRST_BW && y->H >= FIRST_BH) {
+    static PerDeviceOnce first_once;
+    if (first_once.first())
+      HESIC_CUDA(cudaFuncSetAttribute(conv_tc_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    Params q = p;
+    q.bw = FIRST_BW; q.bh = FIRST_BH; q.bb = 1;
+    q.tiles_x = (y->W + FIRST_BW - 1) / FIRST_BW; q.tiles_y = (y->H + FIRST_BH - 1) / FIRST_BH; q.tiles_b = y->B;
+    q.n_tasks = q.tiles_x * q.tiles_y * q.tiles_b;
+    static const int first_dbg = getenv("HESIC_TC_FIRST_DBG") ? atoi(getenv("HESIC_TC_FIRST_DBG")) : 0;
+    q.pl_os = first_dbg;      // diagnostic bits (unused field on this path): 1 = no TMA stores
+    CUtensorMap fa_hi, fa_lo, fw_hi, fw_lo, fy0, fy1;
+    const uint64_t e = 2;
+    {
+      // K = 16 slices (32 B) of the row-pair interleaved ROWPAD input, 18 row pairs x 8 pixels
+      const uint64_t pairB = (uint64_t)(x->W + HESIC_ROWPAD_X) * 8 * e, Hp2 = ((uint64_t)x->H + HESIC_ROWPAD_Y) / 2;
+      uint64_t dims[5] = {(uint64_t)BK, (uint64_t)x->W / 2, 1, Hp2, (uint64_t)x->B};
+      uint64_t strides[4] = {16 * e, pairB, pairB, Hp2 * pairB};
+      uint32_t box[5] = {16u, (uint32_t)FIRST_BW, 1u, (uint32_t)FIRST_BH + 2u, 1u};
+      int r = make_map(&fa_hi, x->p0, 5, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B);
+      if (r == HESIC_OK) r = make_map(&fa_lo, x->p1, 5, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B);
+      if (r != HESIC_OK) return r;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)c->tc_k, (uint64_t)c->CoutPad, (uint64_t)c->tc_taps};
+      uint64_t strides[2] = {(uint64_t)c->tc_k * 2, (uint64_t)c->tc_k * c->CoutPad * 2};
+      uint32_t box[3] = {16u, 128u, 1u};
+      int r = make_map(&fw_hi, c->w_hi, 3, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B);
+      if (r == HESIC_OK) r = make_map(&fw_lo, c->w_lo, 3, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B);
+      if (r != HESIC_OK) return r;
+    }
+    {
+      uint64_t dims[5] = {(uint64_t)y->C, (uint64_t)y->W, 1, (uint64_t)y->H, (uint64_t)y->B};
+      uint64_t strides[4] = {(uint64_t)yCs * e, (uint64_t)y->W * yCs * e, (uint64_t)y->W * yCs * e, (uint64_t)y->H * y->W * yCs * e};
+      uint32_t box[5] = {(uint32_t)FIRST_RC, (uint32_t)FIRST_BW, 1u, 4u, 1u};
+      int r = make_map(&fy0, y->p0, 5, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B);
+      if (r == HESIC_OK) r = make_map(&fy1, y->p1, 5, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B);
+      if (r != HESIC_OK) return r;
+    }
+    const int fgrid = std::min(q.n_tasks, num_sms);
+    conv_tc_first_kernel<<<fgrid, FIRST_THREADS, FIRST_SMEM_BYTES, s>>>(fa_hi, fa_lo, fw_hi, fw_lo, m[2], m[3], fy0, fy1, q);
+    HESIC_LAUNCHED("conv_tc_first_kernel");
     return HESIC_OK;
   }
   const int grid = std::min(p.n_tasks, num_sms);
