@@ -76,7 +76,7 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const int txy = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // weights: resident for the whole kernel
       mbar_expect_tx(w_full, (uint32_t)p.kchunks * 2u * w_bytes);
       for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -100,7 +100,7 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(w_full, 0, 5);
       tc_fence_after();
       const uint32_t idesc = instr_desc(p.NPAD);

@@ -247,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1u; } };
@@ -292,7 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1u; } };
@@ -378,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int txy = p.tiles_x * p.tiles_y;
-    const bool is_issuer = (int)threadIdx.x == 64 + 256 * half;
+    const bool is_issuer = warp == 2 + 8 * half && elect_one();   // one lane of the half's first warp
     const uint32_t stg_set = stg_base + (uint32_t)half * (uint32_t)STAGING_BYTES;
     const uint32_t row_off = stg_set + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
     const bool igdn = p.gdn == 2;
@@ -498,7 +498,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int xi = row & (p.bw - 1), yi = (row >> p.lbw) & (p.bh - 1), bi = row >> (p.lbw + p.lbh);
     const int txy = p.tiles_x * p.tiles_y;
     const int nchunks = p.BN / 32, npairs = (nchunks + 1) / 2;
-    const bool is_issuer = threadIdx.x == 64;
+    const bool is_issuer = warp == 2 && elect_one();
     const uint32_t row_off0 = stg_base + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
     uint32_t pair_ctr = 0;   // store pairs issued so far (selects the staging set)
     // activation as max(v, slope * v): slope 1 = none, 0 = ReLU, 0.01 = LeakyReLU
@@ -745,7 +745,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   }
 
-  if (EPI_WARPS == 8 && p.tma_store && threadIdx.x == 64) bulk_wait_all();   // staged tiles fully written before the CTA retires
+  if (EPI_WARPS == 8 && p.tma_store && warp == 2) bulk_wait_all();   // staged tiles fully written before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -1212,9 +1212,15 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
       if (r != HESIC_OK) return r;
     }
     {
-      uint64_t dims[5] = {(uint64_t)y->C, (uint64_t)y->W, 1, (uint64_t)y->H, (uint64_t)y->B};
-      uint64_t strides[4] = {(uint64_t)yCs * e, (uint64_t)y->W * yCs * e, (uint64_t)y->W * yCs * e, (uint64_t)y->H * y->W * yCs * e};
-      uint32_t box[5] = {(uint32_t)FIRST_RC, (uint32_t)FIRST_BW, 1u, 4u, 1u};
+      // hi and lo planes of one allocation (lo above hi, 16-byte aligned distance): the unused third dimension of the map
+      // becomes the plane and one store writes both
+      const ptrdiff_t plane_d = (const char *)y->p1 - (const char *)y->p0;
+      const bool planes = plane_d > 0 && plane_d % 16 == 0 && plane_d < ((ptrdiff_t)1 << 40);
+      q.pl_phases = planes ? 2 : 1;
+      uint64_t dims[5] = {(uint64_t)y->C, (uint64_t)y->W, planes ? 2u : 1u, (uint64_t)y->H, (uint64_t)y->B};
+      uint64_t strides[4] = {(uint64_t)yCs * e, planes ? (uint64_t)plane_d : (uint64_t)y->W * yCs * e, (uint64_t)y->W * yCs * e,
+                             (uint64_t)y->H * y->W * yCs * e};
+      uint32_t box[5] = {16u, (uint32_t)FIRST_BW, planes ? 2u : 1u, 4u, 1u};
       int r = make_map(&fy0, y->p0, 5, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B);
       if (r == HESIC_OK) r = make_map(&fy1, y->p1, 5, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B);
       if (r != HESIC_OK) return r;

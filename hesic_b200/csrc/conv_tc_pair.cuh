@@ -78,7 +78,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       // the gamma tiles of a GDN step: each CTA loads its 64-row half of gamma_hi and gamma_lo (16 KB) for K chunk c
@@ -124,7 +124,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    if (leader && elect_one()) {
       int stage = 0, lt = 0;
       uint32_t phase = 0;
       const uint32_t idesc256 = instr_desc_pair(256), idesc128 = instr_desc_pair(128);
@@ -189,7 +189,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int xi = row & (p.bw - 1), yi = (row >> p.lbw) & (p.bh - 1), bi = row >> (p.lbw + p.lbh);
-    const bool is_issuer = threadIdx.x == 64;
+    const bool is_issuer = warp == 2 && elect_one();
     const uint32_t row_off = stg_base + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
     const float act_slope = p.act == HESIC_ACT_RELU ? 0.f : (p.act == HESIC_ACT_LEAKY_RELU ? 0.01f : 1.f);
     const uint32_t acc_empty_leader0 = mapa_cta(acc_empty(0), 0), acc_empty_leader1 = mapa_cta(acc_empty(1), 0);

@@ -148,7 +148,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(w_full, 9u * wt_bytes);
       for (int t = 0; t < 9; ++t) tma_load_2d(&map_w, w_base + (uint32_t)t * wt_bytes, w_full, 0, t * 2 * p.N);
       int slot = 0;
@@ -168,7 +168,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = instr_desc(2 * p.N), idesc_n = instr_desc(p.N);
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) { mma_ss(d, a, b, id, acc); };
       auto commit = [&](uint32_t bar) { tc_commit(bar); };
@@ -210,7 +210,7 @@ en_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int xi = row & (TW - 1), yi = row >> 4;
-    const bool is_issuer = (threadIdx.x & 127) == 64;
+    const bool is_issuer = (warp & 3) == 2 && elect_one();
     const uint32_t my_stg = stg + (uint32_t)grp * STG_BYTES;
     const uint32_t row_off = my_stg + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
     const uint32_t res_full = res_full_bar(grp);

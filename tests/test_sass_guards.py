@@ -115,4 +115,30 @@ def test_register_budget_of_the_conv_kernels():
         seen += 1
         assert reg <= 168, (name, reg)
         assert stack <= 64, f"{name}: {stack} bytes of stack (spills) -- the epilogue must stay in registers"
-    assert seen == 3      # conv_tc_kernel<8>, conv_tc_kernel<16>, conv_tc_pair_kernel
+    assert seen == 4      # conv_tc_kernel<8>, conv_tc_kernel<16>, conv_tc_pair_kernel, conv_tc_first_kernel
+
+
+def test_single_thread_issue_regions_have_no_serialisation_loops(sass):
+    """Producer / MMA / store-issuing threads are chosen with elect.sync, not `lane == 0`: the compiler then knows that one
+    thread runs the region and feeds UTCHMMA / UTMALDG / UTMASTG from uniform registers directly.  With `lane == 0` every such
+    instruction sat in an ELECT ... BRA.U.ANY loop over the active lanes (r02: 499 of them in the library; the MMA thread of the
+    first-layer kernel needed ~10 instructions and a branch per MMA and was the kernel's bound)."""
+    _, funcs = sass
+    ins = funcs[_one(funcs, "conv_tc_first_kernel")[0]]
+    assert _count(ins, "BRA.U.ANY") == 0
+    # the other kernels: only the (few per tile) TMA stores / residual loads issued from inside the epilogue keep such a loop
+    for needle in ("conv_tc_pair_kernel", "conv_tc_kernelILi8E", "conv_tc_kernelILi16E", "en_conv_kernel"):
+        ins = funcs[_one(funcs, needle)[0]]
+        loops = [i for i, x in enumerate(ins) if x.startswith("BRA.U.ANY") or " BRA.U.ANY" in x]
+        assert len(loops) <= 12, (needle, len(loops))      # r02 before the change: 60-190 per kernel
+        for i in loops:
+            assert not any(x.startswith("UTCHMMA") for x in ins[max(0, i - 6):i]), needle
+
+
+def test_first_layer_kernel_is_tcgen05_with_resident_operands(sass):
+    _, funcs = sass
+    ins = funcs[_one(funcs, "conv_tc_first_kernel")[0]]
+    assert _count(ins, "UTCHMMA") >= 51          # 27 conv + 24 GDN MMAs per tile, unrolled
+    assert _count(ins, "UTMALDG") > 0 and _count(ins, "UTMASTG") > 0 and _count(ins, "LDTM") > 0 and _count(ins, "STTM") > 0
+    assert _count(ins, "BAR.SYNC") <= 2          # no block-level barrier in the tile loop (start and end only)
+    assert _count(ins, "MEMBAR.ALL.GPU") == 0
