@@ -20,6 +20,9 @@ struct hesic_conv {
   // SIMT operand: fp32 [kh*kw*Cin][Cout] (tap-major rows, Cout contiguous)
   float *w_simt = nullptr;
   float *bias = nullptr;   // [Cout] (zeros when the layer has no bias)
+  // host copy of w_simt for the few-channel stencil layers (Cin <= 8, Cout <= 4, k5): conv_small_kernel takes its weights
+  // as kernel parameters
+  float *w_host = nullptr;
   // tcgen05 operands: bf16 hi / lo planes [kh*kw][CoutPad][Cin] (K-major per tap)
   __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
   int CoutPad = 0;

@@ -361,6 +361,7 @@ extern "C" void hesic_conv_destroy(hesic_conv *c) {
   if (!c) return;
   conv_release(c);
   free(c->tc_maps);
+  free(c->w_host);
   delete c;
 }
 
@@ -422,6 +423,13 @@ extern "C" int hesic_conv_load(hesic_conv *c, const float *weight, const float *
   } else {
     fill_zero_kernel<<<(c->Cout + 255) / 256, 256, 0, s>>>(c->bias, c->Cout);
     HESIC_LAUNCHED("fill_zero_kernel");
+  }
+  if (c->Cin <= 8 && c->Cout <= 4 && c->kh == 5 && c->kw == 5) {
+    // once per load (host copy + sync, like the mask above): the stencil kernel's parameter-space weights
+    const size_t n = taps * c->Cin * c->Cout;
+    if (!c->w_host) c->w_host = (float *)malloc(n * sizeof(float));
+    HESIC_CUDA(cudaMemcpyAsync(c->w_host, c->w_simt, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HESIC_CUDA(cudaStreamSynchronize(s));
   }
   c->loaded = true;
   return HESIC_OK;

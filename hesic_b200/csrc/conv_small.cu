@@ -10,11 +10,13 @@
 //
 // Block = 64 x 16 output pixels, 128 threads, each thread 2 rows x 4 consecutive pixels x Cout
 // accumulators.  The zero-padded input tile (Cin x 20 x 68 fp32) and the weights ([ci][ky][kx][4], the
-// kernel flipped for the transposed form) sit in shared memory; inner loop per (ci, ky): four 16-byte
-// input loads + five 16-byte weight loads feed 120 FMAs.  torch.cat on the reference side is a second
+// kernel flipped for the transposed form) sit in shared memory / the kernel parameters; inner loop per (ci, ky): four 16-byte
+// input loads feed 120 FMAs whose weight operand is a uniform register.  torch.cat on the reference side is a second
 // input pointer (channels [Ca, Cin) come from xb), so the concatenation is never materialised.  The
 // output is NCHW fp32 or, when the consumer is the 3->128 tensor-core layer, directly its ROWPAD8
 // bf16 (hi, lo) input format.
+#include <string.h>
+
 #include "conv.h"
 
 namespace hesic {
@@ -34,22 +36,22 @@ struct Args {
   int act;
   int out_fmt, out_Cs;    // NCHW fp32 (channel slice of out_Cs) or ROWPAD split (out_Cs = 8 or 4 slots)
   void *y0, *y1;
+  // Weights as kernel parameters, [ci][ky][kx][4] with the kernel flipped for the transposed form: the FMA's weight operand
+  // is a uniform register filled from the constant bank (LDCU), no shared-memory weight loads.  r03 measurements of the
+  // alternatives (all bit-identical): weights in shared memory 142-155 us; this form 135-140 us; packed fma.rn.f32x2 with
+  // pixel pairs 155-159 us (one MOV per packed FMA to build the unaligned pairs); packed FMAs over row pairs interleaved in
+  // shared memory, no MOVs, 182-185 us.  A three-source FFMA issues every second cycle per scheduler: the layer runs at
+  // ~70 % of that rate.
+  float wk[8 * 25 * 4];
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(NT) conv_small_kernel(const Args a) {
+__global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(16) float sm[];
-  float *wsm = sm;                       // [CIN*25][4]
-  float *in = sm + CIN * 25 * 4;         // [CIN][ROWS][PITCH]
+  float *in = sm;                        // [CIN][ROWS][PITCH]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
 
-  for (int i = tid; i < CIN * 25 * 4; i += NT) {
-    const int co = i & 3, t = i >> 2;
-    const int kx = t % 5, ky = (t / 5) % 5, ci = t / 25;
-    const int tap = a.transposed ? (4 - ky) * 5 + (4 - kx) : ky * 5 + kx;
-    wsm[i] = co < COUT ? __ldg(a.w + (size_t)(tap * CIN + ci) * COUT + co) : 0.f;
-  }
   // input tile: one warp per (channel, row), lanes along x.  The tile starts at x0 - 2 (even), so with an even
   // image width every float2 is 8-byte aligned and entirely inside or outside the image.
   {
@@ -104,8 +106,8 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const Args a) {
       }
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
-        const float4 wq = *reinterpret_cast<const float4 *>(wsm + ((ci * 5 + ky) * 5 + kx) * 4);
-        const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
+        const float *wq = a.wk + ((ci * 5 + ky) * 5 + kx) * 4;
+        const float wv[4] = {wq[0], wq[1], wq[2], wq[3]};
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const Args a) {
 
 template <int CIN, int COUT>
 static int launch(const Args &a, cudaStream_t s) {
-  const int smem = (CIN * 25 * 4 + CIN * ROWS * PITCH) * (int)sizeof(float);
+  const int smem = CIN * ROWS * PITCH * (int)sizeof(float);
   static PerDeviceOnce once;
   if (once.first())
     HESIC_CUDA(cudaFuncSetAttribute(conv_small_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -213,6 +215,14 @@ int conv_forward_small(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor
   a.xb = xb ? (const float *)xb->p0 : nullptr; a.CsB = xb ? (xb->Cs > 0 ? xb->Cs : xb->C) : 0;
   a.B = y->B; a.H = y->H; a.W = y->W;
   a.w = c->w_simt; a.bias = c->bias; a.transposed = c->transposed;
+  if (!c->w_host) { set_error("conv stencil: weights not loaded"); return HESIC_E_INVALID; }
+  memset(a.wk, 0, sizeof(a.wk));
+  for (int ci = 0; ci < c->Cin; ++ci)
+    for (int ky = 0; ky < 5; ++ky)
+      for (int kx = 0; kx < 5; ++kx) {
+        const int tap = c->transposed ? (4 - ky) * 5 + (4 - kx) : ky * 5 + kx;
+        for (int co = 0; co < c->Cout; ++co) a.wk[((ci * 5 + ky) * 5 + kx) * 4 + co] = c->w_host[(size_t)(tap * c->Cin + ci) * c->Cout + co];
+      }
   a.gdn = c->has_gdn ? (c->gdn_inverse ? 2 : 1) : 0;
   a.beta = c->gdn_beta; a.gamma = c->gdn_w_simt;
   if (c->has_gdn && act != HESIC_ACT_NONE) { set_error("activation after fused GDN is not supported"); return HESIC_E_UNSUPPORTED; }

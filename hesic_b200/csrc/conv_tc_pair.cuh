@@ -23,9 +23,13 @@ constexpr int PAIR_STAGE_BYTES = 2 * A_TILE_BYTES + PAIR_B1_BYTES + PAIR_B2_BYTE
 
 // pair task -> (pixel-tile pair, phase, N tile); CTA `rank` of the pair takes pixel tile 2 * mtp + rank
 __device__ __forceinline__ TaskCoord decode_pair_task(const Params &p, int task, int rank) {
+  // N-tile major: the last N tile of a layer may be narrower (Cout = 192: 128 + 64 columns), and with the N tile as the
+  // fastest index an even grid stride gave every CTA pair the same N tile in every round -- half of the pairs two wide tasks,
+  // the other half two narrow ones (conv 128 -> 192 at 32 x 32: 128 tasks on 74 pairs).  Wide tasks first, narrow ones on top.
   TaskCoord t;
-  t.nt = task % p.n_tiles;
-  const int r = task / p.n_tiles;
+  const int per_nt = p.n_tasks / p.n_tiles;
+  t.nt = task / per_nt;
+  const int r = task - t.nt * per_nt;
   const int mtp = r / p.n_phases;
   t.ph = (r + mtp) % p.n_phases;
   t.mt = 2 * mtp + rank;
