@@ -64,6 +64,8 @@ _sig = {
     "hesic_tc_status": ([], c_int),
     "hesic_gdn": ([_TP, _TP, c_void_p, c_void_p, c_int, c_float, c_void_p], c_int),
     "hesic_warp_perspective": ([_TP, c_void_p, _TP, _TP, c_int, c_void_p], c_int),
+    "hesic_perspective_transform": ([c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
+    "hesic_max_pool2x2": ([_TP, _TP, c_void_p], c_int),
     "hesic_eb_pack": ([POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_int, c_void_p, c_void_p], c_int),
     "hesic_entropy_bottleneck": ([_TP, c_void_p, c_float, _TP, _TP, c_void_p, c_void_p], c_int),
     "hesic_gaussian_conditional": ([_TP, _TP, _TP, c_void_p, c_int, c_int, c_float, c_float, _TP, _TP, _TP, c_void_p, c_void_p], c_int),

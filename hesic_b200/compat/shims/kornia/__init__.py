@@ -2,7 +2,7 @@
 package is not installed.  ``warp_perspective`` runs the hesic_b200 bilinear-gather kernel with
 kornia's normalise -> invert -> grid_sample arithmetic (align_corners=True convention, see
 SURVEY.md section 8c); ``get_perspective_transform`` is the 4-point DLT solve used by the caller
-(test3real.py:179), in plain torch (host-side front-end, outside the forward hot path)."""
+(test3real.py:179): the library's kernel for CUDA tensors, plain torch otherwise."""
 import torch
 
 from hesic_b200 import functional as _F
@@ -17,7 +17,10 @@ def warp_perspective(src, M, dsize, flags="bilinear", border_mode="zeros", align
 
 
 def get_perspective_transform(src, dst):
-    """[B,4,2] point pairs -> [B,3,3] homography (direct linear transform)."""
+    """[B,4,2] point pairs -> [B,3,3] homography (direct linear transform): one kernel launch for CUDA fp32 corners
+    (hesic_perspective_transform), the same system through torch.linalg.solve otherwise."""
+    if src.is_cuda and src.dtype == torch.float32 and dst.dtype == torch.float32 and not (src.requires_grad or dst.requires_grad):
+        return _F.perspective_transform(src, dst)
     B = src.shape[0]
     x, y = src[..., 0], src[..., 1]
     u, v = dst[..., 0], dst[..., 1]

@@ -1352,3 +1352,105 @@ extern "C" int hesic_sum_squared_error(const hesic_tensor *a, const hesic_tensor
   HESIC_LAUNCHED("sse_kernel");
   return HESIC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Homography front-end glue: kornia.get_perspective_transform (+ torch.inverse) and nn.MaxPool2d(2, 2).
+namespace hesic {
+
+// One thread per pair: the 4-point direct linear transform.  Unknowns h0..h7 of H = [[h0 h1 h2] [h3 h4 h5] [h6 h7 1]] from
+//   [x y 1 0 0 0 -x u -y u] h = u,  [0 0 0 x y 1 -x v -y v] h = v      (the system the reference's call sites solve through
+// kornia, ywz/mywork/test3real.py:179, udh/udh/model.py:27), Gaussian elimination with partial pivoting in fp64 (the fp32
+// LAPACK / cuSOLVER solves the reference runs differ from each other in the last digits; fp64 is closer to the exact answer
+// than either), optionally followed by the 3 x 3 inverse (torch.inverse, test3real.py:180) through the adjugate.
+__global__ void perspective_transform_kernel(const float *__restrict__ src, const float *__restrict__ dst, int B, int invert,
+                                             float *__restrict__ H) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double A[8][9];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double x = src[(b * 4 + i) * 2], y = src[(b * 4 + i) * 2 + 1];
+    const double u = dst[(b * 4 + i) * 2], v = dst[(b * 4 + i) * 2 + 1];
+    double *r0 = A[i], *r1 = A[4 + i];
+    r0[0] = x; r0[1] = y; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -x * u; r0[7] = -y * u; r0[8] = u;
+    r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = x; r1[4] = y; r1[5] = 1; r1[6] = -x * v; r1[7] = -y * v; r1[8] = v;
+  }
+  for (int c = 0; c < 8; ++c) {
+    int piv = c;
+    double best = fabs(A[c][c]);
+    for (int r = c + 1; r < 8; ++r)
+      if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
+    if (piv != c)
+      for (int k = c; k < 9; ++k) { const double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+    const double inv = 1.0 / A[c][c];      // singular system (degenerate corners): inf / nan propagate to H, as documented
+    for (int r = c + 1; r < 8; ++r) {
+      const double f = A[r][c] * inv;
+      for (int k = c; k < 9; ++k) A[r][k] -= f * A[c][k];
+    }
+  }
+  double h[9];
+  for (int c = 7; c >= 0; --c) {
+    double s = A[c][8];
+    for (int k = c + 1; k < 8; ++k) s -= A[c][k] * h[k];
+    h[c] = s / A[c][c];
+  }
+  h[8] = 1.0;
+  // the reference path rounds H to fp32 before inverting it (kornia returns fp32, torch.inverse takes it)
+  for (int k = 0; k < 9; ++k) h[k] = (double)(float)h[k];
+  if (invert) {
+    const double a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7], i = h[8];
+    const double c00 = e * i - f * hh, c01 = f * g - d * i, c02 = d * hh - e * g;
+    const double idet = 1.0 / (a * c00 + bb * c01 + c * c02);
+    const double o[9] = {c00 * idet, (c * hh - bb * i) * idet, (bb * f - c * e) * idet,
+                         c01 * idet, (a * i - c * g) * idet, (c * d - a * f) * idet,
+                         c02 * idet, (bb * g - a * hh) * idet, (a * e - bb * d) * idet};
+    for (int k = 0; k < 9; ++k) h[k] = o[k];
+  }
+  for (int k = 0; k < 9; ++k) H[b * 9 + k] = (float)h[k];
+}
+
+// nn.MaxPool2d(2, 2) on dense NCHW fp32 (floor mode: a trailing odd row / column is dropped); thread = two output pixels
+__global__ void max_pool2x2_kernel(const float *__restrict__ x, float *__restrict__ y, int H, int W, int Ho, int Wo, size_t n2) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const int Wo2 = (Wo + 1) / 2;
+  const int ox = (int)(i % Wo2) * 2;
+  const size_t r = i / Wo2;
+  const int oy = (int)(r % Ho);
+  const size_t plane = r / Ho;
+  const float *p = x + (plane * H + 2 * (size_t)oy) * W + 2 * ox;
+  float *o = y + (plane * Ho + oy) * Wo + ox;
+  if (ox + 1 < Wo && (((uintptr_t)p | (uintptr_t)(p + W)) & 15u) == 0) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + W);
+    o[0] = fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+    o[1] = fmaxf(fmaxf(a.z, a.w), fmaxf(b.z, b.w));
+  } else {
+    o[0] = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[W], p[W + 1]));
+    if (ox + 1 < Wo) o[1] = fmaxf(fmaxf(p[2], p[3]), fmaxf(p[W + 2], p[W + 3]));
+  }
+}
+
+}  // namespace hesic
+
+extern "C" int hesic_perspective_transform(const float *src, const float *dst, int B, int invert, float *H, void *stream) {
+  HESIC_REQUIRE(src && dst && H && B >= 0, "perspective_transform: null argument");
+  if (B == 0) return HESIC_OK;
+  perspective_transform_kernel<<<(B + 63) / 64, 64, 0, as_stream(stream)>>>(src, dst, B, invert, H);
+  HESIC_LAUNCHED("perspective_transform_kernel");
+  return HESIC_OK;
+}
+
+extern "C" int hesic_max_pool2x2(const hesic_tensor *x, const hesic_tensor *y, void *stream) {
+  int r;
+  if ((r = check_tensor(x, "max_pool input")) != HESIC_OK) return r;
+  if ((r = check_tensor(y, "max_pool output")) != HESIC_OK) return r;
+  HESIC_REQUIRE(x->fmt == HESIC_FMT_NCHW_F32 && y->fmt == HESIC_FMT_NCHW_F32 && (x->Cs == 0 || x->Cs == x->C) &&
+                    (y->Cs == 0 || y->Cs == y->C),
+                "max_pool2x2: dense NCHW fp32 tensors only");
+  HESIC_REQUIRE(y->B == x->B && y->C == x->C && y->H == x->H / 2 && y->W == x->W / 2, "max_pool2x2: output shape mismatch");
+  const size_t n2 = (size_t)y->B * y->C * y->H * ((y->W + 1) / 2);
+  if (n2 == 0) return HESIC_OK;
+  max_pool2x2_kernel<<<nblk(n2), 256, 0, as_stream(stream)>>>((const float *)x->p0, (float *)y->p0, x->H, x->W, y->H, y->W, n2);
+  HESIC_LAUNCHED("max_pool2x2_kernel");
+  return HESIC_OK;
+}

@@ -170,6 +170,26 @@ def warp_perspective(src, M, dsize, align_corners=True, out=None):
 
 
 @C.device_guard
+def perspective_transform(src, dst, invert=False):
+    """kornia.get_perspective_transform(src, dst) ([B,4,2] corners -> [B,3,3]); invert=True also applies torch.inverse."""
+    src, dst = _f32(src), _f32(dst)
+    if src.shape != dst.shape or src.dim() != 3 or tuple(src.shape[1:]) != (4, 2):
+        raise ValueError(f"perspective_transform: src and dst must be [B,4,2], got {tuple(src.shape)} and {tuple(dst.shape)}")
+    H = torch.empty((src.shape[0], 3, 3), device=src.device, dtype=torch.float32)
+    C.check(_lib.hesic_perspective_transform(C.ptr(src), C.ptr(dst), src.shape[0], int(bool(invert)), C.ptr(H), C.stream()))
+    return H
+
+
+@C.device_guard
+def max_pool2x2(x):
+    """nn.MaxPool2d(2, 2) on NCHW fp32."""
+    x = _f32(x)
+    y = torch.empty((x.shape[0], x.shape[1], x.shape[2] // 2, x.shape[3] // 2), device=x.device, dtype=torch.float32)
+    C.check(_lib.hesic_max_pool2x2(C.ref(C.nchw(x)), C.ref(C.nchw(y)), C.stream()))
+    return y
+
+
+@C.device_guard
 def eb_pack(matrices, biases, factors, quantiles):
     """Pre-activate the EntropyBottleneck parameters into the 60-float-per-channel device table."""
     Cn = quantiles.shape[0]

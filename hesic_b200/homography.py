@@ -4,8 +4,9 @@ network that produces ``h_matrix`` for ``HSIC.forward`` in ywz/mywork/test3real.
 Same class tree, constructor arguments and ``state_dict`` keys as the reference file
 (``cnn.{0-3}.layers.{0,2}.{weight,bias}``, ``fc.{2,5}.{weight,bias}``).  Operator level: the eight 3x3
 convolutions and the two fully-connected layers (as 1x1 convolutions over a 1x1 image) run on the hesic_b200
-conv kernels with the ReLU fused; max-pooling, the 4-point DLT solve and the 3x3 inverse stay in torch -- this is
-the step BEFORE the hot path (2.6 GF per pair against HSIC's 155.7).
+conv kernels with the ReLU fused; max-pooling is ``hesic_max_pool2x2`` and ``get_h`` (4-point DLT + 3x3 inverse) ONE
+kernel launch (``hesic_perspective_transform``; r01/r02 left these in eager torch: 1.7 ms of the 25 ms driver flow) --
+this is the step BEFORE the hot path (2.6 GF per pair against HSIC's 155.7).
 """
 import torch
 import torch.nn as nn
@@ -64,6 +65,19 @@ def photometric_loss(delta, img_a, patch_b, corners):
     return torch.nn.functional.l1_loss(patch_b_hat, patch_b)
 
 
+class MaxPool2d(nn.MaxPool2d):
+    """nn.MaxPool2d(2, 2) of model.py:66 on the library's kernel (CUDA fp32 NCHW); any other configuration or input is
+    torch's."""
+
+    def forward(self, x):
+        k = self.kernel_size if isinstance(self.kernel_size, int) else None
+        s = self.stride if isinstance(self.stride, int) else None
+        if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and k == 2 and s == 2 and self.padding == 0 and
+                self.dilation == 1 and not self.ceil_mode and not self.return_indices and not x.requires_grad):
+            return F.max_pool2x2(x)
+        return super().forward(x)
+
+
 class Flatten(nn.Module):
     def forward(self, x):
         return x.view(x.size(0), -1)
@@ -81,7 +95,7 @@ class Block(nn.Module):
         if batch_norm:
             layers.append(nn.BatchNorm2d(outchannels))
         if pool:
-            layers.append(nn.MaxPool2d(2, 2))
+            layers.append(MaxPool2d(2, 2))
         self.layers = nn.Sequential(*layers)
 
     def forward(self, x):
@@ -108,6 +122,8 @@ class Net(nn.Module):
         return self._delta(a, b)
 
     def get_h(self, a, b, corners):
-        import kornia
         corners_hat = corners + self._delta(a, b)
+        if corners.is_cuda and corners.dtype == torch.float32:
+            return F.perspective_transform(corners, corners_hat, invert=True)   # DLT + inverse, one launch
+        import kornia
         return torch.inverse(kornia.get_perspective_transform(corners, corners_hat))

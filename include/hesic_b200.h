@@ -147,6 +147,17 @@ int hesic_warp_perspective(const hesic_tensor *src, const float *M, const hesic_
                            const hesic_tensor *dst_rowpad, int align_corners, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Homography front-end glue (the step that produces h_matrix, ywz/mywork/test3real.py:171-181):
+ * kornia.get_perspective_transform(src, dst) -- the 4-point direct linear transform, test3real.py:179,
+ * udh/udh/model.py:27 -- optionally followed by torch.inverse (test3real.py:180).  src, dst: dev fp32
+ * [B,4,2] corner coordinates; H: dev fp32 [B,3,3]; invert != 0 writes H^-1 (H rounded to fp32 first, as on
+ * the reference path).  Solved per pair in fp64 with partial pivoting; degenerate corners give inf/nan
+ * entries (torch.linalg.solve raises instead).
+ * hesic_max_pool2x2: nn.MaxPool2d(2, 2) of udh/udh/model.py:66 on dense NCHW fp32, y = [B,C,H/2,W/2]. */
+int hesic_perspective_transform(const float *src, const float *dst, int B, int invert, float *H, void *stream);
+int hesic_max_pool2x2(const hesic_tensor *x, const hesic_tensor *y, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * EntropyBottleneck.forward, eval mode (compressai/entropy_models/entropy_models.py:384-411,
  * 350-382): z_hat = round(z - median) + median; likelihood = |sigmoid(s*u) - sigmoid(s*l)| clamped.
  * params: dev fp32, per channel 58 floats packed as

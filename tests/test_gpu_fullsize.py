@@ -155,7 +155,15 @@ def test_dsic_at_512_vs_oracle():
     dps = {k: abs(m[k] - r[k]) for k in ("psnr1", "psnr2")}
     lik1 = mismatch_fraction(out["likelihoods"]["y1"] > 0.5, ref["likelihoods"]["y1"] > 0.5)
     _note("dsic_512", x_hat_rel_l2=l2, bpp_rel=rel, psnr_abs=dps, y1_lik_side_mismatch=lik1, bpp=m["bpp"], bpp_oracle=r["bpp"])
-    assert_close(out["likelihoods"]["z1"], ref["likelihoods"]["z1"], 1e-4, floor=1e-9, what="z1 likelihood")
+    # z1 likelihoods element-wise, flip-aware as in the HESIC test above: a hyper-latent that sits within the convs' error of a
+    # rounding boundary may round the other way (its likelihood then moves by percents); r02 build: no flip at this seed,
+    # r03 build (first-layer kernel with the x^2-reconstructed GDN pass): one of 8192
+    za, zb = out["likelihoods"]["z1"], ref["likelihoods"]["z1"]
+    zrel = (za - zb).abs() / zb.abs().clamp_min(1e-9)
+    zflip = zrel > 1e-3
+    _note("dsic_512_z1", flipped=int(zflip.sum()), of=zflip.numel(), rel_unflipped=float(zrel[~zflip].max()))
+    assert int(zflip.sum()) <= 4, int(zflip.sum())
+    assert float(zrel[~zflip].max()) < 1e-4
     # view 1 is plain HESIC analysis / synthesis: tight; view 2 passes six softmax-normalised cost volumes whose logits
     # carry the conv error times their magnitude (see test_gpu_dsic.py::test_cost_volume_stages_vs_oracle)
     assert l2["x1_hat"] < 5e-4 and l2["x2_hat"] < 5e-3, l2

@@ -527,3 +527,39 @@ def test_hostfeed_uint8_transport_equals_fp32_transport():
     for p8, p32 in zip(seen8, seen32):
         for u, v in zip(p8, p32):
             assert u.dtype == torch.float32 and torch.equal(u, v)
+
+
+def test_perspective_transform_and_inverse_in_one_launch():
+    """kornia.get_perspective_transform (+ torch.inverse), ywz/mywork/test3real.py:179-180: hesic_perspective_transform against
+    the oracle's restatement, against its defining property (H maps every source corner onto its destination corner, checked
+    in fp64) and through the kornia shim the unmodified driver imports."""
+    import kornia
+    from hesic_b200 import functional as F
+    g = torch.Generator().manual_seed(9)
+    B = 37
+    src = torch.tensor([[[0., 0.], [127., 0.], [127., 127.], [0., 127.]]]).repeat(B, 1, 1) + torch.rand(B, 1, 2, generator=g) * 64
+    dst = src + (torch.rand(B, 4, 2, generator=g) - 0.5) * 24
+    H = F.perspective_transform(src.to(DEV), dst.to(DEV)).cpu()
+    H_ref = O.get_perspective_transform(src, dst)
+    assert_close(H, H_ref, 1e-4, what="perspective transform vs oracle")
+    p = torch.cat([src.double(), torch.ones(B, 4, 1, dtype=torch.float64)], -1) @ H.double().transpose(1, 2)
+    assert torch.allclose(p[..., :2] / p[..., 2:], dst.double(), atol=1e-3)
+    Hi = F.perspective_transform(src.to(DEV), dst.to(DEV), invert=True).cpu()
+    assert_close(Hi, torch.inverse(H_ref), 1e-4, what="inverse homography vs oracle")
+    eye = Hi.double() @ H.double()
+    assert torch.allclose(eye / eye[:, 2:, 2:], torch.eye(3, dtype=torch.float64).expand(B, 3, 3), atol=1e-4)
+    assert torch.equal(kornia.get_perspective_transform(src.to(DEV), dst.to(DEV)).cpu(), H)
+    with pytest.raises(ValueError):
+        F.perspective_transform(src[:, :3].to(DEV), dst[:, :3].to(DEV))
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 16, 24), (1, 3, 33, 30), (3, 64, 128, 128), (1, 2, 7, 9)])
+def test_max_pool2x2(shape):
+    """nn.MaxPool2d(2, 2) of the homography net (udh/udh/model.py:66): bit-equal to torch, odd trailing rows / columns dropped."""
+    from hesic_b200 import functional as F
+    from hesic_b200.homography import MaxPool2d
+    x = _rand(shape, 21).to(DEV)
+    ref = torch.nn.functional.max_pool2d(x, 2, 2)
+    assert torch.equal(F.max_pool2x2(x), ref)
+    assert torch.equal(MaxPool2d(2, 2)(x), ref)
+    assert torch.equal(MaxPool2d(3, 2)(x), torch.nn.functional.max_pool2d(x, 3, 2))     # other configurations: torch's
