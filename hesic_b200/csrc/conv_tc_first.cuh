@@ -37,6 +37,8 @@
 // Two variants with wider rows were built and measured slower: the four warps of a lane quadrant sharing 128-byte rows
 // (mbarrier hand-shake inside the quad: 206 us) and plane-wise rounds of 64-byte rows (the second round waits for the first
 // store to drain: 210 us).  Four-kilobyte rounds per warp (64-byte rows, no waiting) miss the shared-memory budget by 2.5 KB.
+// No staging at all -- every thread writing its 16 channels of a plane with one 256-bit st.global.v8 (one full sector) -- was
+// measured at 217 us: 32 distinct lines per store instruction keep the LSU busier than the staged path keeps the TMA engine.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..17 = epilogue (4 lane quadrants x 4 column groups).
 #pragma once
 
