@@ -563,3 +563,43 @@ def test_max_pool2x2(shape):
     assert torch.equal(F.max_pool2x2(x), ref)
     assert torch.equal(MaxPool2d(2, 2)(x), ref)
     assert torch.equal(MaxPool2d(3, 2)(x), torch.nn.functional.max_pool2d(x, 3, 2))     # other configurations: torch's
+
+
+@pytest.mark.parametrize("size,slice_of", [((2, 44, 60), 128), ((1, 96, 80), 192), ((3, 32, 16), 128), ((1, 28, 36), 128)])
+def test_first_analysis_layer_kernel_ragged_tiles_and_channel_slices(size, slice_of):
+    """conv(3, 128, k5, s2) + fused GDN into the SPLIT planes of the next layer (newnet1.py:583-601): conv_tc_first_kernel
+    (tiles of 8 x 16 output pixels, |x| rebuilt from the x^2 operand) on outputs that do not fill whole tiles, written into a
+    channel slice of a wider buffer, against the oracle at 1e-4 of the rms; the last size is below the kernel's minimum tile
+    and takes conv_tc_kernel<16>.  Exactly the slice is written."""
+    from hesic_b200 import _capi as C
+    from compressai.layers import GDN
+    from compressai.models.utils import conv
+    B, H, W = size
+    mod = conv(3, 128, kernel_size=5, stride=2)
+    w = _rand(tuple(mod.weight.shape), 31, (2.0 / 75) ** 0.5)
+    b = _rand((128,), 32, 0.1)
+    mod.load_state_dict({"weight": w, "bias": b})
+    g = GDN(128)
+    g.load_state_dict({"beta": torch.rand(128, generator=torch.Generator().manual_seed(3)) + 0.5,
+                       "gamma": torch.rand(128, 128, generator=torch.Generator().manual_seed(4)) * 0.02 + 0.1 * torch.eye(128)}, strict=False)
+    x = torch.rand((B, 3, H, W), generator=torch.Generator().manual_seed(5))       # an image: [0, 1)
+    x[0, :, :3, :5] = 0.0                                                           # exact zeros (the 0 * rsqrt(0) guard)
+    ref = O.gdn(O.conv(x, w, b, stride=2), g.beta.detach(), g.gamma.detach())
+    mod, g = mod.to(DEV), g.to(DEV)
+    plan = mod.hesic_plan()
+    plan.set_gdn(g.beta, g.gamma, False, g.beta_min)
+    xs = torch.zeros((2, B, H + C.ROWPAD_Y, W + C.ROWPAD_X, 4), device=DEV, dtype=torch.bfloat16)
+    xd = C.rowpad(xs, 3)
+    C.check(C.lib.hesic_convert(C.ref(C.nchw(x.to(DEV))), C.ref(xd), C.OP_COPY, C.stream()))
+    Ho, Wo = plan.out_hw(H, W)
+    c0 = slice_of - 128
+    ys = torch.zeros((2, B, Ho, Wo, slice_of), device=DEV, dtype=torch.bfloat16)
+    plan.run(xd, C.split(ys, 128, c0), C.ACT_NONE, C.PATH_TC)
+    torch.cuda.synchronize()
+    C.check(C.lib.hesic_tc_status())
+    plan.set_gdn(None, None, False)
+    y = (ys[0].float() + ys[1].float()).cpu()
+    assert_close(y[..., c0:].permute(0, 3, 1, 2), ref, 1e-4, what=f"first layer + GDN {size}")
+    if c0:
+        assert float(y[..., :c0].abs().max()) == 0.0
+    assert torch.isfinite(y).all()
