@@ -18,7 +18,9 @@ namespace hesic {
 namespace tc {
 namespace head {
 
-constexpr int NT = 192;                  // TMA warp, MMA warp, 4 epilogue warps
+constexpr int NT = 320;                  // TMA warp, MMA warp, 8 epilogue warps (r03: 4 left the overlap-add of a tile -- 168
+                                         // items -- to 128 threads in two unequal rounds: 153-162 us per launch)
+constexpr int EPI_T = NT - 64;
 constexpr int TILE_W = 16, TILE_H = 8;   // input pixels per tile (UMMA M = 128), halo included
 constexpr int IN_W = TILE_W - 2, IN_H = TILE_H - 2;
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES;   // one 64-channel chunk, hi + lo
@@ -35,7 +37,7 @@ struct HParams {
   int act;
 };
 
-__device__ __forceinline__ void epi_bar128() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_head() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 template <int COUT>
 __global__ void __launch_bounds__(NT, 1)
@@ -60,7 +62,7 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_map(&map_a_hi); prefetch_map(&map_a_lo); prefetch_map(&map_w_hi); prefetch_map(&map_w_lo);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_T); }
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -134,7 +136,8 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   } else {
     // ===================== epilogue: TMEM -> smem patches -> overlap-add -> NCHW =====================
-    const int quad = warp & 3, row = quad * 32 + lane, tid = (int)threadIdx.x - 64;
+    // warp w reads TMEM lane quadrant w % 4; the two warps of a quadrant split the tile's N columns in 16-column chunks
+    const int quad = warp & 3, row = quad * 32 + lane, tid = (int)threadIdx.x - 64, half = (warp - 2) >> 2;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int Ho = 2 * p.H, Wo = 2 * p.W;
     float bia[COUT], bet[COUT], gam[COUT][COUT];
@@ -154,9 +157,9 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const uint32_t acc = tmem_base + lane_addr + (uint32_t)buf * ACC_STRIDE;
       mbar_wait(acc_full(buf), ((uint32_t)lt >> 1) & 1u, 7);
       tc_fence_after();
-      epi_bar128();   // the previous tile's overlap-add has finished reading the patch buffer
+      epi_bar_head();   // the previous tile's overlap-add has finished reading the patch buffer
       const uint32_t drow = d_base + (uint32_t)(row * pitch) * 4u;
-      for (int c0 = 0; c0 < p.NPAD; c0 += 16) {
+      for (int c0 = 16 * half; c0 < p.NPAD; c0 += 32) {
         uint32_t r[16], q[16];
         tmem_ld16(acc + c0, r);
         tmem_ld16(acc + COL_SMALL + c0, q);
@@ -166,9 +169,9 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       }
       tc_fence_before();
       mbar_arrive(acc_empty(buf));   // patches are in shared memory: release the accumulator
-      epi_bar128();
+      epi_bar_head();
       // one item = interior input pixel (iy, ix) x output row parity ry -> two horizontally adjacent outputs
-      for (int item = tid; item < IN_H * IN_W * 2; item += 128) {
+      for (int item = tid; item < IN_H * IN_W * 2; item += EPI_T) {
         const int ry = item / (IN_H * IN_W), ip = item - ry * (IN_H * IN_W);
         const int iy = ip / IN_W + 1, ix = ip - (ip / IN_W) * IN_W + 1;
         const int gy = y0 + iy, gx = x0 + ix;
