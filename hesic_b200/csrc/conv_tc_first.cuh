@@ -54,9 +54,7 @@ constexpr int FIRST_WK_BYTES = 256 * 32;                          // [Wh ; Wl] r
 constexpr int FIRST_W_BYTES = 9 * FIRST_WK_BYTES;                 // 72 KB
 constexpr int FIRST_G_BYTES = 4 * 128 * 128;                      // gamma: 2 K chunks x (hi, lo) x [128][64], 64 KB
 constexpr int FIRST_STG_BYTES = 16 * 2048;                        // per epilogue warp: 32 pixels x 16 channels x (hi, lo)
-#ifndef HESIC_FIRST_ISSUER
-#define HESIC_FIRST_ISSUER elect_one()
-#endif
+
 constexpr int FIRST_SMEM_BYTES = 1024 + FIRST_W_BYTES + FIRST_G_BYTES + 2 * FIRST_A_BYTES + FIRST_STG_BYTES + 512 + 1024;
 static_assert(FIRST_SMEM_BYTES <= SMEM_LIMIT, "first-layer kernel: shared memory plan does not fit");
 
@@ -235,7 +233,7 @@ conv_tc_first_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     const bool planes = p.pl_phases == 2;
     const uint32_t row_hi = stg + (planes ? (uint32_t)((lane >> 3) * 16 + (lane & 7)) : (uint32_t)lane) * ROW_B;
     const uint32_t row_lo = row_hi + (planes ? 8u : 32u) * ROW_B;
-    const bool issuer = HESIC_FIRST_ISSUER;
+    const bool issuer = elect_one();
 
     // pass 1: x = conv + bias; x^2 -> bf16 (hi, lo) operand over the columns just read; beta -> the norm columns, so that the
     // GDN contraction accumulates onto it
