@@ -595,9 +595,16 @@ def test_first_analysis_layer_kernel_ragged_tiles_and_channel_slices(size, slice
     c0 = slice_of - 128
     ys = torch.zeros((2, B, Ho, Wo, slice_of), device=DEV, dtype=torch.bfloat16)
     plan.run(xd, C.split(ys, 128, c0), C.ACT_NONE, C.PATH_TC)
+    # the same with the lo plane BELOW the hi plane in memory: the kernel's one-store-for-both-planes map does not apply and it
+    # issues one store per plane
+    yr = torch.zeros_like(ys)
+    d = C.split(yr, 128, c0)
+    d.p0, d.p1 = d.p1, d.p0
+    plan.run(xd, d, C.ACT_NONE, C.PATH_TC)
     torch.cuda.synchronize()
     C.check(C.lib.hesic_tc_status())
     plan.set_gdn(None, None, False)
+    assert torch.equal(yr[1], ys[0]) and torch.equal(yr[0], ys[1])
     y = (ys[0].float() + ys[1].float()).cpu()
     assert_close(y[..., c0:].permute(0, 3, 1, 2), ref, 1e-4, what=f"first layer + GDN {size}")
     if c0:
