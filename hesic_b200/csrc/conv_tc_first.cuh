@@ -8,9 +8,10 @@
 // two passes (r02 profile: 33 % of the epilogue's samples sit on norm_full, one instruction issued every ~7 cycles; 277 us).
 // Here nothing waits in registers:
 //   * pass 2 rebuilds |x| from the x^2 operand that is still in TMEM:  y = sign(x) * x^2 * rsqrt(x^2 * (beta + norm))
-//     (IGDN: sign(x) * sqrt(x^2 * (beta + norm))) -- one MUFU per element as before; x^2 = hi + lo carries 16-17 mantissa
-//     bits, i.e. a relative error <= 2^-18 in y, below the 2^-17 the SPLIT output format itself keeps.  The signs of a thread's
-//     32 values travel as eight registers of packed sign bytes.
+//     -- one MUFU per element as before; x^2 = hi + lo carries 16-17 mantissa bits, i.e. a relative error <= 2^-18 in y,
+//     below the 2^-17 the SPLIT output format itself keeps.  The signs of a thread's 32 values travel as 16 registers
+//     holding the sign bytes of a channel pair at the sign positions of a packed bf16 pair (one LOP3 applies them to the
+//     hi and to the lo word of the output).  (The layer is GDN; an IGDN would be sign(x) * sqrt(x^2 * (beta + norm)).)
 //   * so the epilogue warps run the passes of TWO tiles interleaved -- P1(a) P1(b) P2(a) P2(b) -- and every wait for the
 //     tensor pipe (accumulator ready, norm ready) has a whole pass of the other tile in front of it.
 //   * every epilogue warp owns a 32-lane x 32-column block of the accumulator from the first read to the TMA store: its x^2
@@ -62,12 +63,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
   return r;
-}
-// y | (s & 0x80000000): the sign of s onto a non-negative y
-__device__ __forceinline__ float with_sign(float y, uint32_t s) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xf8;" : "=r"(r) : "r"(__float_as_uint(y)), "r"(s));
-  return __uint_as_float(r);
 }
 // K-major, 32B-swizzled shared-memory matrix descriptor: rows of 32 B (one K = 16 slice of bf16), 8-row groups 256 B apart
 __device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
