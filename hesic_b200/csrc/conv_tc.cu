@@ -1189,8 +1189,6 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     q.bw = FIRST_BW; q.bh = FIRST_BH; q.bb = 1;
     q.tiles_x = (y->W + FIRST_BW - 1) / FIRST_BW; q.tiles_y = (y->H + FIRST_BH - 1) / FIRST_BH; q.tiles_b = y->B;
     q.n_tasks = q.tiles_x * q.tiles_y * q.tiles_b;
-    static const int first_dbg = getenv("HESIC_TC_FIRST_DBG") ? atoi(getenv("HESIC_TC_FIRST_DBG")) : 0;
-    q.pl_os = first_dbg;      // diagnostic bits (unused field on this path): 1 = no TMA stores
     CUtensorMap fa_hi, fa_lo, fw_hi, fw_lo, fy0, fy1;
     const uint64_t e = 2;
     {

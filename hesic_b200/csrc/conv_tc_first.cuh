@@ -329,7 +329,7 @@ conv_tc_first_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         }
         fence_async_smem();
         __syncwarp();
-        if (issuer && !(p.pl_os & 1)) {
+        if (issuer) {
           const int c0 = (int)col0 + rd * 16;
           tma_store_5d(&map_y0, stg, c0, tx * FIRST_BW, 0, ty * FIRST_BH + 4 * quad, tb);
           if (!planes) tma_store_5d(&map_y1, stg + 32u * ROW_B, c0, tx * FIRST_BW, 0, ty * FIRST_BH + 4 * quad, tb);
