@@ -529,6 +529,88 @@ def run_extras(args, dev, build, call, timed, C, F, synth, sets, net, model):
         return r
     if model != "dsic":
         guard("latency", latency)
+
+    def hbm_kernels():
+        """The HBM-side kernels of one forward (everything that is not a K-heavy contraction), each timed ALONE with CUDA events
+        on the launching stream, L2 flushed between launches, against the measured copy bandwidth: algorithmic bytes = the
+        fp32-equivalent tensors the operator reads and writes once, at the benchmark's batch (16 x 512 x 512)."""
+        from compressai.layers import GDN
+        from compressai.models.utils import conv, deconv
+        peak = load_peaks()["hbm"]
+        Bk, H, Wd = 16, 512, 512
+        g = torch.Generator(device="cpu").manual_seed(7)
+        flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+        rows = {}
+
+        def run(name, nbytes, fn, ref=None):
+            ts = []
+            for i in range(7):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                if i > 1:
+                    ts.append(e0.elapsed_time(e1))
+            us = 1e3 * sum(ts) / len(ts)
+            rows[name] = {"us": us, "algorithmic_mb": nbytes / 1e6, "gb_s": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / peak}
+            if ref:
+                rows[name]["reference"] = ref
+
+        img = lambda: torch.rand((Bk, 3, H, Wd), generator=g).to(dev)
+        x1, x2 = img(), img()
+        # first analysis layer: conv(3, 128, k5, s2) + GDN, ROWPAD4 planes in, SPLIT planes out
+        l1 = conv(3, 128, kernel_size=5, stride=2).to(dev)
+        p1 = l1.hesic_plan()
+        p1.set_gdn(torch.ones(128, device=dev), 0.1 * torch.eye(128, device=dev) + 0.01, False)
+        rp = torch.zeros((2, Bk, H + C.ROWPAD_Y, Wd + C.ROWPAD_X, 4), device=dev, dtype=torch.bfloat16)
+        y1 = torch.empty((2, Bk, H // 2, Wd // 2, 128), device=dev, dtype=torch.bfloat16)
+        run("x1 -> ROWPAD4 planes (rowpad4_pair_kernel)", Bk * H * Wd * (12 + 16),
+            lambda: C.check(C.lib.hesic_convert(C.ref(C.nchw(x1)), C.ref(C.rowpad(rp, 3)), C.OP_COPY, C.stream())))
+        run("conv 3->128 k5 s2 + GDN (conv_tc_first_kernel)", 4 * Bk * (H * Wd * 3 + (H // 2) * (Wd // 2) * 128),
+            lambda: p1.run(C.rowpad(rp, 3), C.split(y1), C.ACT_NONE, C.PATH_TC), "newnet1.py:583-601")
+        p1.set_gdn(None, None, False)
+        # RGB head: deconv(128, 3, k5, s2) + IGDN, SPLIT planes in, NCHW out
+        l2 = deconv(128, 3, kernel_size=5, stride=2).to(dev)
+        p2 = l2.hesic_plan()
+        p2.set_gdn(torch.ones(3, device=dev), 0.1 * torch.eye(3, device=dev) + 0.01, True)
+        out3 = torch.empty((Bk, 3, H, Wd), device=dev)
+        run("deconv 128->3 k5 s2 + IGDN (conv_head_kernel)", 4 * Bk * ((H // 2) * (Wd // 2) * 128 + H * Wd * 3),
+            lambda: p2.run(C.split(y1), C.nchw(out3), C.ACT_NONE, C.PATH_TC), "newnet1.py:606-624,669-670")
+        p2.set_gdn(None, None, False)
+        # full-resolution stencil: conv(6, 3, k5, s1) on cat(a, b) + GDN
+        l3 = conv(6, 3, kernel_size=5, stride=1).to(dev)
+        p3 = l3.hesic_plan()
+        p3.set_gdn(torch.ones(3, device=dev), 0.1 * torch.eye(3, device=dev) + 0.01, False)
+        run("conv 6->3 k5 s1 on cat + GDN (conv_small_kernel)", 4 * Bk * H * Wd * 9,
+            lambda: p3.run(C.nchw(x1), C.nchw(out3), C.ACT_NONE, C.PATH_AUTO, C.nchw(x2)), "newnet1.py:643-644")
+        p3.set_gdn(None, None, False)
+        # warp
+        hm = sets[0][2][:Bk].contiguous()
+        run("warp_perspective, 3 channels (warp_rgb_kernel)", 4 * Bk * H * Wd * 6,
+            lambda: F.warp_perspective(x1, hm, (H, Wd), out=out3), "newnet1.py:746")
+        # GMM likelihood, K = 5, M = 192 at 32 x 32
+        M_, Kc = 192, 5
+        yl = (torch.randn((Bk, 32, 32, M_), generator=g) * 3).to(dev)                 # channels-last, as the engine feeds it
+        sc = (torch.rand((Bk, 32, 32, M_ * Kc), generator=g) * 2 + 0.1).to(dev)
+        mu = torch.randn((Bk, 32, 32, M_ * Kc), generator=g).to(dev)
+        wt = torch.softmax(torch.randn((Bk, Kc, M_), generator=g), 1).reshape(Bk, Kc * M_).contiguous().to(dev)
+        yh, lk = torch.empty((Bk, M_, 32, 32), device=dev), torch.empty((Bk, M_, 32, 32), device=dev)
+        ys = torch.empty((2, Bk, 32, 32, M_), device=dev, dtype=torch.bfloat16)
+        lacc = torch.zeros(1, device=dev, dtype=torch.float64)
+        run("GMM likelihood K=5 + quantise + y_hat planes (gaussian_tile_kernel)", 4 * Bk * 32 * 32 * M_ * (4 + 2 * Kc),
+            lambda: C.check(C.lib.hesic_gaussian_conditional(C.ref(C.nhwc(yl)), C.ref(C.nhwc(sc)), C.ref(C.nhwc(mu)), C.ptr(wt), Kc, 1,
+                                                             0.11, 1e-9, C.ref(C.nchw(yh)), C.ref(C.nchw(lk)), C.ref(C.split(ys)),
+                                                             C.ptr(lacc), C.stream())), "entropy_models.py:693-702")
+        # SSE partial
+        acc = torch.zeros(1, device=dev, dtype=torch.float64)
+        run("sum of squared errors (sse_dense_kernel)", 4 * Bk * H * Wd * 6, lambda: F.sum_squared_error(x1, x2, acc), "test3real.py:99-111")
+        return {"peak_gb_s": peak, "kernels": rows,
+                "note": "single launches, CUDA events, L2 flushed; an isolated launch carries ~10 us of launch ramp that a launch "
+                        "inside the forward does not (tools/time_gap.py)"}
+    if model == "hesic":
+        guard("hbm_kernels", hbm_kernels)
     return ex
 
 
