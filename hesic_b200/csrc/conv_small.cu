@@ -9,20 +9,25 @@
 // the output (12 B): HBM-bound on paper, FMA-issue-bound in practice.
 //
 // Block = 64 x 16 output pixels, 128 threads, each thread 2 rows x 4 consecutive pixels x Cout
-// accumulators.  The zero-padded input tile (Cin x 20 x 68 fp32) and the weights ([ci][ky][kx][4], the
+// accumulators.  The zero-padded input tile (Cin x 20 x 72 fp32, one TMA box per source tensor) and the weights ([ci][ky][kx][4], the
 // kernel flipped for the transposed form) sit in shared memory / the kernel parameters; inner loop per (ci, ky): four 16-byte
 // input loads feed 120 FMAs whose weight operand is a uniform register.  torch.cat on the reference side is a second
 // input pointer (channels [Ca, Cin) come from xb), so the concatenation is never materialised.  The
 // output is NCHW fp32 or, when the consumer is the 3->128 tensor-core layer, directly its ROWPAD8
 // bf16 (hi, lo) input format.
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv.h"
+#include "tc_ptx.cuh"
 
 namespace hesic {
 namespace small {
 
-constexpr int TW = 64, TH = 16, NT = 128, PITCH = TW + 4, ROWS = TH + 4;
+// the input tile starts FOUR columns left of the output tile (two of halo, two of alignment: a TMA box has to start on a
+// 16-byte boundary of the innermost dimension) and is 72 floats wide
+constexpr int TW = 64, TH = 16, NT = 128, PITCH = TW + 8, ROWS = TH + 4, XOFF = 4;
+constexpr int PLANE = ROWS * PITCH;      // floats of one channel of the input tile
 
 struct Args {
   const float *xa, *xb;   // NCHW fp32; channels [0, Ca) from xa, [Ca, Cin) from xb
@@ -40,19 +45,38 @@ struct Args {
   // is a uniform register filled from the constant bank (LDCU), no shared-memory weight loads.  r03 measurements of the
   // alternatives (all bit-identical): weights in shared memory 142-155 us; this form 135-140 us; packed fma.rn.f32x2 with
   // pixel pairs 155-159 us (one MOV per packed FMA to build the unaligned pairs); packed FMAs over row pairs interleaved in
-  // shared memory, no MOVs, 182-185 us.  A three-source FFMA issues every second cycle per scheduler: the layer runs at
-  // ~70 % of that rate.
+  // shared memory, no MOVs, 182-185 us.  (B200 issues three-source FFMAs at full rate, tools/micro/ffma_rate.cu: what held
+  // this kernel back was the tile fill, see `tma` below.)
   float wk[8 * 25 * 4];
+  // tile fill by TMA (r03): one box [channels][ROWS][PITCH] per source tensor, out-of-image elements zero-filled by the
+  // copy engine.  The per-element cp.async loop it replaces (bounds tests, 64-bit addresses, predicates) was 40 % of the
+  // kernel's executed instructions (ncu source page: FFMA 46 %).  gap_b: floats between the end of xa's box and the
+  // (128-byte aligned) start of xb's.
+  int tma, gap_b;
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ Args a) {
-  extern __shared__ __align__(16) float sm[];
-  float *in = sm;                        // [CIN][ROWS][PITCH]
+__global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ Args a, const __grid_constant__ CUtensorMap map_a,
+                                                       const __grid_constant__ CUtensorMap map_b) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) unsigned long long tile_bar;
+  float *in = sm;                        // [CIN][ROWS][PITCH] (+ gap_b floats before xb's channels)
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
 
-  // input tile: one warp per (channel, row), lanes along x.  The tile starts at x0 - 2 (even), so with an even
+  if (a.tma) {
+    const uint32_t bar = tc::smem_u32(&tile_bar), dst = tc::smem_u32(in);
+    if (tid == 0) {
+      tc::mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      tc::mbar_expect_tx(bar, (uint32_t)(CIN * PLANE * sizeof(float)));
+      tc::tma_load_4d(&map_a, dst, bar, x0 - XOFF, y0 - 2, 0, b);
+      if (a.Ca < CIN) tc::tma_load_4d(&map_b, dst + (uint32_t)((a.Ca * PLANE + a.gap_b) * sizeof(float)), bar, x0 - XOFF, y0 - 2, 0, b);
+    }
+    __syncthreads();
+    tc::mbar_wait(bar, 0, 20);
+  } else
+  // input tile: one warp per (channel, row), lanes along x.  The tile starts at x0 - 4 (even), so with an even
   // image width every float2 is 8-byte aligned and entirely inside or outside the image.
   {
     const int warp = tid >> 5, lane = tid & 31;
@@ -68,21 +92,21 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ 
       const float *safe = a.xa;   // any valid address for the zero-fill form
       if (vec2) {
         for (int col = 2 * lane; col < PITCH; col += 64) {
-          const int gx = x0 - 2 + col;
+          const int gx = x0 - XOFF + col;
           const bool ok = src && gx >= 0 && gx < a.W;
           cp_async<8>(dst + col, ok ? src + gx : safe, ok);
         }
       } else {
         for (int col = lane; col < PITCH; col += 32) {
-          const int gx = x0 - 2 + col;
+          const int gx = x0 - XOFF + col;
           const bool ok = src && gx >= 0 && gx < a.W;
           cp_async<4>(dst + col, ok ? src + gx : safe, ok);
         }
       }
     }
     cp_async_wait_all();
+    __syncthreads();
   }
-  __syncthreads();
 
   float acc[2][4][COUT];
 #pragma unroll
@@ -99,10 +123,12 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ 
       float v[2][8];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const float *row = in + ((size_t)ci * ROWS + ty + 8 * r + ky) * PITCH + 4 * tx;
-        const float4 q0 = *reinterpret_cast<const float4 *>(row), q1 = *reinterpret_cast<const float4 *>(row + 4);
-        v[r][0] = q0.x; v[r][1] = q0.y; v[r][2] = q0.z; v[r][3] = q0.w;
-        v[r][4] = q1.x; v[r][5] = q1.y; v[r][6] = q1.z; v[r][7] = q1.w;
+        const float *row = in + ((size_t)ci * ROWS + ty + 8 * r + ky) * PITCH + 4 * tx + (ci >= a.Ca ? a.gap_b : 0);
+        // columns [4 tx + 2, 4 tx + 10) of the tile (XOFF - 2 = 2 floats into the row): 8 + 16 + 8 bytes
+        const float2 q0 = *reinterpret_cast<const float2 *>(row + 2), q2 = *reinterpret_cast<const float2 *>(row + 8);
+        const float4 q1 = *reinterpret_cast<const float4 *>(row + 4);
+        v[r][0] = q0.x; v[r][1] = q0.y; v[r][2] = q1.x; v[r][3] = q1.y;
+        v[r][4] = q1.z; v[r][5] = q1.w; v[r][6] = q2.x; v[r][7] = q2.y;
       }
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
@@ -183,13 +209,35 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ 
 }
 
 template <int CIN, int COUT>
-static int launch(const Args &a, cudaStream_t s) {
-  const int smem = CIN * ROWS * PITCH * (int)sizeof(float);
+static int launch(Args &a, const hesic_tensor *xa, const hesic_tensor *xb, cudaStream_t s) {
+  CUtensorMap ma, mb;
+  memset(&ma, 0, sizeof(ma));
+  memset(&mb, 0, sizeof(mb));
+  a.tma = 0; a.gap_b = 0;
+  static const bool tma_on = getenv("HESIC_SMALL_NO_TMA") == nullptr;
+  const int Cb = CIN - a.Ca;
+  if (tma_on && a.W % 4 == 0 && ((uintptr_t)a.xa & 15u) == 0 && (!xb || ((uintptr_t)a.xb & 15u) == 0) && (Cb == 0 || xb)) {
+    auto mk = [&](CUtensorMap *m, const float *base, int C, int Cs) {
+      uint64_t dims[4] = {(uint64_t)a.W, (uint64_t)a.H, (uint64_t)C, (uint64_t)a.B};
+      uint64_t strides[3] = {(uint64_t)a.W * 4, (uint64_t)a.H * a.W * 4, (uint64_t)Cs * a.H * a.W * 4};
+      uint32_t box[4] = {(uint32_t)PITCH, (uint32_t)ROWS, (uint32_t)C, 1u};
+      return tc::make_tensor_map(m, base, 4, dims, strides, box, true, false);
+    };
+    int r = mk(&ma, a.xa, a.Ca, a.CsA);
+    if (r == HESIC_OK && Cb > 0) r = mk(&mb, a.xb, Cb, a.CsB);
+    if (r == HESIC_OK) {
+      a.tma = 1;
+      const int bytes_a = a.Ca * PLANE * (int)sizeof(float);
+      a.gap_b = Cb > 0 ? ((bytes_a + 127) / 128 * 128 - bytes_a) / (int)sizeof(float) : 0;
+    }
+  }
+  const int smem = (CIN * PLANE + a.gap_b) * (int)sizeof(float);
   static PerDeviceOnce once;
   if (once.first())
-    HESIC_CUDA(cudaFuncSetAttribute(conv_small_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HESIC_CUDA(cudaFuncSetAttribute(conv_small_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (CIN * PLANE + 32) * (int)sizeof(float)));
   dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B);
-  conv_small_kernel<CIN, COUT><<<grid, NT, smem, s>>>(a);
+  conv_small_kernel<CIN, COUT><<<grid, NT, smem, s>>>(a, ma, mb);
   HESIC_LAUNCHED("conv_small_kernel");
   return HESIC_OK;
 }
@@ -228,8 +276,8 @@ int conv_forward_small(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor
   if (c->has_gdn && act != HESIC_ACT_NONE) { set_error("activation after fused GDN is not supported"); return HESIC_E_UNSUPPORTED; }
   a.act = act;
   a.out_fmt = y->fmt; a.out_Cs = y->Cs > 0 ? y->Cs : y->C; a.y0 = y->p0; a.y1 = y->p1;
-  if (c->Cin == 6) return small::launch<6, 3>(a, s);
-  return small::launch<3, 3>(a, s);
+  if (c->Cin == 6) return small::launch<6, 3>(a, xa, xb, s);
+  return small::launch<3, 3>(a, xa, xb, s);
 }
 
 }  // namespace hesic

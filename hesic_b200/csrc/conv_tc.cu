@@ -806,8 +806,9 @@ static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *
 
 // exported to the other tcgen05 translation units (enhance.cu)
 int make_tensor_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
-                    const uint32_t *box, bool f32) {
-  return make_map(m, base, rank, dims, strides, box, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+                    const uint32_t *box, bool f32, bool swizzle128) {
+  return make_map(m, base, rank, dims, strides, box, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }

@@ -9,10 +9,10 @@ namespace tc {
 
 constexpr int BM = 128;                 // pixels per tile (UMMA M)
 
-// rank-n tensor map (bf16, or fp32), 128B swizzle, zero OOB fill; dims / box innermost first, strides in bytes for
-// dims 1..n-1 (conv_tc.cu)
+// rank-n tensor map (bf16, or fp32), 128B swizzle (or none: dense box rows), zero OOB fill; dims / box innermost first,
+// strides in bytes for dims 1..n-1 (conv_tc.cu)
 int make_tensor_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
-                    const uint32_t *box, bool f32 = false);
+                    const uint32_t *box, bool f32 = false, bool swizzle128 = true);
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
