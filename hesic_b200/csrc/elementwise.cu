@@ -694,6 +694,49 @@ __global__ void __launch_bounds__(256) gaussian_tile_kernel(const TView y, const
 // ---------------------------------------------------------------------------------------------
 // spatial_pool2d: global max per (b, c).
 // NHWC: block = 32 channels x 8 pixel lanes (a warp reads 32 consecutive channels of one pixel).
+// Vector form (channels-last fp32, C % 4 == 0, 16-byte aligned): a thread owns one channel QUAD and every 32nd pixel; a warp
+// instruction reads 4 pixels x 32 channels as 16-byte loads and four of them are in flight per thread (16 KB per block), running
+// maxima advance by pointer increments.  r03: the scalar form below (one channel per thread, 64-bit index arithmetic per load:
+// IMAD + LEA were 54 % of its instructions, 81 % of its stall samples waiting for loads) took 27 us for 63 MB.
+__global__ void __launch_bounds__(256) spatial_max_nhwc4_kernel(const TView x, float *__restrict__ out) {
+  __shared__ float4 red[32][8];
+  const int b = blockIdx.y;
+  const int q = threadIdx.x & 7, pl = threadIdx.x >> 3;          // channel quad, pixel lane (0..31)
+  const int c = blockIdx.x * 32 + 4 * q;
+  const int P = x.H * x.W;
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (c < x.C) {
+    const size_t step = (size_t)32 * x.Cs;
+    const float *ptr = (const float *)x.p0 + ((size_t)b * P + pl) * x.Cs + c;
+    float4 m1 = m, m2 = m, m3 = m;
+    int p = pl;
+    for (; p + 96 < P; p += 128, ptr += 4 * step) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4 *>(ptr)), v1 = __ldg(reinterpret_cast<const float4 *>(ptr + step));
+      const float4 v2 = __ldg(reinterpret_cast<const float4 *>(ptr + 2 * step)), v3 = __ldg(reinterpret_cast<const float4 *>(ptr + 3 * step));
+      m = make_float4(fmaxf(m.x, v0.x), fmaxf(m.y, v0.y), fmaxf(m.z, v0.z), fmaxf(m.w, v0.w));
+      m1 = make_float4(fmaxf(m1.x, v1.x), fmaxf(m1.y, v1.y), fmaxf(m1.z, v1.z), fmaxf(m1.w, v1.w));
+      m2 = make_float4(fmaxf(m2.x, v2.x), fmaxf(m2.y, v2.y), fmaxf(m2.z, v2.z), fmaxf(m2.w, v2.w));
+      m3 = make_float4(fmaxf(m3.x, v3.x), fmaxf(m3.y, v3.y), fmaxf(m3.z, v3.z), fmaxf(m3.w, v3.w));
+    }
+    for (; p < P; p += 32, ptr += step) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4 *>(ptr));
+      m = make_float4(fmaxf(m.x, v0.x), fmaxf(m.y, v0.y), fmaxf(m.z, v0.z), fmaxf(m.w, v0.w));
+    }
+    m = make_float4(fmaxf(fmaxf(m.x, m1.x), fmaxf(m2.x, m3.x)), fmaxf(fmaxf(m.y, m1.y), fmaxf(m2.y, m3.y)),
+                    fmaxf(fmaxf(m.z, m1.z), fmaxf(m2.z, m3.z)), fmaxf(fmaxf(m.w, m1.w), fmaxf(m2.w, m3.w)));
+  }
+  red[pl][q] = m;
+  __syncthreads();
+  if (pl == 0 && c < x.C) {
+#pragma unroll 4
+    for (int j = 1; j < 32; ++j) {
+      const float4 v = red[j][q];
+      m = make_float4(fmaxf(m.x, v.x), fmaxf(m.y, v.y), fmaxf(m.z, v.z), fmaxf(m.w, v.w));
+    }
+    *reinterpret_cast<float4 *>(out + (size_t)b * x.C + c) = m;
+  }
+}
+
 __global__ void __launch_bounds__(256) spatial_max_nhwc_kernel(const TView x, float *__restrict__ out) {
   __shared__ float red[8][33];
   const int b = blockIdx.y;
@@ -1205,7 +1248,11 @@ extern "C" int hesic_spatial_max(const hesic_tensor *x, float *out_max, void *st
     spatial_max_nchw_kernel<<<(x->B * x->C + 7) / 8, 256, 0, as_stream(stream)>>>(view(x), out_max);
   } else {
     dim3 grid((x->C + 31) / 32, x->B);
-    spatial_max_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(view(x), out_max);
+    const int xCs = x->Cs > 0 ? x->Cs : x->C;
+    if (x->fmt == HESIC_FMT_NHWC_F32 && (x->C & 3) == 0 && (xCs & 3) == 0 && ((uintptr_t)x->p0 & 15u) == 0 && ((uintptr_t)out_max & 15u) == 0)
+      spatial_max_nhwc4_kernel<<<grid, 256, 0, as_stream(stream)>>>(view(x), out_max);
+    else
+      spatial_max_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(view(x), out_max);
   }
   HESIC_LAUNCHED("spatial_max_kernel");
   return HESIC_OK;
