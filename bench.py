@@ -215,9 +215,14 @@ def run_ours(args):
     def step(x1, x2, h):
         out = call(net, model, x1, x2, h)
         partial.zero_()
-        partial[:4].copy_(net.hesic_engine.log2_sums)
-        F.sum_squared_error(out["x1_hat"], x1, partial[4:5])
-        F.sum_squared_error(out["x2_hat"], x2, partial[5:6])
+        eng = net.hesic_engine
+        partial[:4].copy_(eng.log2_sums)
+        if getattr(eng, "sse_sums", None) is not None:
+            # HESIC / HESIC+: the squared errors come out of the epilogues that store x1_hat / x2_hat (no pass over the images)
+            partial[4:].copy_(eng.sse_sums)
+        else:
+            F.sum_squared_error(out["x1_hat"], x1, partial[4:5])
+            F.sum_squared_error(out["x2_hat"], x2, partial[5:6])
         sharding.reduce_partials(partial)     # the path's only collective: 48 bytes over NVLink (no-op at N=1)
         return out
 
@@ -578,6 +583,11 @@ def run_extras(args, dev, build, call, timed, C, F, synth, sets, net, model):
         out3 = torch.empty((Bk, 3, H, Wd), device=dev)
         run("deconv 128->3 k5 s2 + IGDN (conv_head_kernel)", 4 * Bk * ((H // 2) * (Wd // 2) * 128 + H * Wd * 3),
             lambda: p2.run(C.split(y1), C.nchw(out3), C.ACT_NONE, C.PATH_TC), "newnet1.py:606-624,669-670")
+        # the same launch with the squared error against a target image taken from its epilogue (x1_hat vs x1 in the forward)
+        acc_f = torch.zeros(1, device=dev, dtype=torch.float64)
+        run("deconv 128->3 k5 s2 + IGDN + squared error vs target (conv_head_kernel)",
+            4 * Bk * ((H // 2) * (Wd // 2) * 128 + 2 * H * Wd * 3),
+            lambda: p2.run(C.split(y1), C.nchw(out3), C.ACT_NONE, C.PATH_TC, None, (C.nchw(x2), acc_f)), "newnet1.py:612 + test3real.py:99-111")
         p2.set_gdn(None, None, False)
         # full-resolution stencil: conv(6, 3, k5, s1) on cat(a, b) + GDN
         l3 = conv(6, 3, kernel_size=5, stride=1).to(dev)
@@ -586,6 +596,13 @@ def run_extras(args, dev, build, call, timed, C, F, synth, sets, net, model):
         run("conv 6->3 k5 s1 on cat + GDN (conv_small_kernel)", 4 * Bk * H * Wd * 9,
             lambda: p3.run(C.nchw(x1), C.nchw(out3), C.ACT_NONE, C.PATH_AUTO, C.nchw(x2)), "newnet1.py:643-644")
         p3.set_gdn(None, None, False)
+        l4 = deconv(6, 3, kernel_size=5, stride=1).to(dev)
+        p4 = l4.hesic_plan()
+        p4.set_gdn(None, None, False)
+        x3 = img()
+        run("deconv 6->3 k5 s1 on cat + squared error vs target (conv_small_kernel)", 4 * Bk * H * Wd * 12,
+            lambda: p4.run(C.nchw(x1), C.nchw(out3), C.ACT_NONE, C.PATH_AUTO, C.nchw(x2), (C.nchw(x3), acc_f)),
+            "newnet1.py:686 + test3real.py:99-111")
         # warp
         hm = sets[0][2][:Bk].contiguous()
         run("warp_perspective, 3 channels (warp_rgb_kernel)", 4 * Bk * H * Wd * 6,

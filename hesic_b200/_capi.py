@@ -56,6 +56,7 @@ _sig = {
     "hesic_conv_detect_kband": ([c_void_p, c_void_p, c_void_p], c_int),
     "hesic_conv_forward": ([c_void_p, _TP, _TP, c_int, c_int, c_void_p], c_int),
     "hesic_conv_forward_cat": ([c_void_p, _TP, _TP, _TP, c_int, c_int, c_void_p], c_int),
+    "hesic_conv_forward_sse": ([c_void_p, _TP, _TP, _TP, c_int, c_int, _TP, c_void_p, c_void_p], c_int),
     "hesic_en_conv_create": ([c_int, c_int], c_void_p),
     "hesic_en_conv_destroy": ([c_void_p], None),
     "hesic_en_conv_load": ([c_void_p, c_void_p, c_void_p, c_void_p], c_int),

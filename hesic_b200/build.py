@@ -1,6 +1,9 @@
 """Build recipe for libhesic_b200.so (sm_100a only, in-tree so it travels with gpurun snapshots).
 
-    python -m hesic_b200.build [--force] [--verbose]
+    python -m hesic_b200.build [--force] [--verbose] [--diag]
+
+--diag compiles the diagnostic environment switches in (-DHESIC_DIAG); the default build reads
+no environment variable.
 """
 import os
 import subprocess
@@ -23,8 +26,8 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, diag=False):
+    if not force and not diag and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -35,7 +38,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(objdir, src + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["-DHESIC_DIAG"] if diag else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -51,4 +54,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv))

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <string>
@@ -188,6 +189,14 @@ __device__ __forceinline__ float nonneg_reparam(float p, float minimum) {
   float o = fmaxf(p, bound);
   return o * o - pedestal;
 }
+
+// Diagnostic switches (A/B measurements of kernel variants and fallbacks) exist only in a library
+// built with -DHESIC_DIAG (`python -m hesic_b200.build --diag`): the production build reads no environment variable.
+#ifdef HESIC_DIAG
+inline const char *diag_env(const char *name) { return getenv(name); }
+#else
+inline const char *diag_env(const char *) { return nullptr; }
+#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

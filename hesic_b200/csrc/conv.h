@@ -46,6 +46,11 @@ struct hesic_conv {
   double *gn_stats = nullptr;   // [B][groups][HESIC_GN_SLOTS][2] partial (sum, sum of squares), zeroed by the caller
   int gn_groups = 0;
   bool gn_fused = false;        // out: the launched kernel accumulated the statistics
+  // squared error against a target image fused into the epilogue (hesic_conv_forward_sse): set for the duration of one launch
+  const float *sse_target = nullptr;   // NCHW fp32, the output's shape; channel stride of an image = sse_Cs channels
+  int sse_Cs = 0;
+  double *sse_acc = nullptr;    // += sum((y - target)^2), fp64
+  bool sse_fused = false;       // out: the launched kernel accumulated the sum
   // tcgen05 path: cached TMA tensor maps of the static operands (w_hi, w_lo, gamma_hi, gamma_lo)
   unsigned char *tc_maps = nullptr;
   int tc_maps_bn = 0, tc_maps_gdn = -1;

@@ -538,7 +538,7 @@ static int conv_forward_any(hesic_conv *c, const hesic_tensor *x, const hesic_te
     return HESIC_E_UNSUPPORTED;
   }
   if (path == HESIC_PATH_TCGEN05 || (path == HESIC_PATH_AUTO && tc_ok)) return conv_forward_tc(c, x, y, act, s);
-  static const bool trace = getenv("HESIC_TRACE_SIMT") != nullptr;   // which layers miss the tensor-core path
+  static const bool trace = diag_env("HESIC_TRACE_SIMT") != nullptr;   // which layers miss the tensor-core path
   if (trace)
     fprintf(stderr, "[hesic] CUDA-core conv: %d->%d k%dx%d s%d tr%d  in fmt%d %dx%dx%d  out fmt%d %dx%d path=%d\n", c->Cin, c->Cout,
             c->kh, c->kw, c->stride, c->transposed, x->fmt, x->B, x->H, x->W, y->fmt, y->H, y->W, path);
@@ -561,7 +561,7 @@ extern "C" int hesic_conv_forward_gn(hesic_conv *c, const hesic_tensor *x, const
   HESIC_REQUIRE(y->fmt == HESIC_FMT_NHWC_F32 && c->Cout % groups == 0, "hesic_conv_forward_gn: NHWC fp32 output, channels divisible by groups");
   cudaStream_t s = as_stream(stream);
   HESIC_CUDA(cudaMemsetAsync(stats, 0, (size_t)y->B * groups * HESIC_GN_SLOTS * 2 * sizeof(double), s));
-  static const bool unfused = getenv("HESIC_GN_UNFUSED") != nullptr;     // diagnostic: always use the statistics kernel
+  static const bool unfused = diag_env("HESIC_GN_UNFUSED") != nullptr;     // diagnostic: always use the statistics kernel
   c->gn_stats = unfused ? nullptr : stats; c->gn_groups = groups; c->gn_fused = false;
   const int r = conv_forward_any(c, x, nullptr, y, HESIC_ACT_NONE, path, stream);
   const bool fused = c->gn_fused;
@@ -574,6 +574,26 @@ extern "C" int hesic_conv_forward_cat(hesic_conv *c, const hesic_tensor *xa, con
                                       int act, int path, void *stream) {
   HESIC_REQUIRE(xb != nullptr, "hesic_conv_forward_cat: null second input");
   return conv_forward_any(c, xa, xb, y, act, path, stream);
+}
+
+// Convolution whose NCHW fp32 output is a reconstruction compared with a target image (the MSE term of RateDistortionLoss,
+// ywz/mywork/test3real.py:99-111): *sse += sum((y - target)^2) -- in the epilogue of the kernels that produce the images
+// (RGB synthesis head, full-resolution stencil: the output is still in registers, no second pass over it), else with the
+// squared-error kernel.
+extern "C" int hesic_conv_forward_sse(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y, int act,
+                                      int path, const hesic_tensor *target, double *sse, void *stream) {
+  HESIC_REQUIRE(c && y && target && sse, "hesic_conv_forward_sse: null argument");
+  int r;
+  if ((r = check_tensor(target, "sse target")) != HESIC_OK) return r;
+  HESIC_REQUIRE(y->fmt == HESIC_FMT_NCHW_F32 && target->fmt == HESIC_FMT_NCHW_F32 && same_shape(y, target),
+                "hesic_conv_forward_sse: output and target must be NCHW fp32 of the same shape");
+  c->sse_target = (const float *)target->p0; c->sse_Cs = target->Cs > 0 ? target->Cs : target->C;
+  c->sse_acc = sse; c->sse_fused = false;
+  r = conv_forward_any(c, xa, xb, y, act, path, stream);
+  const bool fused = c->sse_fused;
+  c->sse_target = nullptr; c->sse_Cs = 0; c->sse_acc = nullptr; c->sse_fused = false;
+  if (r != HESIC_OK || fused) return r;
+  return hesic_sum_squared_error(y, target, sse, stream);
 }
 
 extern "C" int hesic_gdn(const hesic_tensor *x, const hesic_tensor *y, const float *beta, const float *gamma,

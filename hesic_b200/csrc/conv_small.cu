@@ -53,6 +53,11 @@ struct Args {
   // kernel's executed instructions (ncu source page: FFMA 46 %).  gap_b: floats between the end of xa's box and the
   // (128-byte aligned) start of xb's.
   int tma, gap_b;
+  // squared error of the NCHW output against a target image (MSE partial of RateDistortionLoss, test3real.py:99-111),
+  // accumulated from the registers the output is stored from: one atomic per block
+  const float *target;
+  int tgt_Cs;
+  double *sse;
 };
 
 template <int CIN, int COUT>
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ 
 #pragma unroll
     for (int j = 0; j < COUT; ++j) gam[j][c] = a.gdn ? __ldg(a.gamma + j * COUT + c) : 0.f;
   }
+  double se = 0.0;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int oy = y0 + ty + 8 * r;
@@ -192,6 +198,22 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ 
           for (int p = 0; p < 4; ++p)
             if (ox + p < a.W) dst[p] = o[c][p];
         }
+        if (a.sse) {
+          const float *tg = a.target + (((size_t)b * a.tgt_Cs + c) * a.H + oy) * a.W + ox;
+          float t[4];
+          if (ox + 3 < a.W && (((uintptr_t)tg) & 15u) == 0) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(tg));
+            t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+          } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) t[p] = ox + p < a.W ? __ldg(tg + p) : o[c][p];
+          }
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float d = o[c][p] - t[p];
+            se += (double)d * (double)d;
+          }
+        }
       }
     } else {   // ROWPAD split: one store of all channel slots per pixel and plane
       TView yv;
@@ -206,6 +228,18 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ 
       }
     }
   }
+  if (a.sse) {   // uniform
+    __shared__ double part[NT / 32];
+    se = warp_sum(se);
+    if ((tid & 31) == 0) part[tid >> 5] = se;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) s += part[w];
+      atomicAdd(a.sse, s);
+    }
+  }
 }
 
 template <int CIN, int COUT>
@@ -214,7 +248,7 @@ static int launch(Args &a, const hesic_tensor *xa, const hesic_tensor *xb, cudaS
   memset(&ma, 0, sizeof(ma));
   memset(&mb, 0, sizeof(mb));
   a.tma = 0; a.gap_b = 0;
-  static const bool tma_on = getenv("HESIC_SMALL_NO_TMA") == nullptr;
+  static const bool tma_on = diag_env("HESIC_SMALL_NO_TMA") == nullptr;
   const int Cb = CIN - a.Ca;
   if (tma_on && a.W % 4 == 0 && ((uintptr_t)a.xa & 15u) == 0 && (!xb || ((uintptr_t)a.xb & 15u) == 0) && (Cb == 0 || xb)) {
     auto mk = [&](CUtensorMap *m, const float *base, int C, int Cs) {
@@ -276,6 +310,11 @@ int conv_forward_small(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor
   if (c->has_gdn && act != HESIC_ACT_NONE) { set_error("activation after fused GDN is not supported"); return HESIC_E_UNSUPPORTED; }
   a.act = act;
   a.out_fmt = y->fmt; a.out_Cs = y->Cs > 0 ? y->Cs : y->C; a.y0 = y->p0; a.y1 = y->p1;
+  a.target = nullptr; a.tgt_Cs = 0; a.sse = nullptr;
+  if (c->sse_acc && y->fmt == HESIC_FMT_NCHW_F32) {
+    a.target = c->sse_target; a.tgt_Cs = c->sse_Cs; a.sse = c->sse_acc;
+    c->sse_fused = true;
+  }
   if (c->Cin == 6) return small::launch<6, 3>(a, xa, xb, s);
   return small::launch<3, 3>(a, xa, xb, s);
 }

@@ -930,6 +930,10 @@ static int launch_head(hesic_conv *c, const hesic_tensor *x, const hesic_tensor 
   p.bias = c->bias; p.act = act;
   p.gdn = c->has_gdn ? (c->gdn_inverse ? 2 : 1) : 0;
   p.beta = c->gdn_beta; p.gamma = c->gdn_w_simt;
+  if (c->sse_acc) {
+    p.target = c->sse_target; p.tgt_Cs = c->sse_Cs; p.sse = c->sse_acc;
+    c->sse_fused = true;
+  }
   const int fixed = 1024 + 256 + p.kchunks * 2 * p.NPAD * 128 + BM * (p.NPAD + 1) * 4;
   p.stages = std::min(8, (SMEM_LIMIT - fixed) / head::STAGE_BYTES);
   if (p.stages < 2) { set_error("conv head: operands do not fit shared memory"); return HESIC_E_UNSUPPORTED; }
@@ -1035,12 +1039,12 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   }
   p.w_resident = (c->tc_kind == HESIC_TC_ROW2 && p.n_tiles == 1 && p.b_bytes <= (uint32_t)A_TILE_BYTES) ? 1 : 0;
   // diagnostic switches, read once per process
-  static const bool env_no_resident = getenv("HESIC_TC_NO_RESIDENT") != nullptr, env_narrow = getenv("HESIC_TC_NARROW") != nullptr,
-                    env_direct_store = getenv("HESIC_TC_DIRECT_STORE") != nullptr,
-                    env_one_staging = getenv("HESIC_TC_ONE_STAGING") != nullptr;
+  static const bool env_no_resident = diag_env("HESIC_TC_NO_RESIDENT") != nullptr, env_narrow = diag_env("HESIC_TC_NARROW") != nullptr,
+                    env_direct_store = diag_env("HESIC_TC_DIRECT_STORE") != nullptr,
+                    env_one_staging = diag_env("HESIC_TC_ONE_STAGING") != nullptr;
   if (env_no_resident) p.w_resident = 0;
   p.wide_n = (!planar && p.BN == 128 && !env_narrow) ? 1 : 0;
-  static const int gdn_at_env = getenv("HESIC_TC_GDN_AT") ? atoi(getenv("HESIC_TC_GDN_AT")) : GDN_AT;
+  static const int gdn_at_env = diag_env("HESIC_TC_GDN_AT") ? atoi(diag_env("HESIC_TC_GDN_AT")) : GDN_AT;
   p.gdn_at = std::max(0, gdn_at_env);
   p.stage_bytes = 2u * A_TILE_BYTES + (p.w_resident ? 0u : 2u * p.b_bytes);
   // TMA-store epilogue: channels-last outputs; for the sub-pixel phases of a transposed conv the phase
@@ -1145,7 +1149,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   }
   const CUtensorMap *m = (const CUtensorMap *)c->tc_maps;
   // CTA-pair kernel (conv_tc_pair.cuh): plain K-heavy layers with full 128-column N tiles
-  static const bool pair_on = getenv("HESIC_TC_SINGLE_CTA") == nullptr;
+  static const bool pair_on = diag_env("HESIC_TC_SINGLE_CTA") == nullptr;
   if (pair_on && c->tc_kind == HESIC_TC_GENERIC && !planar && p.tma_store && p.BN == 128 && !p.w_resident &&
       num_sms >= 2 && p.kchunks * ntaps >= 8) {
     static PerDeviceOnce pair_once;
@@ -1180,7 +1184,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
     return HESIC_OK;
   }
   // first analysis layer (conv_tc_first.cuh): two tiles interleaved in the epilogue, one activation box per tile
-  static const bool first_on = getenv("HESIC_TC_NO_FIRST") == nullptr;
+  static const bool first_on = diag_env("HESIC_TC_NO_FIRST") == nullptr;
   if (first_on && c->tc_kind == HESIC_TC_ROW2 && p.gdn == 1 && p.w_resident && y->fmt == HESIC_FMT_NHWC_SPLIT && c->Cout == 128 &&
       p.tma_store && y->W >= FIRST_BW && y->H >= FIRST_BH) {
     static PerDeviceOnce first_once;
@@ -1231,7 +1235,7 @@ int conv_forward_tc(hesic_conv *c, const hesic_tensor *x, const hesic_tensor *y,
   }
   const int grid = std::min(p.n_tasks, num_sms);
   // fused GDN on a short K loop (the first analysis layer): 16 epilogue warps, 32 channels per thread
-  static const bool epi16_on = getenv("HESIC_TC_EPI8") == nullptr;
+  static const bool epi16_on = diag_env("HESIC_TC_EPI8") == nullptr;
   if (epi16_on && p.gdn && !planar && p.tma_store && y->fmt == HESIC_FMT_NHWC_SPLIT && p.BN == 128 && p.n_tiles == 1 &&
       p.stg_sets == 2 && c->Cout == 128) {
     conv_tc_kernel<16><<<grid, 64 + 32 * 16, smem_bytes, s>>>(ma_hi, ma_lo, m[0], m[1], m[2], m[3], my0, my1, p);

@@ -1135,7 +1135,7 @@ extern "C" int hesic_warp_perspective(const hesic_tensor *src, const float *M, c
     HESIC_LAUNCHED("warp_rgb_kernel");
     return HESIC_OK;
   }
-  static const int rows = getenv("HESIC_WARP_ROWS") ? atoi(getenv("HESIC_WARP_ROWS")) : 4;
+  static const int rows = diag_env("HESIC_WARP_ROWS") ? atoi(diag_env("HESIC_WARP_ROWS")) : 4;
   const int ty = 8 * (rows == 1 ? 1 : (rows == 2 ? 2 : 4));
   dim3 blk(32, 8), grid((dst->W + WARP_TILE - 1) / WARP_TILE, (dst->H + ty - 1) / ty, dst->B);
   if (rows == 1) warp_kernel<1><<<grid, blk, 0, as_stream(stream)>>>(view(src), M, view(dst), d2, align_corners);

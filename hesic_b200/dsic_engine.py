@@ -161,6 +161,8 @@ class DsicEngine(HesicEngine):
         N, M, K = m.N, m.M, m.K
         acc = torch.zeros(4, device=dev, dtype=torch.float64)
         self.log2_sums = acc
+        sse = torch.zeros(2, device=dev, dtype=torch.float64)   # squared errors of x1_hat / x2_hat, from the RGB heads' epilogues
+        self.sse_sums = sse
         a = lambda i: acc[i:i + 1]
         lv = [None] + [self._split(B, H >> s, W >> s, 3 * N) for s in (1, 2, 3, 3, 2, 1)]   # level buffers 1..6
         g = lambda k: C.split(lv[k], N, 2 * N)
@@ -185,7 +187,7 @@ class DsicEngine(HesicEngine):
         self._run(d1.g_s_conv1, y1h_d, B, Hy, Wy, "split", gdn=d1.g_s_gdn1, dst=(lv[4], 2 * N))
         self._run(d1.g_s_conv2, g(4), B, H >> 3, W >> 3, "split", gdn=d1.g_s_gdn2, dst=(lv[5], 2 * N))
         self._run(d1.g_s_conv3, g(5), B, H >> 2, W >> 2, "split", gdn=d1.g_s_gdn3, dst=(lv[6], 2 * N))
-        x1_hat, _, _, _ = self._run(d1.g_s_conv4, g(6), B, H >> 1, W >> 1, "nchw")
+        x1_hat, _, _, _ = self._run(d1.g_s_conv4, g(6), B, H >> 1, W >> 1, "nchw", sse=(C.nchw(x1), sse[0:1]))
 
         # ---- global context volumes from y1_hat (mynet6_plus.py:240-246) ------------------------------
         gc = m._global_context.global_net
@@ -227,7 +229,7 @@ class DsicEngine(HesicEngine):
         self._cost_volume(m._cost_volume5, lv[5], ctx, 1, B, H >> 2, W >> 2)
         self._run(m.pic2_g_s_conv3, wa(5), B, H >> 2, W >> 2, "split", gdn=m.pic2_g_s_gdn3, dst=(lv[6], N))
         self._cost_volume(m._cost_volume6, lv[6], ctx, 0, B, H >> 1, W >> 1)
-        x2_hat, _, _, _ = self._run(m.pic2_g_s_conv4, wa(6), B, H >> 1, W >> 1, "nchw")
+        x2_hat, _, _, _ = self._run(m.pic2_g_s_conv4, wa(6), B, H >> 1, W >> 1, "nchw", sse=(C.nchw(x2), sse[1:2]))
 
         self._end(main)
         return {"x1_hat": x1_hat, "x2_hat": x2_hat,

@@ -115,6 +115,7 @@ class CapturedForward:
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.outputs = run(*self.inputs)
                 self.log2_sums = engine.log2_sums
+                self.sse_sums = getattr(engine, "sse_sums", None)
             self.n_launches = int(_lib.hesic_launch_count(0)) - before
             # the graph owns these buffers for its whole life: take them out of the engine's per-forward list
             self._live, engine._live = engine._live, []
@@ -142,12 +143,12 @@ class HesicEngine(EngineBase):
         self.align_corners = align_corners
         self.path = path
         self.log2_sums = None
+        self.sse_sums = None
         # The view-2 analysis (warp of x1, pre_conv, encoder2, h_a2, bottleneck 2) does not depend on view 1 until
         # the conditioning buffer is assembled: it is enqueued on a side stream so that its HBM-bound kernels fill
-        # the gaps of view 1's tensor-core kernels (and vice versa).  HESIC_ONE_STREAM=1 disables the fork.
+        # the gaps of view 1's tensor-core kernels (and vice versa).  ``engine.two_streams = False`` disables the fork.
         self._side = {}
-        import os
-        self.two_streams = not os.environ.get("HESIC_ONE_STREAM")
+        self.two_streams = True
 
     def _side_stream(self, dev):
         s = self._side.get(dev)
@@ -164,10 +165,12 @@ class HesicEngine(EngineBase):
             plan.set_gdn(None, None, False)
         return plan
 
-    def _run(self, conv_mod, x_desc, B, H, W, kind, act=C.ACT_NONE, gdn=None, dst=None, xb_desc=None):
+    def _run(self, conv_mod, x_desc, B, H, W, kind, act=C.ACT_NONE, gdn=None, dst=None, xb_desc=None, sse=None):
         """Convolve and return (tensor, descriptor).  kind: 'split' | 'nhwc' | 'nchw' | 'rowpad'.
         dst=(tensor, c0) writes a channel slice of an existing concat buffer of that kind;
-        xb_desc: the input is cat((x, xb), 1), never materialised."""
+        xb_desc: the input is cat((x, xb), 1), never materialised;
+        sse=(target_desc, acc): the layer emits a reconstruction, its squared error against the target image is
+        accumulated in the same epilogue."""
         plan = self._plan(conv_mod, gdn)
         Ho, Wo = plan.out_hw(H, W)
         Cout = plan.geom[1]
@@ -178,7 +181,7 @@ class HesicEngine(EngineBase):
             c0 = 0
             t = {"split": self._split, "nhwc": self._nhwc}[kind](B, Ho, Wo, Cout) if kind != "nchw" else self._nchw(B, Cout, Ho, Wo)
         d = {"split": C.split, "nhwc": C.nhwc, "nchw": C.nchw, "rowpad": C.rowpad}[kind](t, Cout, c0)
-        plan.run(x_desc, d, act, self.path, xb_desc)
+        plan.run(x_desc, d, act, self.path, xb_desc, sse)
         return t, d, Ho, Wo
 
     def _rowpad_buf(self, slot, B, H, W, slots=4):
@@ -217,12 +220,12 @@ class HesicEngine(EngineBase):
         y, d, H, W = self._run(enc.g_a_conv4, d, B, H, W, "nhwc")
         return y, d, H, W
 
-    def _synthesis(self, dec, y_desc, B, H, W, last_kind="nchw", last_gdn=None, last_dst=None):
+    def _synthesis(self, dec, y_desc, B, H, W, last_kind="nchw", last_gdn=None, last_dst=None, last_sse=None):
         """Decoder1 / the g_s part of Decoder2 (newnet1.py:603-624)."""
         _, d, H, W = self._run(dec.g_s_conv1, y_desc, B, H, W, "split", gdn=dec.g_s_gdn1)
         _, d, H, W = self._run(dec.g_s_conv2, d, B, H, W, "split", gdn=dec.g_s_gdn2)
         _, d, H, W = self._run(dec.g_s_conv3, d, B, H, W, "split", gdn=dec.g_s_gdn3)
-        return self._run(dec.g_s_conv4, d, B, H, W, last_kind, gdn=last_gdn, dst=last_dst)
+        return self._run(dec.g_s_conv4, d, B, H, W, last_kind, gdn=last_gdn, dst=last_dst, sse=last_sse)
 
     def _seq3(self, seq, idx, acts, x_desc, B, H, W, last_kind, last_dst=None):
         """Three-layer nn.Sequential (conv/deconv at ``idx``) with activations ``acts``."""
@@ -292,6 +295,10 @@ class HesicEngine(EngineBase):
         M, K = m.M, m.K
         acc = torch.zeros(4, device=dev, dtype=torch.float64)  # sum log2 p: y1, y2, z1, z2
         self.log2_sums = acc
+        # sum of squared errors of the two reconstructions against the inputs (the MSE terms of RateDistortionLoss,
+        # test3real.py:99-111), accumulated by the epilogues that store x1_hat / x2_hat
+        sse = torch.zeros(2, device=dev, dtype=torch.float64)
+        self.sse_sums = sse
         a = lambda i: acc[i:i + 1]
         joint = self.variant == "joint"
 
@@ -344,7 +351,7 @@ class HesicEngine(EngineBase):
             _, m_d, _, _ = self._seq3(hs.gmm_means, (0, 2, 4), (C.ACT_LEAKY, C.ACT_LEAKY, C.ACT_NONE), z1h_d, B, Hz, Wz, "nhwc")
             w1 = self._mixture_head(hs.gmm_weights, z1h_d, B, Hz, Wz, K, M)
             y1_hat, y1_lik, y1h_split_d = self._gmm(m.gaussian1, y1_d, s_d, m_d, w1, B, Hy, Wy, M, K, a(0))
-        x1_hat, _, _, _ = self._synthesis(m.decoder1, y1h_split_d, B, Hy, Wy)
+        x1_hat, _, _, _ = self._synthesis(m.decoder1, y1h_split_d, B, Hy, Wy, last_sse=(C.nchw(x1), sse[0:1]))
 
         x1hw_d = C.nchw(cat_out, 3, 3)
         x1hw_rp = None
@@ -390,7 +397,7 @@ class HesicEngine(EngineBase):
             co_d = self._rowpad("cat_out", C.nchw(cat_out), B, 6, H, W)
         else:
             co_d = C.nchw(cat_out)     # CUDA-core stencil reads the NCHW concatenation buffer directly
-        x2_hat, _, _, _ = self._run(dec2.after_conv, co_d, B, H, W, "nchw")
+        x2_hat, _, _, _ = self._run(dec2.after_conv, co_d, B, H, W, "nchw", sse=(C.nchw(x2), sse[1:2]))
 
         out = {"x1_hat": x1_hat, "x2_hat": x2_hat}
         if self.variant != "newnet9":

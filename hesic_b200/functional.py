@@ -107,9 +107,13 @@ class ConvPlan:
             return (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
         return (H - 1) * s - 2 * p + kh + op, (W - 1) * s - 2 * p + kw + op
 
-    def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO, xb_desc=None):
-        """xb_desc: second part of a channel concatenation (torch.cat((x, xb), 1) on the reference side)."""
-        if xb_desc is not None:
+    def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO, xb_desc=None, sse=None):
+        """xb_desc: second part of a channel concatenation (torch.cat((x, xb), 1) on the reference side).
+        sse = (target_desc, acc): also add sum((y - target)^2) to the fp64 device scalar ``acc`` (hesic_conv_forward_sse)."""
+        if sse is not None:
+            C.check(_lib.hesic_conv_forward_sse(self.h, C.ref(x_desc), C.ref(xb_desc) if xb_desc is not None else None,
+                                                C.ref(y_desc), act, path, C.ref(sse[0]), C.ptr(sse[1]), C.stream()))
+        elif xb_desc is not None:
             C.check(_lib.hesic_conv_forward_cat(self.h, C.ref(x_desc), C.ref(xb_desc), C.ref(y_desc), act, path, C.stream()))
         else:
             C.check(_lib.hesic_conv_forward(self.h, C.ref(x_desc), C.ref(y_desc), act, path, C.stream()))

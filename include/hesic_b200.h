@@ -108,6 +108,13 @@ int hesic_conv_forward(hesic_conv *c, const hesic_tensor *x, const hesic_tensor 
  * full-resolution few-channel k5 s1 layers only (else HESIC_E_UNSUPPORTED). */
 int hesic_conv_forward_cat(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y,
                            int act, int path, void *stream);
+/* The layers that emit a reconstruction (decoder1.g_s_conv4 -> x1_hat, newnet1.py:612; decoder2.after_conv -> x2_hat,
+ * :686), with the MSE partial of RateDistortionLoss (ywz/mywork/test3real.py:99-111) taken from the same epilogue:
+ * *sse += sum((y - target)^2) in fp64, y and target NCHW fp32 of one shape; xb may be NULL (no concatenation).  The RGB
+ * synthesis head and the full-resolution stencil accumulate it from the registers they store from; any other layer
+ * runs hesic_sum_squared_error on the written output (same result to fp64 rounding). */
+int hesic_conv_forward_sse(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y,
+                           int act, int path, const hesic_tensor *target, double *sse, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Enhancement network layers (Independent_EN, ywz/mywork/newnet1.py:272-311,1278-1300; ResidualBlock,

@@ -57,6 +57,11 @@ def test_forward_small_vs_reference_fixture(name, modname):
     for i, k in enumerate(("y1", "y2", "z1", "z2")):
         direct = float(torch.log2(out["likelihoods"][k].double()).sum())
         assert math.isclose(float(sums[i]), direct, rel_tol=1e-5, abs_tol=1e-3), k
+    # fused squared-error sums (epilogues of the layers that store x1_hat / x2_hat) agree with the images they summarise
+    sse = net.hesic_engine.sse_sums.cpu()
+    for i, (k, x) in enumerate((("x1_hat", x1), ("x2_hat", x2))):
+        direct = float(((out[k].cpu() - x).double() ** 2).sum())     # fp32 difference, fp64 square and sum
+        assert math.isclose(float(sse[i]), direct, rel_tol=1e-11), k
 
 
 @pytest.mark.parametrize("name,modname", [("hsic_newnet1", "newnet1"), ("hsic_joint", "newnet1_joint")])

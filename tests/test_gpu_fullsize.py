@@ -125,8 +125,11 @@ def test_sharded_reduction_matches_the_oracle_of_the_whole_batch():
         out = net(a1, a2, ah)
         partial = torch.zeros(6, device=DEV, dtype=torch.float64)
         partial[:4].copy_(net.hesic_engine.log2_sums)
-        F.sum_squared_error(out["x1_hat"], a1, partial[4:5])
-        F.sum_squared_error(out["x2_hat"], a2, partial[5:6])
+        partial[4:].copy_(net.hesic_engine.sse_sums)            # accumulated by the epilogues that store x1_hat / x2_hat
+        check = torch.zeros(2, device=DEV, dtype=torch.float64)
+        F.sum_squared_error(out["x1_hat"], a1, check[0:1])
+        F.sum_squared_error(out["x2_hat"], a2, check[1:2])
+        assert torch.allclose(partial[4:], check, rtol=1e-11, atol=0)
         total += sharding.reduce_partials(partial).cpu()        # world size 1 here: the sum over ranks is the loop
     got = sharding.metrics_from_partials(total, n, 512, 512)
     ref = _oracle_batched(O.hsic_forward, sd, x1, x2, h)
@@ -149,6 +152,9 @@ def test_dsic_at_512_vs_oracle():
         ref = O.dsic_forward(sd, x1, x2, taps=taps)
     out = _cpu(net(x1.to(DEV), x2.to(DEV)))
     C.check(C.lib.hesic_tc_status())
+    sse = net.hesic_engine.sse_sums.cpu()        # from the epilogues of the two RGB heads (128 and 256 input channels)
+    for i, (k, x) in enumerate((("x1_hat", x1), ("x2_hat", x2))):
+        assert math.isclose(float(sse[i]), float(((out[k] - x).double() ** 2).sum()), rel_tol=1e-11), k
     m, r = synth.rd_metrics(out, x1, x2), synth.rd_metrics(ref, x1, x2)
     l2 = {k: _rel_l2(out[k], ref[k]) for k in ("x1_hat", "x2_hat")}
     rel = {k: abs(m[k] - r[k]) / abs(r[k]) for k in ("bpp", "bpp1", "bpp2")}
@@ -212,6 +218,7 @@ def test_cuda_graph_replay_equals_eager():
     eager = net(y1, y2, g)
     eager = {k: v.clone() for k, v in eager.items() if k != "likelihoods"} | {k: v.clone() for k, v in eager["likelihoods"].items()}
     sums = net.hesic_engine.log2_sums.clone()
+    sse = net.hesic_engine.sse_sums.clone()
     C.lib.hesic_launch_count(1)
     out = cap.replay(y1, y2, g)
     torch.cuda.synchronize()
@@ -221,6 +228,7 @@ def test_cuda_graph_replay_equals_eager():
     for k in ("y1", "y2", "z1", "z2"):
         assert torch.equal(out["likelihoods"][k], eager[k]), k
     assert torch.allclose(cap.log2_sums, sums, rtol=1e-12)
+    assert torch.allclose(cap.sse_sums, sse, rtol=1e-12)
     # and again on the first inputs: the graph is reusable, the engine still runs eagerly afterwards
     out = cap.replay(x1, x2, h)
     again = net(x1, x2, h)

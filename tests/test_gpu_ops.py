@@ -114,6 +114,65 @@ def test_few_channel_stencil_cat_gdn_rowpad(size, transposed, slots):
     plan.set_gdn(None, None, False)
 
 
+@pytest.mark.parametrize("kind", ["head", "stencil", "stencil_cat", "other_layer"])
+@pytest.mark.parametrize("size", [(2, 16, 16), (3, 7, 5), (1, 20, 36)])
+def test_squared_error_fused_into_the_reconstruction_layers(kind, size):
+    """hesic_conv_forward_sse: the layers that store x1_hat / x2_hat (RGB synthesis head, newnet1.py:612; after_conv, :686)
+    also accumulate sum((y - target)^2) -- the MSE partial of RateDistortionLoss (test3real.py:99-111) -- from the registers
+    they store from.  Checked against the separate squared-error kernel on the written output and against a float64 sum on
+    the host; the output itself must not change; a layer without the fused epilogue falls back to the kernel."""
+    from hesic_b200 import _capi as C
+    from hesic_b200 import functional as F
+    from compressai.models.utils import conv, deconv
+    B, H, W = size
+    if kind == "head":
+        mod = deconv(128, 3, kernel_size=5, stride=2)
+        scale, Hi, Wi = (2.0 / (128 * 25 / 4)) ** 0.5, H, W
+        Ho, Wo = 2 * H, 2 * W
+    elif kind == "other_layer":
+        mod = conv(16, 3, kernel_size=3, stride=1)      # CUDA-core generic path: no fused epilogue
+        scale, Hi, Wi, Ho, Wo = 0.1, H, W, H, W
+    else:
+        mod = deconv(6 if kind == "stencil_cat" else 3, 3, kernel_size=5, stride=1)
+        scale, Hi, Wi, Ho, Wo = 0.1, 2 * H + 1, 2 * W + 3, 2 * H + 1, 2 * W + 3   # odd sizes: scalar tails of the stores
+    Cin = mod.weight.shape[0] if kind != "other_layer" else 16
+    mod.load_state_dict({"weight": _rand(tuple(mod.weight.shape), 31, scale), "bias": _rand((3,), 32, 0.1)})
+    mod = mod.to(DEV)
+    plan = mod.hesic_plan()
+    plan.set_gdn(None, None, False)
+    x = _rand((B, Cin, Hi, Wi), 33).to(DEV)
+    target = torch.zeros((B, 5, Ho, Wo), device=DEV)          # the target as a channel slice of a wider tensor
+    target[:, 1:4] = _rand((B, 3, Ho, Wo), 34).to(DEV)
+    tgt_d = C.nchw(target, 3, 1)
+    if kind == "head":
+        xs = torch.empty((2, B, Hi, Wi, 128), device=DEV, dtype=torch.bfloat16)
+        C.check(C.lib.hesic_convert(C.ref(C.nchw(x)), C.ref(C.split(xs)), C.OP_COPY, C.stream()))
+        xd, xb, path = C.split(xs), None, C.PATH_TC
+    elif kind == "stencil_cat":
+        xa_t, xb_t = x[:, :3].contiguous(), x[:, 3:].contiguous()
+        xd, xb, path = C.nchw(xa_t), C.nchw(xb_t), C.PATH_AUTO
+    else:
+        xd, xb, path = C.nchw(x), None, C.PATH_AUTO
+    plain = torch.empty((B, 3, Ho, Wo), device=DEV)
+    plan.run(xd, C.nchw(plain), C.ACT_NONE, path, xb)
+    out = torch.empty((B, 3, Ho, Wo), device=DEV)
+    acc = torch.full((1,), 5.0, device=DEV, dtype=torch.float64)      # accumulates: starts from a non-zero value
+    launches0 = C.lib.hesic_launch_count(0)
+    plan.run(xd, C.nchw(out), C.ACT_NONE, path, xb, sse=(tgt_d, acc))
+    n_launch = C.lib.hesic_launch_count(0) - launches0
+    assert n_launch == (2 if kind == "other_layer" else 1), "fused layers must not launch the squared-error kernel"
+    assert torch.equal(out, plain)
+    sep = torch.zeros(1, device=DEV, dtype=torch.float64)
+    C.check(C.lib.hesic_sum_squared_error(C.ref(C.nchw(out)), C.ref(tgt_d), C.ptr(sep), C.stream()))
+    host = float(((out - target[:, 1:4]).double() ** 2).sum())           # fp32 difference, fp64 square and sum
+    got = float(acc) - 5.0
+    assert abs(got - float(sep)) <= 1e-11 * host and abs(got - host) <= 1e-11 * host, (got, float(sep), host)
+    # error behaviour: a target of another shape is rejected before anything is launched
+    bad = torch.zeros((B, 3, Ho + 1, Wo), device=DEV)
+    with pytest.raises(ValueError):
+        plan.run(xd, C.nchw(out), C.ACT_NONE, path, xb, sse=(C.nchw(bad), acc))
+
+
 @pytest.mark.parametrize("size", [(2, 16, 16), (3, 7, 5), (1, 20, 36), (1, 64, 64)])
 @pytest.mark.parametrize("igdn", [False, True])
 def test_rgb_head_scatter_form(size, igdn):

@@ -35,10 +35,10 @@ orig_run = F.ConvPlan.run
 orig_init = F.ConvPlan.__init__
 
 
-def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO, xb_desc=None):
+def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO, xb_desc=None, sse=None):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    orig_run(self, x_desc, y_desc, act, path, xb_desc)
+    orig_run(self, x_desc, y_desc, act, path, xb_desc, sse)
     e.record()
     note(self, y_desc, s, e, "")
 

@@ -29,6 +29,7 @@ mod = __import__("newnet1_joint" if model == "hesic_plus" else "newnet1")
 net = mod.HSIC(128, 192, 5).eval()
 net.load_state_dict(synth.synth_state_dict(net, seed=0))
 net = net.to(dev)
+net.hesic_engine.two_streams = False     # one stream: the per-call events then bracket exactly one kernel
 x1, x2, h = (t.to(dev) for t in synth.stereo_pairs(B, 512, 512, seed=1234))
 
 for _ in range(2):
@@ -64,13 +65,13 @@ def tdesc(ref):
 orig_run = F.ConvPlan.run
 
 
-def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO, xb_desc=None):
+def run(self, x_desc, y_desc, act=C.ACT_NONE, path=C.PATH_AUTO, xb_desc=None, sse=None):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    orig_run(self, x_desc, y_desc, act, path, xb_desc)
+    orig_run(self, x_desc, y_desc, act, path, xb_desc, sse)
     e.record()
     Cin, Cout, kh, kw, st, p, tr, op = self.geom
-    gdn = "+gdn" if self._gdn_key is not None else ""
+    gdn = ("+gdn" if self._gdn_key is not None else "") + ("+sse" if sse is not None else "")
     fl = 2.0 * y_desc.B * y_desc.H * y_desc.W * Cout * Cin * kh * kw / (st * st if tr else 1)
     records.append((f"{'deconv' if tr else 'conv'} {Cin}->{Cout} k{kh} s{st}{gdn} out {y_desc.H}x{y_desc.W} "
                     f"{('nchw', 'nhwc', 'split', 'rowpad')[y_desc.fmt]}", s, e, fl))
