@@ -583,9 +583,9 @@ def run_extras(args, dev, build, call, timed, C, F, synth, sets, net, model):
         out3 = torch.empty((Bk, 3, H, Wd), device=dev)
         run("deconv 128->3 k5 s2 + IGDN (conv_head_kernel)", 4 * Bk * ((H // 2) * (Wd // 2) * 128 + H * Wd * 3),
             lambda: p2.run(C.split(y1), C.nchw(out3), C.ACT_NONE, C.PATH_TC), "newnet1.py:606-624,669-670")
-        # the same launch with the squared error against a target image taken from its epilogue (x1_hat vs x1 in the forward)
+        # hesic_conv_forward_sse on this layer (x1_hat vs x1 in the forward): the head + the squared-error kernel, two launches
         acc_f = torch.zeros(1, device=dev, dtype=torch.float64)
-        run("deconv 128->3 k5 s2 + IGDN + squared error vs target (conv_head_kernel)",
+        run("deconv 128->3 k5 s2 + IGDN + squared error vs target (conv_head_kernel, sse_dense_kernel)",
             4 * Bk * ((H // 2) * (Wd // 2) * 128 + 2 * H * Wd * 3),
             lambda: p2.run(C.split(y1), C.nchw(out3), C.ACT_NONE, C.PATH_TC, None, (C.nchw(x2), acc_f)), "newnet1.py:612 + test3real.py:99-111")
         p2.set_gdn(None, None, False)
@@ -600,7 +600,7 @@ def run_extras(args, dev, build, call, timed, C, F, synth, sets, net, model):
         p4 = l4.hesic_plan()
         p4.set_gdn(None, None, False)
         x3 = img()
-        run("deconv 6->3 k5 s1 on cat + squared error vs target (conv_small_kernel)", 4 * Bk * H * Wd * 12,
+        run("deconv 6->3 k5 s1 on cat + squared error vs target in the epilogue (conv_small_kernel)", 4 * Bk * H * Wd * 12,
             lambda: p4.run(C.nchw(x1), C.nchw(out3), C.ACT_NONE, C.PATH_AUTO, C.nchw(x2), (C.nchw(x3), acc_f)),
             "newnet1.py:686 + test3real.py:99-111")
         # warp

@@ -35,11 +35,6 @@ struct HParams {
   int gdn;                 // 0 none, 1 GDN, 2 inverse GDN over the Cout channels (registers)
   const float *beta, *gamma;
   int act;
-  // squared error against a target image (MSE partial of RateDistortionLoss, test3real.py:99-111) accumulated from the
-  // registers the output is stored from; null: off.  One fp64 atomic per epilogue warp at the end of the kernel.
-  const float *target;
-  int tgt_Cs;
-  double *sse;
 };
 
 __device__ __forceinline__ void epi_bar_head() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
@@ -153,7 +148,6 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
       for (int j = 0; j < COUT; ++j) gam[j][c] = p.gdn ? __ldg(p.gamma + j * COUT + c) : 0.f;
     }
-    double se = 0.0;
     int lt = 0;
     for (int task = blockIdx.x; task < p.n_tasks; task += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -229,24 +223,8 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           float *dst = p.y + (((size_t)b * p.out_Cs + c) * Ho + oy) * Wo + ox;
           if ((((uintptr_t)dst) & 7u) == 0) *reinterpret_cast<float2 *>(dst) = make_float2(o[0][c], o[1][c]);
           else { dst[0] = o[0][c]; dst[1] = o[1][c]; }
-          if (p.sse) {
-            const float *tg = p.target + (((size_t)b * p.tgt_Cs + c) * Ho + oy) * Wo + ox;
-            float t0, t1;
-            if ((((uintptr_t)tg) & 7u) == 0) {
-              const float2 q = __ldg(reinterpret_cast<const float2 *>(tg));
-              t0 = q.x; t1 = q.y;
-            } else {
-              t0 = __ldg(tg); t1 = __ldg(tg + 1);
-            }
-            const float d0 = o[0][c] - t0, d1 = o[1][c] - t1;
-            se += (double)d0 * (double)d0 + (double)d1 * (double)d1;
-          }
         }
       }
-    }
-    if (p.sse) {
-      se = warp_sum(se);
-      if (lane == 0) atomicAdd(p.sse, se);
     }
   }
 

@@ -577,9 +577,8 @@ extern "C" int hesic_conv_forward_cat(hesic_conv *c, const hesic_tensor *xa, con
 }
 
 // Convolution whose NCHW fp32 output is a reconstruction compared with a target image (the MSE term of RateDistortionLoss,
-// ywz/mywork/test3real.py:99-111): *sse += sum((y - target)^2) -- in the epilogue of the kernels that produce the images
-// (RGB synthesis head, full-resolution stencil: the output is still in registers, no second pass over it), else with the
-// squared-error kernel.
+// ywz/mywork/test3real.py:99-111): *sse += sum((y - target)^2) -- in the epilogue of the full-resolution stencil (the
+// output is still in registers, no second pass over it), else with the squared-error kernel on the written image.
 extern "C" int hesic_conv_forward_sse(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y, int act,
                                       int path, const hesic_tensor *target, double *sse, void *stream) {
   HESIC_REQUIRE(c && y && target && sse, "hesic_conv_forward_sse: null argument");

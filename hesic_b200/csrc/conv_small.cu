@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ 
     const int ox = x0 + 4 * tx;
     if (ox >= a.W) continue;
     if (a.out_fmt == HESIC_FMT_NCHW_F32) {
+      float se_row = 0.f;
 #pragma unroll
       for (int c = 0; c < COUT; ++c) {
         float *dst = (float *)a.y0 + (((size_t)b * a.out_Cs + c) * a.H + oy) * a.W + ox;
@@ -211,10 +212,11 @@ __global__ void __launch_bounds__(NT) conv_small_kernel(const __grid_constant__ 
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const float d = o[c][p] - t[p];
-            se += (double)d * (double)d;
+            se_row = fmaf(d, d, se_row);
           }
         }
       }
+      se += (double)se_row;   // fp32 over the row's 4 * COUT squares, fp64 across rows and threads
     } else {   // ROWPAD split: one store of all channel slots per pixel and plane
       TView yv;
       yv.p0 = a.y0; yv.p1 = a.y1; yv.fmt = HESIC_FMT_ROWPAD8_SPLIT; yv.B = a.B; yv.C = COUT; yv.H = a.H; yv.W = a.W; yv.Cs = a.out_Cs;

@@ -930,10 +930,11 @@ static int launch_head(hesic_conv *c, const hesic_tensor *x, const hesic_tensor 
   p.bias = c->bias; p.act = act;
   p.gdn = c->has_gdn ? (c->gdn_inverse ? 2 : 1) : 0;
   p.beta = c->gdn_beta; p.gamma = c->gdn_w_simt;
-  if (c->sse_acc) {
-    p.target = c->sse_target; p.tgt_Cs = c->sse_Cs; p.sse = c->sse_acc;
-    c->sse_fused = true;
-  }
+  // hesic_conv_forward_sse: NOT fused here (c->sse_fused stays false, the caller runs the squared-error kernel on the
+  // written image).  Measured r04, 16 x 3 x 512 x 512: this kernel 124.5 us + sse_dense_kernel 27 us, against 172-183 us
+  // with the target read and the squares in this epilogue (whether the target values were fetched where they are used,
+  // at the top of the tile, or one tile ahead): the epilogue is what bounds this kernel, and its 14-pixel-wide tile rows
+  // make the extra loads as expensive as its stores.
   const int fixed = 1024 + 256 + p.kchunks * 2 * p.NPAD * 128 + BM * (p.NPAD + 1) * 4;
   p.stages = std::min(8, (SMEM_LIMIT - fixed) / head::STAGE_BYTES);
   if (p.stages < 2) { set_error("conv head: operands do not fit shared memory"); return HESIC_E_UNSUPPORTED; }

@@ -110,9 +110,10 @@ int hesic_conv_forward_cat(hesic_conv *c, const hesic_tensor *xa, const hesic_te
                            int act, int path, void *stream);
 /* The layers that emit a reconstruction (decoder1.g_s_conv4 -> x1_hat, newnet1.py:612; decoder2.after_conv -> x2_hat,
  * :686), with the MSE partial of RateDistortionLoss (ywz/mywork/test3real.py:99-111) taken from the same epilogue:
- * *sse += sum((y - target)^2) in fp64, y and target NCHW fp32 of one shape; xb may be NULL (no concatenation).  The RGB
- * synthesis head and the full-resolution stencil accumulate it from the registers they store from; any other layer
- * runs hesic_sum_squared_error on the written output (same result to fp64 rounding). */
+ * *sse += sum((y - target)^2) in fp64, y and target NCHW fp32 of one shape; xb may be NULL (no concatenation).  The
+ * full-resolution stencil (after_conv) accumulates it from the registers it stores from; the RGB synthesis head (measured
+ * slower with the target read in its epilogue) and any other layer run hesic_sum_squared_error on the written output
+ * (same result to 1e-7 relative: the stencil sums the 12 squares of a store group in fp32 before the fp64 accumulator). */
 int hesic_conv_forward_sse(hesic_conv *c, const hesic_tensor *xa, const hesic_tensor *xb, const hesic_tensor *y,
                            int act, int path, const hesic_tensor *target, double *sse, void *stream);
 

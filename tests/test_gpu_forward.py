@@ -61,7 +61,7 @@ def test_forward_small_vs_reference_fixture(name, modname):
     sse = net.hesic_engine.sse_sums.cpu()
     for i, (k, x) in enumerate((("x1_hat", x1), ("x2_hat", x2))):
         direct = float(((out[k].cpu() - x).double() ** 2).sum())     # fp32 difference, fp64 square and sum
-        assert math.isclose(float(sse[i]), direct, rel_tol=1e-11), k
+        assert math.isclose(float(sse[i]), direct, rel_tol=1e-7), k
 
 
 @pytest.mark.parametrize("name,modname", [("hsic_newnet1", "newnet1"), ("hsic_joint", "newnet1_joint")])

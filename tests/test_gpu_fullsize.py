@@ -129,7 +129,7 @@ def test_sharded_reduction_matches_the_oracle_of_the_whole_batch():
         check = torch.zeros(2, device=DEV, dtype=torch.float64)
         F.sum_squared_error(out["x1_hat"], a1, check[0:1])
         F.sum_squared_error(out["x2_hat"], a2, check[1:2])
-        assert torch.allclose(partial[4:], check, rtol=1e-11, atol=0)
+        assert torch.allclose(partial[4:], check, rtol=1e-8, atol=0)
         total += sharding.reduce_partials(partial).cpu()        # world size 1 here: the sum over ranks is the loop
     got = sharding.metrics_from_partials(total, n, 512, 512)
     ref = _oracle_batched(O.hsic_forward, sd, x1, x2, h)
@@ -154,7 +154,7 @@ def test_dsic_at_512_vs_oracle():
     C.check(C.lib.hesic_tc_status())
     sse = net.hesic_engine.sse_sums.cpu()        # from the epilogues of the two RGB heads (128 and 256 input channels)
     for i, (k, x) in enumerate((("x1_hat", x1), ("x2_hat", x2))):
-        assert math.isclose(float(sse[i]), float(((out[k] - x).double() ** 2).sum()), rel_tol=1e-11), k
+        assert math.isclose(float(sse[i]), float(((out[k] - x).double() ** 2).sum()), rel_tol=1e-8), k
     m, r = synth.rd_metrics(out, x1, x2), synth.rd_metrics(ref, x1, x2)
     l2 = {k: _rel_l2(out[k], ref[k]) for k in ("x1_hat", "x2_hat")}
     rel = {k: abs(m[k] - r[k]) / abs(r[k]) for k in ("bpp", "bpp1", "bpp2")}

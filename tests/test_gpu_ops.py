@@ -160,13 +160,18 @@ def test_squared_error_fused_into_the_reconstruction_layers(kind, size):
     launches0 = C.lib.hesic_launch_count(0)
     plan.run(xd, C.nchw(out), C.ACT_NONE, path, xb, sse=(tgt_d, acc))
     n_launch = C.lib.hesic_launch_count(0) - launches0
-    assert n_launch == (2 if kind == "other_layer" else 1), "fused layers must not launch the squared-error kernel"
+    # the stencil accumulates in its own epilogue; the RGB head (measured slower fused, conv_tc.cu launch_head) and any
+    # other layer run the squared-error kernel on the written image
+    assert n_launch == (1 if kind.startswith("stencil") else 2)
     assert torch.equal(out, plain)
     sep = torch.zeros(1, device=DEV, dtype=torch.float64)
     C.check(C.lib.hesic_sum_squared_error(C.ref(C.nchw(out)), C.ref(tgt_d), C.ptr(sep), C.stream()))
     host = float(((out - target[:, 1:4]).double() ** 2).sum())           # fp32 difference, fp64 square and sum
     got = float(acc) - 5.0
-    assert abs(got - float(sep)) <= 1e-11 * host and abs(got - host) <= 1e-11 * host, (got, float(sep), host)
+    # the stencil sums the 12 squares of one store group in fp32 before they enter the fp64 accumulator (each partial within
+    # 12 * 2^-24 of exact, the total far closer): one F32 -> F64 conversion per group (16 per clock per SM on B200,
+    # tools/micro/dfma_rate.cu)
+    assert abs(got - float(sep)) <= 2e-7 * host and abs(got - host) <= 2e-7 * host, (got, float(sep), host)
     # error behaviour: a target of another shape is rejected before anything is launched
     bad = torch.zeros((B, 3, Ho + 1, Wo), device=DEV)
     with pytest.raises(ValueError):
