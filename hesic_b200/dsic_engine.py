@@ -180,9 +180,10 @@ class DsicEngine(HesicEngine):
         z1, z1_d, Hz, Wz = self._seq3(m._h_a1.encode_hyper, (0, 2, 4), (R, R, C.ACT_NONE), C.split(y1_abs), B, Hy, Wy, "nhwc")
         z1_hat, z1h_d, z1_lik = self._bottleneck(m.entropy_bottleneck1, z1, z1_d, B, Hz, Wz, a(2))
         hs = m._h_s1
-        _, s_d, _, _ = self._seq3(hs.gmm_sigma, (0, 2, 4), (R, R, R), z1h_d, B, Hz, Wz, "nhwc")
-        _, m_d, _, _ = self._seq3(hs.gmm_means, (0, 2, 4), (L, L, C.ACT_NONE), z1h_d, B, Hz, Wz, "nhwc")
-        w1 = self._mixture_head(hs.gmm_weights, z1h_d, B, Hz, Wz, K, M)
+        (_, s_d, _, _), (_, m_d, _, _), w1 = self._branches(
+            lambda: self._seq3(hs.gmm_sigma, (0, 2, 4), (R, R, R), z1h_d, B, Hz, Wz, "nhwc"),
+            lambda: self._seq3(hs.gmm_means, (0, 2, 4), (L, L, C.ACT_NONE), z1h_d, B, Hz, Wz, "nhwc"),
+            lambda: self._mixture_head(hs.gmm_weights, z1h_d, B, Hz, Wz, K, M))
         y1_hat, y1_lik, y1h_d = self._gmm(m.gaussian1, y1_d, s_d, m_d, w1, B, Hy, Wy, M, K, a(0))
         self._run(d1.g_s_conv1, y1h_d, B, Hy, Wy, "split", gdn=d1.g_s_gdn1, dst=(lv[4], 2 * N))
         self._run(d1.g_s_conv2, g(4), B, H >> 3, W >> 3, "split", gdn=d1.g_s_gdn2, dst=(lv[5], 2 * N))

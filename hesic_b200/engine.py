@@ -149,12 +149,44 @@ class HesicEngine(EngineBase):
         # the gaps of view 1's tensor-core kernels (and vice versa).  ``engine.two_streams = False`` disables the fork.
         self._side = {}
         self.two_streams = True
+        self.branch_streams = True     # independent branches of the hyper path side by side (_branches)
 
     def _side_stream(self, dev):
         s = self._side.get(dev)
         if s is None:
             s = self._side[dev] = torch.cuda.Stream(device=dev)
         return s
+
+    def _branches(self, *fns):
+        """Independent sub-graphs side by side: fns[0] on the current stream, the others on auxiliary streams forked from it
+        and joined back.  Used for the three branches (sigma, means, weights) of gmm_hyper_y1 / gmm_hyper_y2
+        (newnet1.py:456-514, 517-577) and for the hyper path beside the context model of HESIC+: the stride-2 transposed
+        convs at 8 x 8 and 16 x 16 are 16-32 tiles for 148 SMs and last ~23 us each whatever their size (a chain of L2 -> SM
+        fills), so five of them in a row cost 113 us on one stream and the time of two when the branches overlap.  Measured
+        r04 in bursts from an idle GPU (tools/time_forward.py, 16 pairs): HESIC 6.18 -> 6.04 ms, HESIC+ 5.34 -> 5.26 ms; in a
+        loop that has reached the 1 kW power cap the governor's clock, not the schedule, sets the time."""
+        cur = torch.cuda.current_stream(self.dev)
+        if not self.branch_streams or len(fns) < 2:
+            return [f() for f in fns]
+        res = [None] * len(fns)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        ends = []
+        for i in range(1, len(fns)):
+            key = (self.dev, i)
+            aux = self._side.get(key)
+            if aux is None:
+                aux = self._side[key] = torch.cuda.Stream(device=self.dev)
+            aux.wait_event(fork)
+            with torch.cuda.stream(aux):
+                res[i] = fns[i]()
+                e = torch.cuda.Event()
+                e.record(aux)
+            ends.append(e)
+        res[0] = fns[0]()
+        for e in ends:
+            cur.wait_event(e)
+        return res
 
     # ---- helpers -------------------------------------------------------------------------
     def _plan(self, conv_mod, gdn_mod=None):
@@ -347,9 +379,10 @@ class HesicEngine(EngineBase):
                                           C.split(y1_abs), B, Hy, Wy, "nhwc")
             z1_hat, z1h_d, z1_lik = self._bottleneck(m.entropy_bottleneck1, z1, z1_d, B, Hz, Wz, a(2))
             hs = m._h_s1
-            _, s_d, _, _ = self._seq3(hs.gmm_sigma, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_RELU), z1h_d, B, Hz, Wz, "nhwc")
-            _, m_d, _, _ = self._seq3(hs.gmm_means, (0, 2, 4), (C.ACT_LEAKY, C.ACT_LEAKY, C.ACT_NONE), z1h_d, B, Hz, Wz, "nhwc")
-            w1 = self._mixture_head(hs.gmm_weights, z1h_d, B, Hz, Wz, K, M)
+            (_, s_d, _, _), (_, m_d, _, _), w1 = self._branches(
+                lambda: self._seq3(hs.gmm_sigma, (0, 2, 4), (C.ACT_RELU, C.ACT_RELU, C.ACT_RELU), z1h_d, B, Hz, Wz, "nhwc"),
+                lambda: self._seq3(hs.gmm_means, (0, 2, 4), (C.ACT_LEAKY, C.ACT_LEAKY, C.ACT_NONE), z1h_d, B, Hz, Wz, "nhwc"),
+                lambda: self._mixture_head(hs.gmm_weights, z1h_d, B, Hz, Wz, K, M))
             y1_hat, y1_lik, y1h_split_d = self._gmm(m.gaussian1, y1_d, s_d, m_d, w1, B, Hy, Wy, M, K, a(0))
         x1_hat, _, _, _ = self._synthesis(m.decoder1, y1h_split_d, B, Hy, Wy, last_sse=(C.nchw(x1), sse[0:1]))
 
@@ -385,9 +418,12 @@ class HesicEngine(EngineBase):
             hs = m._h_s2
             cd = C.split(cond_buf)
             r3, r2 = C.ACT_RELU, C.ACT_LEAKY
-            _, s_d, _, _ = self._seq3(hs.gmm_sigma, (0, 2, 4), (r3, r3, r3), cd, B, Hy, Wy, "nhwc")
-            _, m_d, _, _ = self._seq3(hs.gmm_means, (0, 2, 4), (r2, r2, C.ACT_NONE), cd, B, Hy, Wy, "nhwc")
-            w2 = self._mixture_head(hs.gmm_weights, cd, B, Hy, Wy, K, M)
+            # the 128 -> 960 layers of the three branches are 1024 tasks for 74 CTA pairs (13.8 rounds): side by side, one
+            # branch's last partial round is filled by the next branch's first
+            (_, s_d, _, _), (_, m_d, _, _), w2 = self._branches(
+                lambda: self._seq3(hs.gmm_sigma, (0, 2, 4), (r3, r3, r3), cd, B, Hy, Wy, "nhwc"),
+                lambda: self._seq3(hs.gmm_means, (0, 2, 4), (r2, r2, C.ACT_NONE), cd, B, Hy, Wy, "nhwc"),
+                lambda: self._mixture_head(hs.gmm_weights, cd, B, Hy, Wy, K, M))
             y2_hat, y2_lik, y2h_split_d = self._gmm(m.gaussian2, y2_d, s_d, m_d, w2, B, Hy, Wy, M, K, a(1))
 
         # ---- view 2 synthesis ---------------------------------------------------------------
@@ -420,23 +456,32 @@ class HesicEngine(EngineBase):
         ctxp = getattr(m, f"context_prediction{view}")
         eb = getattr(m, f"entropy_bottleneck{view}")
         L = C.ACT_LEAKY
-        y_split = self._split(B, Hy, Wy, M)
-        self._convert(y_d, C.split(y_split))
-        z, z_d, Hz, Wz = self._seq3(h_a, (0, 2, 4), (L, L, C.ACT_NONE), C.split(y_split), B, Hy, Wy, "nhwc")
-        z_hat, zh_d, z_lik = self._bottleneck(eb, z, z_d, B, Hz, Wz, acc_z)
+        # cat(params, ctx_params) (newnet1_joint.py:687-688): the two halves come from independent chains -- the hyper path
+        # (h_a, bottleneck, h_s: six small layers) and the masked context model on round(y) -- which write disjoint channel
+        # slices of one buffer and run side by side (_branches)
+        buf = self._split(B, Hy, Wy, 4 * M) if view == 1 else cond_buf
+
+        def hyper():
+            y_split = self._split(B, Hy, Wy, M)
+            self._convert(y_d, C.split(y_split))
+            z, z_d, Hz, Wz = self._seq3(h_a, (0, 2, 4), (L, L, C.ACT_NONE), C.split(y_split), B, Hy, Wy, "nhwc")
+            z_hat, zh_d, z_lik = self._bottleneck(eb, z, z_d, B, Hz, Wz, acc_z)
+            self._seq3(h_s, (0, 2, 4), (L, L, C.ACT_NONE), zh_d, B, Hz, Wz, "split", last_dst=(buf, 0))
+            return z_lik
+
+        def context():
+            yh_d = C.split(self._split(B, Hy, Wy, M))
+            self._convert(y_d, yh_d, C.OP_ROUND)         # y_hat = round(y)  (:684-685)
+            y_hat = self._nchw(B, M, Hy, Wy)
+            self._convert(yh_d, C.nchw(y_hat))
+            self._run(ctxp, yh_d, B, Hy, Wy, "split", dst=(buf, 2 * M))
+            return y_hat, yh_d
+
+        z_lik, (y_hat, yh_d) = self._branches(hyper, context)
         if view == 1:
             self._z_liks = [z_lik, None]
-            buf = self._split(B, Hy, Wy, 4 * M)      # cat(params1, ctx_params1)  newnet1_joint.py:687-688
         else:
             self._z_liks[1] = z_lik
-            buf = cond_buf
-        self._seq3(h_s, (0, 2, 4), (L, L, C.ACT_NONE), zh_d, B, Hz, Wz, "split", last_dst=(buf, 0))
-        yh_split = self._split(B, Hy, Wy, M)
-        yh_d = C.split(yh_split)
-        self._convert(y_d, yh_d, C.OP_ROUND)         # y_hat = round(y)  (:684-685)
-        y_hat = self._nchw(B, M, Hy, Wy)
-        self._convert(yh_d, C.nchw(y_hat))
-        self._run(ctxp, yh_d, B, Hy, Wy, "split", dst=(buf, 2 * M))
         gp, gp_d, _, _ = self._seq3(ep, (0, 2, 4), (L, L, C.ACT_NONE), C.split(buf), B, Hy, Wy, "nhwc")
         scales_d = C.nhwc(gp, M, 0)
         means_d = C.nhwc(gp, M, M)
