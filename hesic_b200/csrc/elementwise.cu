@@ -254,7 +254,10 @@ constexpr int WRGB_STAGE = 1408;              // floats per warp (5.5 KB, a mult
 constexpr int WRGB_BW = 40, WRGB_BH = 11, WRGB_PLANE = WRGB_BW * WRGB_BH;
 static_assert(3 * WRGB_PLANE <= WRGB_STAGE, "warp window does not fit the warp's staging slice");
 
-__global__ void __launch_bounds__(32 * WRGB_WARPS) warp_rgb_kernel(const __grid_constant__ CUtensorMap map_src, const TView src,
+// r04: capped at 80 registers (3 blocks = 24 warps per SM; 98 registers and 2 blocks without the cap): the kernel is bound by the
+// latency of each warp's window load, which only other resident warps hide -- 54.5 -> 50.2 us; a cap of 64 (4 blocks, 60 bytes
+// of spills) 51.6 us.
+__global__ void __launch_bounds__(32 * WRGB_WARPS, 3) warp_rgb_kernel(const __grid_constant__ CUtensorMap map_src, const TView src,
                                                                    const float *__restrict__ Mx, const TView dst, const TView dst2,
                                                                    int align_corners) {
   __shared__ double T[9], S[12];
