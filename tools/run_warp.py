@@ -17,4 +17,4 @@ for i in range(reps + 1):
     e0.record(); F.warp_perspective(x1, h, (512, 512), True, out=out); e1.record(); torch.cuda.synchronize()
     if i: ts.append(e0.elapsed_time(e1))
 ms = sum(ts) / len(ts)
-print(f"warp rows={os.environ.get('HESIC_WARP_ROWS', '4')}: {ms * 1e3:.1f} us, {2 * x1.numel() * 4 / ms / 1e6:.0f} GB/s algorithmic, checksum {float(out.double().sum()):.6f}")
+print(f"warp_perspective {B} x 3 x 512 x 512: {ms * 1e3:.1f} us, {2 * x1.numel() * 4 / ms / 1e6:.0f} GB/s algorithmic, checksum {float(out.double().sum()):.6f}")
