@@ -150,11 +150,13 @@ class DsicEngine(HesicEngine):
 
     def capture(self, x1, x2):
         C.require_cuda(x1, x2)
+        self._streams_for_capture(x1.device)
         return CapturedForward(self, (x1, x2), self.forward)
 
     def _forward(self, x1, x2, B, H, W):
         m = self.m
         self.dev = dev = x1.device
+        self._work = B * H * W
         main = self._begin(dev)
         x1 = self._keep(x1.float().contiguous())
         x2 = self._keep(x2.float().contiguous())

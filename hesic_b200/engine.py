@@ -150,11 +150,19 @@ class HesicEngine(EngineBase):
         self._side = {}
         self.two_streams = True
         self.branch_streams = True     # independent branches of the hyper path side by side (_branches)
+        self._work = 1 << 30           # pixels per forward (B * H * W), set by _forward
 
     def _side_stream(self, dev):
         s = self._side.get(dev)
         if s is None:
             s = self._side[dev] = torch.cuda.Stream(device=dev)
+        return s
+
+    def _aux_stream(self, dev, i):
+        key = (dev, i)
+        s = self._side.get(key)
+        if s is None:
+            s = self._side[key] = torch.cuda.Stream(device=dev)
         return s
 
     def _branches(self, *fns):
@@ -166,17 +174,18 @@ class HesicEngine(EngineBase):
         r04 in bursts from an idle GPU (tools/time_forward.py, 16 pairs): HESIC 6.18 -> 6.04 ms, HESIC+ 5.34 -> 5.26 ms; in a
         loop that has reached the 1 kW power cap the governor's clock, not the schedule, sets the time."""
         cur = torch.cuda.current_stream(self.dev)
-        if not self.branch_streams or len(fns) < 2:
+        # a small eager forward is bound by the host issuing its ~60 launches (one 512 x 512 pair: 1.6 ms of Python for 0.9-1.3 ms
+        # of GPU work), where the forks' events only add host time (2.0 ms); under graph capture, or from a few pairs up, the GPU
+        # is the bound and the overlap pays
+        small = self._work < 4 * 512 * 512 and not torch.cuda.is_current_stream_capturing()
+        if not self.branch_streams or small or len(fns) < 2:
             return [f() for f in fns]
         res = [None] * len(fns)
         fork = torch.cuda.Event()
         fork.record(cur)
         ends = []
         for i in range(1, len(fns)):
-            key = (self.dev, i)
-            aux = self._side.get(key)
-            if aux is None:
-                aux = self._side[key] = torch.cuda.Stream(device=self.dev)
+            aux = self._aux_stream(self.dev, i)
             aux.wait_event(fork)
             with torch.cuda.stream(aux):
                 res[i] = fns[i]()
@@ -315,11 +324,19 @@ class HesicEngine(EngineBase):
     def capture(self, x1, x2, h):
         """Freeze one forward for these input shapes into a CUDA graph (see ``CapturedForward``)."""
         C.require_cuda(x1, x2, h)
+        self._streams_for_capture(x1.device)
         return CapturedForward(self, (x1, x2, h), self.forward)
+
+    def _streams_for_capture(self, dev):
+        """Every stream a forward may fork onto exists before the capture starts (a small eager warm-up does not fork)."""
+        self._side_stream(dev)
+        for i in (1, 2):
+            self._aux_stream(dev, i)
 
     def _forward(self, x1, x2, h, B, H, W):
         m = self.m
         self.dev = dev = x1.device
+        self._work = B * H * W
         main = self._begin(dev)
         x1 = self._keep(x1.float().contiguous())
         x2 = self._keep(x2.float().contiguous())
