@@ -218,6 +218,17 @@ def test_no_cpu_fallback():
         net.train()(x, x, torch.eye(3)[None])
 
 
+def test_conv_forward_sse_rejects_bad_arguments_before_any_launch():
+    """hesic_conv_forward_sse (the reconstruction layers + the MSE partial of RateDistortionLoss, test3real.py:99-111): null
+    arguments and a target that is not the output's shape are HESIC_E_INVALID (ValueError on the Python side) before anything
+    touches the device -- checked here without a GPU."""
+    from hesic_b200 import _capi as C
+    rc = C.lib.hesic_conv_forward_sse(None, None, None, None, 0, 0, None, None, None)
+    assert rc == -1 and "null argument" in C.last_error()
+    with pytest.raises(ValueError):
+        C.check(rc)
+
+
 def test_gdn_init_and_masks():
     """Closed-form pins of the reference's tests/test_layers.py: parameters at init, mask patterns."""
     from compressai.layers import GDN, MaskedConv2d
